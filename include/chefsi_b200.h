@@ -1,0 +1,165 @@
+/*
+ * chefsi_b200.h -- C ABI of libchefsi_b200.so
+ *
+ * B200-native (sm_100a CUDA, FP64) implementation of ONE hot path of SPARC: the
+ * Chebyshev-filtered subspace iteration (CheFSI) filter, i.e. the repeated
+ * (H - cI) * X product fused with the three-term Chebyshev recurrence.
+ *
+ * Everything here is plain C: pointers, sizes, POD structs.  No CUDA, torch or
+ * MPI types cross this boundary.  The reference-side binding (the functions
+ * SPARC itself calls) lives in sparc_b200/csrc/sparc_shim.c, which flattens
+ * SPARC_OBJ into the structs below; see INTEGRATION.md.
+ *
+ * Reference interfaces replaced (paths relative to the SPARC tree):
+ *   chefsi_chebyshev_filter        <- ChebyshevFiltering            src/eigenSolver.c:722-798
+ *                                     (decl. src/include/eigenSolver.h:93-97)
+ *   chefsi_chebyshev_filter_kpt    <- ChebyshevFiltering_kpt        src/eigenSolverKpt.c:458-535
+ *                                     (decl. src/include/eigenSolverKpt.h:41-45)
+ *   chefsi_hamiltonian_mult        <- Hamiltonian_vectors_mult      src/hamiltonianVecRoutines.c:45-121
+ *   chefsi_hamiltonian_mult_kpt    <- Hamiltonian_vectors_mult_kpt  src/hamiltonianVecRoutines.c:132-242
+ *                                     (decl. src/include/hamiltonianVecRoutines.h:30-47)
+ *   chefsi_set_grid                <- the SPARC_OBJ fields read by Lap_plus_diag_vec_mult_{orth,nonorth}[_kpt]
+ *                                     (src/lapVecRoutines.c:306,940; src/lapVecRoutinesKpt.c:179,567)
+ *   chefsi_set_projectors          <- ATOM_NLOC_INFLUENCE_OBJ / NLOC_PROJ_OBJ / PSD_OBJ.Gamma / IP_displ
+ *                                     as read by Vnl_vec_mult[_kpt] (src/nlocVecRoutines.c:798,889)
+ *   chefsi_set_veff                <- Veff_loc argument / Transfer_Veff_loc (src/electronicGroundState.c:1313)
+ *
+ * Conventions
+ *   - Grid functions are stored x-fastest: index = k*Nx*Ny + j*Nx + i (lapVecRoutines.c:313).
+ *   - A block of orbitals is column-major: column n starts at ptr + n*ld (ld >= Nd).
+ *   - Complex data is interleaved (re,im) doubles, identical to C99 `double _Complex`.
+ *   - All functions return 0 on success, non-zero on failure; chefsi_last_error() then
+ *     returns a message.  There is NO CPU fallback: if no CUDA device is usable the
+ *     call fails.
+ *   - A context is bound to one CUDA device and is not thread-safe (the reference calls
+ *     the path from its single MPI-rank thread).
+ */
+#ifndef CHEFSI_B200_H
+#define CHEFSI_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHEFSI_MAX_FDN 12 /* FD_ORDER <= 24 */
+
+/* Discretisation of one (unsplit) domain.  Field meaning and provenance:
+ * src/include/isddft.h:391 (cell_typ), :396-398 (Nx..), :401-403 (range_*), :411 (dV),
+ * :464 (order), :467-481 (stencil coefficient tables), :667-669 (BC*).
+ * Coefficient tables are the values SPARC computed in src/initialization.c:2112-2178;
+ * this library never recomputes them. */
+typedef struct chefsi_grid {
+    int Nx, Ny, Nz;
+    int BCx, BCy, BCz; /* 0 periodic, 1 Dirichlet (zero halo) */
+    int FDn;           /* order / 2 */
+    int cell_typ;      /* 0 orthogonal; 11..17 non-orthogonal flavours */
+    double dV;
+    double range_x, range_y, range_z; /* cell lengths, used for Bloch phases */
+    double D2_x[CHEFSI_MAX_FDN + 1], D2_y[CHEFSI_MAX_FDN + 1], D2_z[CHEFSI_MAX_FDN + 1];
+    double D2_xy[CHEFSI_MAX_FDN + 1], D2_xz[CHEFSI_MAX_FDN + 1], D2_yz[CHEFSI_MAX_FDN + 1];
+    double D1_x[CHEFSI_MAX_FDN + 1], D1_y[CHEFSI_MAX_FDN + 1], D1_z[CHEFSI_MAX_FDN + 1];
+    double D1_xy[CHEFSI_MAX_FDN + 1], D1_yx[CHEFSI_MAX_FDN + 1];
+    double D1_xz[CHEFSI_MAX_FDN + 1], D1_zx[CHEFSI_MAX_FDN + 1];
+    double D1_yz[CHEFSI_MAX_FDN + 1], D1_zy[CHEFSI_MAX_FDN + 1];
+} chefsi_grid_t;
+
+/* Kleinman-Bylander nonlocal projectors, flattened over atom types.
+ * "image" = one entry of Atom_Influence_nloc[ityp] (an atom or one of its periodic
+ * images whose rc-sphere touches the domain), in the order ityp-major, iat-minor
+ * (the loop order of nlocVecRoutines.c:807-831). */
+typedef struct chefsi_nloc {
+    int n_atom;             /* real atoms; alpha has IP_displ[n_atom] rows per column   */
+    const int *IP_displ;    /* [n_atom+1]   isddft.h:460, nlocVecRoutines.c:769-791     */
+    const double *gamma;    /* [IP_displ[n_atom]]  PSD_OBJ.Gamma expanded to one value   */
+                            /* per (atom, projector) in alpha order (nlocVecRoutines.c:841-863) */
+    int n_img;
+    const int *img_atom;    /* [n_img]   atom_index  (isddft.h:206)                      */
+    const int *img_ndc;     /* [n_img]   grid points in the rc-sphere (isddft.h:213)     */
+    const double *img_coords; /* [3*n_img] image coordinates (isddft.h:205); only used   */
+                            /* for the k-point Bloch factor (nlocVecRoutines.c:911-921)  */
+    const long long *pos_off; /* [n_img+1] offsets into grid_pos                         */
+    const long long *chi_off; /* [n_img+1] offsets into chi                              */
+    const int *grid_pos;    /* linear grid indices of each sphere (isddft.h:214)         */
+    const double *chi;      /* per image: ndc x nproj, column-major, real values         */
+                            /* (NLOC_PROJ_OBJ.Chi, or creal(Chi_c): nlocVecRoutines.c:731) */
+} chefsi_nloc_t;
+
+typedef struct chefsi_ctx chefsi_ctx_t;
+
+/* flags for the filter entry points */
+#define CHEFSI_FLAG_NO_X_COPYBACK 1 /* host entry points: do not copy the clobbered X back   */
+                                    /* (the caller reuses X as scratch, eigenSolver.c:364)   */
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+int chefsi_create(chefsi_ctx_t **ctx, int device);
+void chefsi_destroy(chefsi_ctx_t *ctx);
+const char *chefsi_last_error(const chefsi_ctx_t *ctx);
+const char *chefsi_version(void);
+
+/* ---- problem description (host pointers; copied to the device) ---------------------- */
+int chefsi_set_grid(chefsi_ctx_t *ctx, const chefsi_grid_t *grid);
+int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nloc); /* NULL: no Vnl */
+int chefsi_set_veff(chefsi_ctx_t *ctx, const double *veff_host);        /* Nd doubles   */
+int chefsi_set_kpoint(chefsi_ctx_t *ctx, double k1, double k2, double k3);
+
+/* ---- host-buffer entry points: what the reference's functions bind to ---------------
+ * X is in/out (ends as p_{m-1}(H) X0, as in the reference), Y is out (p_m(H) X0).
+ * a = lambda_cutoff, b = eigmax, a0 = eigmin (eigenSolver.c:729).                       */
+int chefsi_chebyshev_filter(chefsi_ctx_t *ctx, double *X, size_t ldi, double *Y, size_t ldo,
+                            int ncol, int m, double a, double b, double a0, int flags);
+int chefsi_chebyshev_filter_kpt(chefsi_ctx_t *ctx, void *X, size_t ldi, void *Y, size_t ldo,
+                                int ncol, int m, double a, double b, double a0, int flags);
+/* Hx = (-1/2 Lap + Veff + c) x + Vnl x */
+int chefsi_hamiltonian_mult(chefsi_ctx_t *ctx, int ncol, double c, const double *x, size_t ldi,
+                            double *Hx, size_t ldo);
+int chefsi_hamiltonian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double c, const void *x,
+                                size_t ldi, void *Hx, size_t ldo);
+
+/* ---- device-resident entry points ---------------------------------------------------
+ * Buffers are device pointers holding ncol columns with leading dimension
+ * chefsi_device_ld(ctx) elements (doubles, or complex pairs for the _kpt variants).
+ * The three buffers rotate through the recurrence; on return *y_slot / *x_slot say
+ * which of {0:bufA, 1:bufB, 2:bufC} hold Y = p_m(H)X0 and X = p_{m-1}(H)X0.
+ * bufA holds X0 on entry.  All work is enqueued on the context's stream and the call
+ * returns after enqueueing (use chefsi_synchronize).                                    */
+size_t chefsi_device_ld(const chefsi_ctx_t *ctx);
+int chefsi_chebyshev_filter_device(chefsi_ctx_t *ctx, double *bufA, double *bufB, double *bufC,
+                                   int ncol, int m, double a, double b, double a0,
+                                   int *y_slot, int *x_slot);
+int chefsi_chebyshev_filter_kpt_device(chefsi_ctx_t *ctx, void *bufA, void *bufB, void *bufC,
+                                       int ncol, int m, double a, double b, double a0,
+                                       int *y_slot, int *x_slot);
+int chefsi_hamiltonian_mult_device(chefsi_ctx_t *ctx, int ncol, double c, const double *x,
+                                   double *Hx);
+int chefsi_hamiltonian_mult_kpt_device(chefsi_ctx_t *ctx, int ncol, double c, const void *x,
+                                       void *Hx);
+int chefsi_synchronize(chefsi_ctx_t *ctx);
+
+/* Fill ncol device columns with the synthetic start vectors of SURVEY.md section 8(d):
+ * U(-0.5,0.5) from a counter-based generator keyed on (seed, global column, grid index),
+ * so any column block is reproducible on CPU and GPU (mirrors Init_orbital,
+ * src/orbitalElecDensInit.c:388-392).  is_complex != 0 fills (re,im) pairs.            */
+int chefsi_fill_random_device(chefsi_ctx_t *ctx, void *buf, int ncol, long long first_col,
+                              unsigned long long seed, int is_complex);
+
+/* ---- introspection (timing, counters) ------------------------------------------------ */
+typedef struct chefsi_stats {
+    unsigned long long kernel_launches; /* kernels of this library launched so far         */
+    double last_filter_ms;              /* device time of the last filter call (events)    */
+    double last_stencil_ms;             /* summed device time of its stencil-step kernels  */
+    double last_nloc_ms;                /* summed device time of its projector kernels     */
+    int last_stencil_launches;
+    int last_path;                      /* 0 = general kernel, 1 = streaming orth kernel   */
+} chefsi_stats_t;
+int chefsi_get_stats(const chefsi_ctx_t *ctx, chefsi_stats_t *out);
+/* when on, every kernel of a filter call is bracketed by CUDA events (adds host
+ * overhead; used by bench.py's roofline leg, off by default) */
+int chefsi_set_profiling(chefsi_ctx_t *ctx, int on);
+void *chefsi_stream(chefsi_ctx_t *ctx); /* cudaStream_t the context launches on */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHEFSI_B200_H */
