@@ -1,0 +1,86 @@
+"""ctypes binding of ``libchefsi_b200.so`` (the C ABI in ``include/chefsi_b200.h``).
+
+This is the product path: it loads the hand-written sm_100a CUDA library that lives in-tree
+next to this file and fails loudly if it is missing or if no B200 is visible.  There is no CPU
+fallback and nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libchefsi_b200.so")
+
+# every symbol include/chefsi_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = (
+    "chefsi_create", "chefsi_destroy", "chefsi_last_error", "chefsi_version",
+    "chefsi_set_grid", "chefsi_set_projectors", "chefsi_set_veff", "chefsi_set_kpoint",
+    "chefsi_chebyshev_filter", "chefsi_chebyshev_filter_kpt",
+    "chefsi_hamiltonian_mult", "chefsi_hamiltonian_mult_kpt",
+    "chefsi_device_ld",
+    "chefsi_chebyshev_filter_device", "chefsi_chebyshev_filter_kpt_device",
+    "chefsi_hamiltonian_mult_device", "chefsi_hamiltonian_mult_kpt_device",
+    "chefsi_synchronize", "chefsi_fill_random_device",
+    "chefsi_get_stats", "chefsi_set_profiling", "chefsi_stream",
+)
+
+
+class ChefsiStats(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_ulonglong),
+        ("last_filter_ms", C.c_double),
+        ("last_stencil_ms", C.c_double),
+        ("last_nloc_ms", C.c_double),
+        ("last_stencil_launches", C.c_int),
+        ("last_path", C.c_int),
+    ]
+
+
+class ChefsiError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA library; raise (never fall back) if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ChefsiError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, dp, sz, i, d = C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double
+    ip = C.POINTER(C.c_int)
+    lib.chefsi_create.argtypes = [C.POINTER(vp), i]
+    lib.chefsi_destroy.argtypes = [vp]
+    lib.chefsi_destroy.restype = None
+    lib.chefsi_last_error.argtypes = [vp]
+    lib.chefsi_last_error.restype = C.c_char_p
+    lib.chefsi_version.restype = C.c_char_p
+    lib.chefsi_set_grid.argtypes = [vp, vp]
+    lib.chefsi_set_projectors.argtypes = [vp, vp]
+    lib.chefsi_set_veff.argtypes = [vp, dp]
+    lib.chefsi_set_kpoint.argtypes = [vp, d, d, d]
+    for name in ("chefsi_chebyshev_filter", "chefsi_chebyshev_filter_kpt"):
+        getattr(lib, name).argtypes = [vp, dp, sz, dp, sz, i, i, d, d, d, i]
+    for name in ("chefsi_hamiltonian_mult", "chefsi_hamiltonian_mult_kpt"):
+        getattr(lib, name).argtypes = [vp, i, d, dp, sz, dp, sz]
+    lib.chefsi_device_ld.argtypes = [vp]
+    lib.chefsi_device_ld.restype = sz
+    for name in ("chefsi_chebyshev_filter_device", "chefsi_chebyshev_filter_kpt_device"):
+        getattr(lib, name).argtypes = [vp, dp, dp, dp, i, i, d, d, d, ip, ip]
+    for name in ("chefsi_hamiltonian_mult_device", "chefsi_hamiltonian_mult_kpt_device"):
+        getattr(lib, name).argtypes = [vp, i, d, dp, dp]
+    lib.chefsi_synchronize.argtypes = [vp]
+    lib.chefsi_fill_random_device.argtypes = [vp, dp, i, C.c_longlong, C.c_ulonglong, i]
+    lib.chefsi_get_stats.argtypes = [vp, C.POINTER(ChefsiStats)]
+    lib.chefsi_set_profiling.argtypes = [vp, i]
+    lib.chefsi_stream.argtypes = [vp]
+    lib.chefsi_stream.restype = vp
+    _lib = lib
+    return lib

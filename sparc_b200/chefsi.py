@@ -1,0 +1,154 @@
+"""Host-side mirror of the reference's operator interface for the CheFSI filter path.
+
+The method names, argument meaning and in/out behaviour follow the reference functions they
+stand in for, so the parity tests read like calls into SPARC:
+
+    ChebyshevFiltering        src/eigenSolver.c:722     (X in/out -> p_{m-1}(H)X0, Y out -> p_m(H)X0)
+    ChebyshevFiltering_kpt    src/eigenSolverKpt.c:458
+    Hamiltonian_vectors_mult  src/hamiltonianVecRoutines.c:45    Hx = (-1/2 Lap + Veff + c) x + Vnl x
+    Hamiltonian_vectors_mult_kpt                          :132
+
+Blocks of orbitals are arrays of shape ``(ncol, ld)`` (column n at ``n*ld``: the reference's
+column-major layout).  numpy arrays, pinned torch CPU tensors (host entry points) and torch CUDA
+tensors / raw device addresses (``*_device`` entry points) are accepted; torch is only plumbing
+for memory, the arithmetic is all inside ``libchefsi_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .problem import Grid, Projectors
+
+
+def _addr(obj) -> int:
+    if obj is None:
+        return 0
+    if isinstance(obj, int):
+        return obj
+    if isinstance(obj, np.ndarray):
+        if not obj.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return obj.ctypes.data
+    if hasattr(obj, "data_ptr"):  # torch tensor
+        if not obj.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return obj.data_ptr()
+    raise TypeError(f"cannot take the address of {type(obj)}")
+
+
+def _is_complex(obj) -> bool:
+    if isinstance(obj, np.ndarray):
+        return np.iscomplexobj(obj)
+    if hasattr(obj, "is_complex"):
+        return bool(obj.is_complex())
+    raise TypeError("need an array to infer real/complex")
+
+
+class ChefsiContext:
+    """One CUDA device's instance of the filter path (``chefsi_ctx_t``)."""
+
+    FLAG_NO_X_COPYBACK = 1
+
+    def __init__(self, device: int = 0):
+        self._lib = capi.load_library()
+        h = C.c_void_p()
+        if self._lib.chefsi_create(C.byref(h), int(device)) != 0:
+            raise capi.ChefsiError(self._lib.chefsi_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self.grid = None
+        self._keep = []
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.chefsi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise capi.ChefsiError(self._lib.chefsi_last_error(self._h).decode())
+
+    # -- problem description ------------------------------------------------------------------
+    def set_grid(self, grid: Grid):
+        g = grid.to_c()
+        self._check(self._lib.chefsi_set_grid(self._h, C.byref(g)))
+        self.grid = grid
+
+    def set_projectors(self, proj: Projectors | None):
+        if proj is None:
+            self._check(self._lib.chefsi_set_projectors(self._h, None))
+            return
+        s = proj.to_c()
+        self._check(self._lib.chefsi_set_projectors(self._h, C.byref(s)))
+
+    def set_veff(self, veff):
+        if veff is not None:
+            veff = np.ascontiguousarray(veff, dtype=np.float64)
+            assert veff.size == self.grid.Nd
+        self._check(self._lib.chefsi_set_veff(self._h, _addr(veff)))
+
+    def set_kpoint(self, k):
+        self._check(self._lib.chefsi_set_kpoint(self._h, float(k[0]), float(k[1]), float(k[2])))
+
+    @property
+    def device_ld(self) -> int:
+        return int(self._lib.chefsi_device_ld(self._h))
+
+    # -- reference-named host entry points ------------------------------------------------------
+    def ChebyshevFiltering(self, X, Y, m, a, b, a0, copy_back_x=True):
+        """X, Y: real arrays (ncol, ld).  X is overwritten with p_{m-1}(H)X0, Y with p_m(H)X0."""
+        ncol, ldi = X.shape
+        flags = 0 if copy_back_x else self.FLAG_NO_X_COPYBACK
+        fn = self._lib.chefsi_chebyshev_filter_kpt if _is_complex(X) else self._lib.chefsi_chebyshev_filter
+        self._check(fn(self._h, _addr(X), ldi, _addr(Y), Y.shape[1], ncol, int(m), float(a), float(b), float(a0), flags))
+
+    ChebyshevFiltering_kpt = ChebyshevFiltering
+
+    def Hamiltonian_vectors_mult(self, c, x, Hx):
+        ncol, ldi = x.shape
+        fn = self._lib.chefsi_hamiltonian_mult_kpt if _is_complex(x) else self._lib.chefsi_hamiltonian_mult
+        self._check(fn(self._h, ncol, float(c), _addr(x), ldi, _addr(Hx), Hx.shape[1]))
+
+    Hamiltonian_vectors_mult_kpt = Hamiltonian_vectors_mult
+
+    # -- device-resident entry points -------------------------------------------------------------
+    def filter_device(self, bufA, bufB, bufC, ncol, m, a, b, a0, is_complex=False):
+        """Enqueue one filter on device buffers; returns (y_slot, x_slot) in {0,1,2}."""
+        ys, xs = C.c_int(-1), C.c_int(-1)
+        fn = self._lib.chefsi_chebyshev_filter_kpt_device if is_complex else self._lib.chefsi_chebyshev_filter_device
+        self._check(fn(self._h, _addr(bufA), _addr(bufB), _addr(bufC), int(ncol), int(m), float(a), float(b),
+                       float(a0), C.byref(ys), C.byref(xs)))
+        return ys.value, xs.value
+
+    def hamiltonian_device(self, ncol, c, x, Hx, is_complex=False):
+        fn = self._lib.chefsi_hamiltonian_mult_kpt_device if is_complex else self._lib.chefsi_hamiltonian_mult_device
+        self._check(fn(self._h, int(ncol), float(c), _addr(x), _addr(Hx)))
+
+    def fill_random_device(self, buf, ncol, first_col=0, seed=1, is_complex=False):
+        self._check(self._lib.chefsi_fill_random_device(self._h, _addr(buf), int(ncol), int(first_col), int(seed),
+                                                        int(bool(is_complex))))
+
+    def synchronize(self):
+        self._check(self._lib.chefsi_synchronize(self._h))
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.chefsi_set_profiling(self._h, int(bool(on))))
+
+    def stats(self) -> dict:
+        s = capi.ChefsiStats()
+        self._check(self._lib.chefsi_get_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.chefsi_stream(self._h) or 0)

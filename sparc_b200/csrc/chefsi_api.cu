@@ -1,0 +1,573 @@
+/*
+ * chefsi_api.cu -- the C ABI of libchefsi_b200.so (include/chefsi_b200.h) and the host-side
+ * orchestration of the Chebyshev filter.
+ *
+ * ChebyshevFiltering (eigenSolver.c:722-798) in this library is:
+ *     e=(b-a)/2, c=(b+a)/2, sigma=sigma1=e/(a0-c), gamma=2/sigma1                      (:747-750)
+ *     Y    = (sigma1/e) (H - c) X                                                      (:755-768)
+ *     for j = 1..m-1: sigma2 = 1/(gamma-sigma)
+ *                     Ynew = (2 sigma2/e)(H - c) Y - (sigma sigma2) X ; X<-Y ; Y<-Ynew  (:772-796)
+ * where every "(H - c) .  scaled, minus xprev" is ONE fused stencil launch plus the nonlocal
+ * projector launches, and X<-Y<-Ynew is a rotation of three device buffers (no copies).
+ */
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "chefsi_internal.h"
+
+/* ------------------------------------------------------------------------------------------ */
+int chefsi_fail(chefsi_ctx *ctx, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) {
+        strncpy(ctx->err, buf, sizeof(ctx->err) - 1);
+        ctx->err[sizeof(ctx->err) - 1] = 0;
+    }
+    if (getenv("CHEFSI_B200_VERBOSE")) fprintf(stderr, "[chefsi_b200] error: %s\n", buf);
+    return 1;
+}
+
+static char g_create_err[512] = "";
+
+extern "C" const char *chefsi_version(void) { return "chefsi_b200 0.1 (sm_100a, FP64)"; }
+
+extern "C" const char *chefsi_last_error(const chefsi_ctx_t *ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
+{
+    if (!out) return 1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "no CUDA device available (%s); this library has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return 1;
+    }
+    if (device < 0 || device >= ndev) {
+        snprintf(g_create_err, sizeof(g_create_err), "device %d out of range (0..%d)", device, ndev - 1);
+        return 1;
+    }
+    chefsi_ctx *ctx = new (std::nothrow) chefsi_ctx();
+    if (!ctx) return 1;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        snprintf(g_create_err, sizeof(g_create_err), "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+        delete ctx;
+        return 1;
+    }
+    if (prop.major != 10) {
+        snprintf(g_create_err, sizeof(g_create_err), "device %d is sm_%d%d; this library is built for sm_100a only",
+                 device, prop.major, prop.minor);
+        delete ctx;
+        return 1;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
+    cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
+    ctx->force_general = getenv("CHEFSI_B200_FORCE_GENERAL") ? atoi(getenv("CHEFSI_B200_FORCE_GENERAL")) : 0;
+    *out = ctx;
+    return 0;
+}
+
+static void free_nloc(NlocDev &d)
+{
+    cudaFree(d.IP_displ); cudaFree(d.gamma); cudaFree(d.img_atom); cudaFree(d.img_ndc);
+    cudaFree(d.pos_off); cudaFree(d.chi_off); cudaFree(d.grid_pos); cudaFree(d.chi);
+    cudaFree(d.img_phase); cudaFree(d.atom_img_off); cudaFree(d.atom_img);
+    free(d.h_img_coords);
+    d = NlocDev();
+}
+
+extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_nloc(ctx->nl);
+    cudaFree(ctx->d_veff);
+    for (int i = 0; i < 3; i++) cudaFree(ctx->d_buf[i]);
+    cudaFree(ctx->d_alpha);
+    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    delete ctx;
+}
+
+/* ---- grid ---------------------------------------------------------------------------------- */
+static void update_phases(chefsi_ctx *ctx)
+{
+    const chefsi_grid_t &g = ctx->grid;
+    for (int oz = -1; oz <= 1; oz++)
+        for (int oy = -1; oy <= 1; oy++)
+            for (int ox = -1; ox <= 1; ox++) {
+                /* exp(i k.(ox Lx, oy Ly, oz Lz)), lapVecRoutinesKpt.c:370-382,647-660 */
+                const double th = ctx->kvec[0] * (ox * g.range_x) + ctx->kvec[1] * (oy * g.range_y) +
+                                  ctx->kvec[2] * (oz * g.range_z);
+                const int q = (oz + 1) * 9 + (oy + 1) * 3 + (ox + 1);
+                ctx->desc.ph_re[q] = cos(th);
+                ctx->desc.ph_im[q] = sin(th);
+            }
+}
+
+static int update_nloc_phases(chefsi_ctx *ctx)
+{
+    NlocDev &d = ctx->nl;
+    if (d.n_img == 0) return 0;
+    const chefsi_grid_t &g = ctx->grid;
+    std::vector<double2> ph(d.n_img);
+    for (int J = 0; J < d.n_img; J++) {
+        /* nlocVecRoutines.c:911-921 */
+        const double *co = d.h_img_coords + 3 * J;
+        const double th = -ctx->kvec[0] * (floor(co[0] / g.range_x) * g.range_x) -
+                          ctx->kvec[1] * (floor(co[1] / g.range_y) * g.range_y) -
+                          ctx->kvec[2] * (floor(co[2] / g.range_z) * g.range_z);
+        ph[J] = make_double2(cos(th), sin(th));
+    }
+    CHEFSI_CUDA(ctx, cudaMemcpyAsync(d.img_phase, ph.data(), sizeof(double2) * d.n_img, cudaMemcpyHostToDevice, ctx->stream));
+    CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int chefsi_set_grid(chefsi_ctx_t *ctx, const chefsi_grid_t *g)
+{
+    if (!ctx || !g) return 1;
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (g->FDn < 1 || g->FDn > CHEFSI_MAX_FDN) return chefsi_fail(ctx, "FDn %d out of range", g->FDn);
+    if (!(g->cell_typ == 0 || (g->cell_typ >= 11 && g->cell_typ <= 17)))
+        return chefsi_fail(ctx, "cell_typ %d not supported (0, 11..17)", g->cell_typ);
+    if (g->Nx < 1 || g->Ny < 1 || g->Nz < 1) return chefsi_fail(ctx, "bad grid size");
+    const int per[3] = {!g->BCx, !g->BCy, !g->BCz}, N[3] = {g->Nx, g->Ny, g->Nz};
+    for (int d = 0; d < 3; d++)
+        if (per[d] && N[d] < g->FDn) return chefsi_fail(ctx, "periodic axis %d has fewer points than the FD radius", d);
+    ctx->grid = *g;
+    ctx->Nd = (size_t)g->Nx * g->Ny * g->Nz;
+    ctx->ld = (ctx->Nd + 15) / 16 * 16;
+
+    StencilDesc &d = ctx->desc;
+    memset(&d, 0, sizeof(d));
+    d.Nx = g->Nx; d.Ny = g->Ny; d.Nz = g->Nz;
+    d.bc[0] = g->BCx; d.bc[1] = g->BCy; d.bc[2] = g->BCz;
+    d.F = g->FDn;
+    const double a = -0.5; /* hamiltonianVecRoutines.c:63-83 */
+    d.coef0 = (g->D2_x[0] + g->D2_y[0] + g->D2_z[0]) * a;
+    for (int r = 0; r <= g->FDn; r++) {
+        d.wx[r] = g->D2_x[r] * a;
+        d.wy[r] = g->D2_y[r] * a;
+        d.wz[r] = g->D2_z[r] * a;
+    }
+    /* the reference's two-stage mixed-derivative composition, lapVecRoutines.c:1210-1297 and the
+       compact weight table :1337-1423 */
+    auto set_mix = [&](int q, int ext, int ax1, const double *c1, int ax2, const double *c2, const double *wm) {
+        MixedComp &m = d.mix[q];
+        m.ext = ext; m.ax1 = ax1; m.ax2 = ax2;
+        for (int r = 0; r <= g->FDn; r++) {
+            m.c1[r] = c1[r];
+            m.c2[r] = c2 ? c2[r] : 0.0;
+            m.wm[r] = wm[r] * a;
+        }
+    };
+    switch (g->cell_typ) {
+    case 0: d.nmix = 0; break;
+    case 11: d.nmix = 1; set_mix(0, 0, 1, g->D1_y, -1, nullptr, g->D2_xy); break;
+    case 12: d.nmix = 1; set_mix(0, 0, 2, g->D1_z, -1, nullptr, g->D2_xz); break;
+    case 13: d.nmix = 1; set_mix(0, 1, 2, g->D1_z, -1, nullptr, g->D2_yz); break;
+    case 14: d.nmix = 1; set_mix(0, 0, 1, g->D1_xy, 2, g->D1_xz, g->D1_x); break;
+    case 15: d.nmix = 1; set_mix(0, 2, 0, g->D1_zx, 1, g->D1_zy, g->D1_z); break;
+    case 16: d.nmix = 1; set_mix(0, 1, 0, g->D1_yx, 2, g->D1_yz, g->D1_y); break;
+    case 17:
+        d.nmix = 2;
+        set_mix(0, 0, 1, g->D1_xy, 2, g->D1_xz, g->D1_x);
+        set_mix(1, 1, 2, g->D1_z, -1, nullptr, g->D2_yz);
+        break;
+    }
+    update_phases(ctx);
+
+    /* Veff buffer (+ a zero page behind it used as the source of Dirichlet halos) */
+    cudaFree(ctx->d_veff);
+    ctx->d_veff = nullptr;
+    const size_t nv = ctx->ld + 4096;
+    CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_veff, nv * sizeof(double)));
+    CHEFSI_CUDA(ctx, cudaMemsetAsync(ctx->d_veff, 0, nv * sizeof(double), ctx->stream));
+    CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_veff = false;
+    ctx->have_grid = true;
+    /* projector tables refer to grid indices: drop them */
+    free_nloc(ctx->nl);
+    return 0;
+}
+
+extern "C" int chefsi_set_kpoint(chefsi_ctx_t *ctx, double k1, double k2, double k3)
+{
+    if (!ctx) return 1;
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->kvec[0] = k1; ctx->kvec[1] = k2; ctx->kvec[2] = k3;
+    update_phases(ctx);
+    return update_nloc_phases(ctx);
+}
+
+extern "C" int chefsi_set_veff(chefsi_ctx_t *ctx, const double *veff_host)
+{
+    if (!ctx) return 1;
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!veff_host) { ctx->have_veff = false; return 0; }
+    CHEFSI_CUDA(ctx, cudaMemcpyAsync(ctx->d_veff, veff_host, ctx->Nd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_veff = true;
+    return 0;
+}
+
+/* ---- projectors ------------------------------------------------------------------------------ */
+template <typename T>
+static int upload(chefsi_ctx *ctx, T **dst, const T *src, size_t n)
+{
+    *dst = nullptr;
+    CHEFSI_CUDA(ctx, cudaMalloc((void **)dst, (n ? n : 1) * sizeof(T)));
+    if (n) CHEFSI_CUDA(ctx, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
+{
+    if (!ctx) return 1;
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    free_nloc(ctx->nl);
+    if (!nl || nl->n_img == 0 || nl->n_atom == 0) return 0;
+    NlocDev &d = ctx->nl;
+    d.n_atom = nl->n_atom;
+    d.n_img = nl->n_img;
+    d.ntot = nl->IP_displ[nl->n_atom];
+    d.max_nproj = 0;
+    for (int a = 0; a < nl->n_atom; a++) {
+        const int np = nl->IP_displ[a + 1] - nl->IP_displ[a];
+        if (np > d.max_nproj) d.max_nproj = np;
+    }
+    const long long npos = nl->pos_off[nl->n_img], nchi = nl->chi_off[nl->n_img];
+    d.total_pts = npos;
+    /* validate + overlap detection (decides whether the scatter needs atomics) */
+    std::vector<unsigned char> seen(ctx->Nd, 0);
+    d.overlap = 0;
+    for (int J = 0; J < nl->n_img; J++) {
+        if (nl->img_atom[J] < 0 || nl->img_atom[J] >= nl->n_atom) return chefsi_fail(ctx, "projectors: bad atom index");
+        if (nl->pos_off[J + 1] - nl->pos_off[J] != nl->img_ndc[J]) return chefsi_fail(ctx, "projectors: pos_off/ndc mismatch");
+        const int np = nl->IP_displ[nl->img_atom[J] + 1] - nl->IP_displ[nl->img_atom[J]];
+        if (nl->chi_off[J + 1] - nl->chi_off[J] != (long long)nl->img_ndc[J] * np)
+            return chefsi_fail(ctx, "projectors: chi_off mismatch");
+        for (long long i = nl->pos_off[J]; i < nl->pos_off[J + 1]; i++) {
+            const int p = nl->grid_pos[i];
+            if (p < 0 || (size_t)p >= ctx->Nd) return chefsi_fail(ctx, "projectors: grid_pos out of range");
+            if (seen[p]) d.overlap = 1;
+            seen[p] = 1;
+        }
+    }
+    /* CSR atom -> images */
+    std::vector<int> off(nl->n_atom + 1, 0), lst(nl->n_img);
+    for (int J = 0; J < nl->n_img; J++) off[nl->img_atom[J] + 1]++;
+    for (int a = 0; a < nl->n_atom; a++) off[a + 1] += off[a];
+    {
+        std::vector<int> cur(off.begin(), off.end() - 1);
+        for (int J = 0; J < nl->n_img; J++) lst[cur[nl->img_atom[J]]++] = J;
+    }
+    if (upload(ctx, &d.IP_displ, nl->IP_displ, (size_t)nl->n_atom + 1)) return 1;
+    if (upload(ctx, &d.gamma, nl->gamma, (size_t)d.ntot)) return 1;
+    if (upload(ctx, &d.img_atom, nl->img_atom, (size_t)nl->n_img)) return 1;
+    if (upload(ctx, &d.img_ndc, nl->img_ndc, (size_t)nl->n_img)) return 1;
+    if (upload(ctx, &d.pos_off, nl->pos_off, (size_t)nl->n_img + 1)) return 1;
+    if (upload(ctx, &d.chi_off, nl->chi_off, (size_t)nl->n_img + 1)) return 1;
+    if (upload(ctx, &d.grid_pos, nl->grid_pos, (size_t)npos)) return 1;
+    if (upload(ctx, &d.chi, nl->chi, (size_t)nchi)) return 1;
+    if (upload(ctx, &d.atom_img_off, off.data(), off.size())) return 1;
+    if (upload(ctx, &d.atom_img, lst.data(), lst.size())) return 1;
+    CHEFSI_CUDA(ctx, cudaMalloc((void **)&d.img_phase, sizeof(double2) * nl->n_img));
+    d.h_img_coords = (double *)malloc(sizeof(double) * 3 * nl->n_img);
+    memcpy(d.h_img_coords, nl->img_coords, sizeof(double) * 3 * nl->n_img);
+    return update_nloc_phases(ctx);
+}
+
+/* ---- one fused step ---------------------------------------------------------------------------- */
+struct EvPair { cudaEvent_t a, b; int kind; };
+
+struct Profiler {
+    chefsi_ctx *ctx;
+    std::vector<EvPair> evs;
+    explicit Profiler(chefsi_ctx *c) : ctx(c) {}
+    void begin(int kind)
+    {
+        if (!ctx->profiling) return;
+        EvPair p;
+        cudaEventCreate(&p.a);
+        cudaEventCreate(&p.b);
+        p.kind = kind;
+        cudaEventRecord(p.a, ctx->stream);
+        evs.push_back(p);
+    }
+    void end()
+    {
+        if (!ctx->profiling) return;
+        cudaEventRecord(evs.back().b, ctx->stream);
+    }
+    void finish()
+    {
+        if (!ctx->profiling) return;
+        cudaStreamSynchronize(ctx->stream);
+        double st = 0, nl = 0;
+        int ns = 0;
+        for (auto &p : evs) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, p.a, p.b);
+            if (p.kind == 0) { st += ms; ns++; } else nl += ms;
+            cudaEventDestroy(p.a);
+            cudaEventDestroy(p.b);
+        }
+        ctx->stats.last_stencil_ms = st;
+        ctx->stats.last_nloc_ms = nl;
+        ctx->stats.last_stencil_launches = ns;
+        evs.clear();
+    }
+};
+
+static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void *xprev, void *out, int ncol, double c,
+                      double s1, double s2, bool is_complex)
+{
+    StepArgs a;
+    a.x = x; a.xprev = xprev; a.out = out;
+    a.veff = ctx->have_veff ? ctx->d_veff : nullptr;
+    a.ld = ctx->ld; a.ncol = ncol; a.c = c; a.s1 = s1; a.s2 = s2;
+    int n;
+    prof.begin(0);
+    if (stream_orth_supported(ctx, is_complex)) {
+        n = launch_stencil_stream_orth(ctx, a, is_complex);
+        ctx->stats.last_path = 1;
+    } else {
+        n = launch_stencil_general(ctx, a, is_complex);
+        ctx->stats.last_path = 0;
+    }
+    prof.end();
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    prof.begin(1);
+    n = launch_nloc_apply(ctx, x, out, ctx->ld, ncol, s1, is_complex);
+    prof.end();
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    return 0;
+}
+
+static int filter_device(chefsi_ctx *ctx, void *bufs[3], int ncol, int m, double a, double b, double a0, bool is_complex,
+                         int *y_slot, int *x_slot)
+{
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (m < 1) return chefsi_fail(ctx, "Chebyshev degree must be >= 1");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    Profiler prof(ctx);
+    const double e = 0.5 * (b - a);
+    const double c = 0.5 * (b + a);
+    double sigma = e / (a0 - c);
+    const double sigma1 = sigma;
+    const double gamma = 2.0 / sigma1;
+    int X = 0, Y = 1, W = 2;
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    if (apply_step(ctx, prof, bufs[X], nullptr, bufs[Y], ncol, -c, sigma1 / e, 0.0, is_complex)) return 1;
+    for (int j = 1; j < m; j++) {
+        const double sigma2 = 1.0 / (gamma - sigma);
+        if (apply_step(ctx, prof, bufs[Y], bufs[X], bufs[W], ncol, -c, 2.0 * sigma2 / e, sigma * sigma2, is_complex)) return 1;
+        const int t = X; X = Y; Y = W; W = t;
+        sigma = sigma2;
+    }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    prof.finish();
+    if (y_slot) *y_slot = Y;
+    if (x_slot) *x_slot = X;
+    return 0;
+}
+
+extern "C" size_t chefsi_device_ld(const chefsi_ctx_t *ctx) { return ctx ? ctx->ld : 0; }
+
+extern "C" int chefsi_chebyshev_filter_device(chefsi_ctx_t *ctx, double *bufA, double *bufB, double *bufC, int ncol, int m,
+                                              double a, double b, double a0, int *y_slot, int *x_slot)
+{
+    if (!ctx) return 1;
+    void *bufs[3] = {bufA, bufB, bufC};
+    return filter_device(ctx, bufs, ncol, m, a, b, a0, false, y_slot, x_slot);
+}
+extern "C" int chefsi_chebyshev_filter_kpt_device(chefsi_ctx_t *ctx, void *bufA, void *bufB, void *bufC, int ncol, int m,
+                                                  double a, double b, double a0, int *y_slot, int *x_slot)
+{
+    if (!ctx) return 1;
+    void *bufs[3] = {bufA, bufB, bufC};
+    return filter_device(ctx, bufs, ncol, m, a, b, a0, true, y_slot, x_slot);
+}
+
+static int hmult_device(chefsi_ctx *ctx, int ncol, double c, const void *x, void *Hx, bool is_complex)
+{
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    Profiler prof(ctx);
+    const int rc = apply_step(ctx, prof, x, nullptr, Hx, ncol, c, 1.0, 0.0, is_complex);
+    prof.finish();
+    return rc;
+}
+extern "C" int chefsi_hamiltonian_mult_device(chefsi_ctx_t *ctx, int ncol, double c, const double *x, double *Hx)
+{
+    return ctx ? hmult_device(ctx, ncol, c, x, Hx, false) : 1;
+}
+extern "C" int chefsi_hamiltonian_mult_kpt_device(chefsi_ctx_t *ctx, int ncol, double c, const void *x, void *Hx)
+{
+    return ctx ? hmult_device(ctx, ncol, c, x, Hx, true) : 1;
+}
+
+extern "C" int chefsi_synchronize(chefsi_ctx_t *ctx)
+{
+    if (!ctx) return 1;
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->stats.last_filter_ms = ms;
+    else cudaGetLastError();
+    return 0;
+}
+
+/* ---- host-buffer entry points ---------------------------------------------------------------- */
+static int ensure_bufs(chefsi_ctx *ctx, size_t bytes_each)
+{
+    if (bytes_each <= ctx->buf_bytes) return 0;
+    for (int i = 0; i < 3; i++) { cudaFree(ctx->d_buf[i]); ctx->d_buf[i] = nullptr; }
+    ctx->buf_bytes = 0;
+    for (int i = 0; i < 3; i++) CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_buf[i], bytes_each));
+    ctx->buf_bytes = bytes_each;
+    return 0;
+}
+
+/* columns per chunk so that three blocks + alpha fit in the free device memory */
+static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
+{
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+    free_b += 3 * ctx->buf_bytes + ctx->alpha_bytes; /* what we already hold can be reused */
+    const size_t per_col = 3 * ctx->ld * esz + (size_t)ctx->nl.ntot * esz;
+    size_t budget = (size_t)(0.85 * (double)free_b);
+    const char *env = getenv("CHEFSI_B200_MAX_CHUNK_BYTES");
+    if (env) { size_t v = strtoull(env, nullptr, 10); if (v && v < budget) budget = v; }
+    size_t n = budget / (per_col ? per_col : 1);
+    if (n < 1) n = 1;
+    if (n > (size_t)ncol) n = (size_t)ncol;
+    return (int)n;
+}
+
+static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo, int ncol, int m, double a, double b,
+                       double a0, int flags, bool is_complex)
+{
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ncol <= 0) return 0;
+    if (ldi < ctx->Nd || ldo < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
+    const int chunk = chunk_columns(ctx, ncol, esz);
+    if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
+    const size_t row = ctx->Nd * esz;
+    double total_ms = 0;
+    for (int c0 = 0; c0 < ncol; c0 += chunk) {
+        const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
+        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_buf[0], ctx->ld * esz, (const char *)X + (size_t)c0 * ldi * esz, ldi * esz,
+                                           row, nc, cudaMemcpyHostToDevice, ctx->stream));
+        int ys = 1, xs = 0;
+        if (filter_device(ctx, ctx->d_buf, nc, m, a, b, a0, is_complex, &ys, &xs)) return 1;
+        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Y + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_buf[ys], ctx->ld * esz, row, nc,
+                                           cudaMemcpyDeviceToHost, ctx->stream));
+        if (!(flags & CHEFSI_FLAG_NO_X_COPYBACK))
+            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)X + (size_t)c0 * ldi * esz, ldi * esz, ctx->d_buf[xs], ctx->ld * esz, row,
+                                               nc, cudaMemcpyDeviceToHost, ctx->stream));
+        CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) total_ms += ms; else cudaGetLastError();
+    }
+    ctx->stats.last_filter_ms = total_ms;
+    return 0;
+}
+
+extern "C" int chefsi_chebyshev_filter(chefsi_ctx_t *ctx, double *X, size_t ldi, double *Y, size_t ldo, int ncol, int m,
+                                       double a, double b, double a0, int flags)
+{
+    return ctx ? filter_host(ctx, X, ldi, Y, ldo, ncol, m, a, b, a0, flags, false) : 1;
+}
+extern "C" int chefsi_chebyshev_filter_kpt(chefsi_ctx_t *ctx, void *X, size_t ldi, void *Y, size_t ldo, int ncol, int m,
+                                           double a, double b, double a0, int flags)
+{
+    return ctx ? filter_host(ctx, X, ldi, Y, ldo, ncol, m, a, b, a0, flags, true) : 1;
+}
+
+static int hmult_host(chefsi_ctx *ctx, int ncol, double c, const void *x, size_t ldi, void *Hx, size_t ldo, bool is_complex)
+{
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ncol <= 0) return 0;
+    if (ldi < ctx->Nd || ldo < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
+    const int chunk = chunk_columns(ctx, ncol, esz);
+    if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
+    const size_t row = ctx->Nd * esz;
+    for (int c0 = 0; c0 < ncol; c0 += chunk) {
+        const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
+        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_buf[0], ctx->ld * esz, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz,
+                                           row, nc, cudaMemcpyHostToDevice, ctx->stream));
+        if (hmult_device(ctx, nc, c, ctx->d_buf[0], ctx->d_buf[1], is_complex)) return 1;
+        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Hx + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_buf[1], ctx->ld * esz, row, nc,
+                                           cudaMemcpyDeviceToHost, ctx->stream));
+        CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+extern "C" int chefsi_hamiltonian_mult(chefsi_ctx_t *ctx, int ncol, double c, const double *x, size_t ldi, double *Hx,
+                                       size_t ldo)
+{
+    return ctx ? hmult_host(ctx, ncol, c, x, ldi, Hx, ldo, false) : 1;
+}
+extern "C" int chefsi_hamiltonian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double c, const void *x, size_t ldi, void *Hx,
+                                           size_t ldo)
+{
+    return ctx ? hmult_host(ctx, ncol, c, x, ldi, Hx, ldo, true) : 1;
+}
+
+/* ---- misc ---------------------------------------------------------------------------------------- */
+extern "C" int chefsi_fill_random_device(chefsi_ctx_t *ctx, void *buf, int ncol, long long first_col,
+                                         unsigned long long seed, int is_complex)
+{
+    if (!ctx) return 1;
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t mul = is_complex ? 2 : 1;
+    const int n = launch_fill_random(ctx, (double *)buf, ctx->Nd * mul, ctx->ld * mul, ncol, first_col, seed);
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    return 0;
+}
+
+extern "C" int chefsi_get_stats(const chefsi_ctx_t *ctx, chefsi_stats_t *out)
+{
+    if (!ctx || !out) return 1;
+    *out = ctx->stats;
+    return 0;
+}
+extern "C" int chefsi_set_profiling(chefsi_ctx_t *ctx, int on)
+{
+    if (!ctx) return 1;
+    ctx->profiling = on;
+    return 0;
+}
+extern "C" void *chefsi_stream(chefsi_ctx_t *ctx) { return ctx ? (void *)ctx->stream : nullptr; }

@@ -1,0 +1,117 @@
+/*
+ * chefsi_internal.h -- internal declarations shared by the CUDA translation units of
+ * libchefsi_b200.so.  Not part of the C ABI (that is include/chefsi_b200.h).
+ */
+#ifndef CHEFSI_INTERNAL_H
+#define CHEFSI_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/chefsi_b200.h"
+
+#define CHEFSI_MAXR CHEFSI_MAX_FDN
+
+/* ---- stencil description handed to the kernels by value ------------------------------ */
+struct MixedComp {
+    int ext, ax1, ax2;        /* axes 0:x 1:y 2:z ; ax2 = -1 when the inner derivative is single */
+    double c1[CHEFSI_MAXR + 1];
+    double c2[CHEFSI_MAXR + 1];
+    double wm[CHEFSI_MAXR + 1]; /* already scaled by a = -1/2 */
+};
+
+struct StencilDesc {
+    int Nx, Ny, Nz;
+    int bc[3];
+    int F;
+    int nmix;
+    double coef0;               /* a * (D2x[0] + D2y[0] + D2z[0]) */
+    double wx[CHEFSI_MAXR + 1]; /* a * D2_x[r] ... */
+    double wy[CHEFSI_MAXR + 1];
+    double wz[CHEFSI_MAXR + 1];
+    MixedComp mix[2];
+    double ph_re[27], ph_im[27]; /* Bloch phases exp(i k.(ox Lx, oy Ly, oz Lz)), index (oz+1)*9+(oy+1)*3+(ox+1) */
+};
+
+/* out = s1 * ((-1/2 Lap + veff + c) x) - s2 * xprev      (xprev may be NULL when s2 == 0)
+ * one launch handles ncol columns with leading dimension ld (elements of T).               */
+struct StepArgs {
+    const void *x;
+    const void *xprev;
+    void *out;
+    const double *veff;
+    size_t ld;
+    int ncol;
+    double c, s1, s2;
+};
+
+/* ---- nonlocal projector tables on the device ----------------------------------------- */
+struct NlocDev {
+    int n_atom = 0, n_img = 0, ntot = 0, max_nproj = 0;
+    int overlap = 1;           /* 1: some grid point lies in more than one sphere -> atomics */
+    int *IP_displ = nullptr;   /* [n_atom+1] */
+    double *gamma = nullptr;   /* [ntot]     */
+    int *img_atom = nullptr;   /* [n_img]    */
+    int *img_ndc = nullptr;
+    long long *pos_off = nullptr, *chi_off = nullptr;
+    int *grid_pos = nullptr;
+    double *chi = nullptr;
+    double2 *img_phase = nullptr; /* [n_img] (cos theta, sin theta) for the current k-point */
+    int *atom_img_off = nullptr;  /* CSR atom -> images */
+    int *atom_img = nullptr;
+    /* host copies needed to rebuild phases */
+    double *h_img_coords = nullptr;
+    long long total_pts = 0;
+};
+
+struct chefsi_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    bool have_grid = false;
+    chefsi_grid_t grid{};
+    StencilDesc desc{};
+    size_t Nd = 0, ld = 0;
+    double *d_veff = nullptr;
+    bool have_veff = false;
+    NlocDev nl;
+    double kvec[3] = {0, 0, 0};
+    /* scratch owned by the host entry points */
+    void *d_buf[3] = {nullptr, nullptr, nullptr};
+    size_t buf_bytes = 0;
+    void *d_alpha = nullptr;
+    size_t alpha_bytes = 0;
+    /* stats */
+    chefsi_stats_t stats{};
+    int profiling = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int num_sms = 148;
+    size_t max_smem_optin = 0;
+    int force_general = 0;
+    char err[512] = {0};
+};
+
+int chefsi_fail(chefsi_ctx *ctx, const char *fmt, ...);
+#define CHEFSI_CUDA(ctx, call)                                                                \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return chefsi_fail((ctx), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,           \
+                               cudaGetErrorString(e_));                                       \
+    } while (0)
+
+/* ---- kernel launchers (each returns the number of kernels it launched, <0 on error) --- */
+int launch_stencil_general(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
+bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex);
+int launch_stencil_stream_orth(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
+
+/* alpha = dV * phase * Chi^T x   (per atom, summed over its images), then
+ * out += scale * conj(phase) * Chi (Gamma .* alpha)                                         */
+int launch_nloc_apply(chefsi_ctx *ctx, const void *x, void *out, size_t ld, int ncol, double scale,
+                      bool is_complex);
+
+int launch_fill_random(chefsi_ctx *ctx, double *buf, size_t n_per_col, size_t ld_doubles, int ncol,
+                       long long first_col, unsigned long long seed);
+
+#endif

@@ -1,0 +1,55 @@
+"""Generate tests/golden/*.npz from the reference's own compiled routines.
+
+Run in the dev container (needs oracle/_ref/, i.e. /root/reference):
+
+    python tests/golden/make_golden.py
+
+Each file stores the complete inputs (grid tables, Veff, projector tables, start vectors,
+bounds, k-point) together with the outputs of the UNMODIFIED reference functions
+Hamiltonian_vectors_mult[_kpt] and ChebyshevFiltering[_kpt] on them, so the vectors can be
+checked anywhere (the GPU box has no /root/reference).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.bindings import Reference  # noqa: E402
+from sparc_b200 import problem as P  # noqa: E402
+from tests.cases import BOUNDS, KVEC, small_case  # noqa: E402
+
+CASES = {
+    # name: (cell_typ, BC, complex, m)
+    "orth_gamma": (0, (0, 0, 0), False, 8),
+    "orth_dirichlet_gamma": (0, (1, 0, 1), False, 5),
+    "si8lat_gamma": (17, (0, 0, 0), False, 8),
+    "orth_kpt": (0, (0, 0, 0), True, 6),
+    "si8lat_kpt": (17, (0, 0, 0), True, 6),
+    "type14_mixedbc_gamma": (14, (0, 1, 0), False, 5),
+}
+
+
+def main():
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    a, b, a0 = BOUNDS
+    for name, (ct, BC, cplx, m) in CASES.items():
+        g, veff, proj, x = small_case(ct, BC, N=(12, 10, 14), L=(6.0, 5.2, 7.0), ncol=2, complex_=cplx, seed=3)
+        ref = Reference(g, proj, veff, kvec=KVEC)
+        Hx = ref.hamiltonian_mult(-0.25, x)
+        Xo, Yo = ref.chebyshev_filter(x, m, a, b, a0)
+        coefs = np.stack([g.coefs[n] for n in P._COEF_NAMES])
+        np.savez_compressed(
+            os.path.join(out_dir, name + ".npz"),
+            N=np.array(g.N), BC=np.array(g.BC), L=np.array(g.L), FDn=g.FDn, cell_typ=g.cell_typ, dV=g.dV,
+            coefs=coefs, veff=veff, kvec=np.array(KVEC), bounds=np.array([a, b, a0]), m=m, c_shift=-0.25,
+            IP_displ=proj.IP_displ, gamma=proj.gamma, img_atom=proj.img_atom, img_ndc=proj.img_ndc,
+            img_coords=proj.img_coords, pos_off=proj.pos_off, chi_off=proj.chi_off, grid_pos=proj.grid_pos,
+            chi=proj.chi, X0=x, Hx=Hx, X_out=Xo, Y_out=Yo)
+        print(name, "cell_typ", g.cell_typ, "n_img", proj.n_img, "|Y|", np.linalg.norm(Yo))
+
+
+if __name__ == "__main__":
+    main()

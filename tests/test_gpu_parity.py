@@ -1,0 +1,225 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libchefsi_b200.so), against
+the oracle on the same seeded inputs, against the committed reference-generated vectors, and --
+at sizes the oracle cannot reach in seconds -- through size-independent properties.
+
+Tolerance: north_star's <= 1e-10 relative Frobenius error on filtered vectors (FP64 throughout;
+only summation order differs from the reference).
+"""
+import numpy as np
+import pytest
+
+from sparc_b200 import problem as P
+from tests.cases import BOUNDS, GOLDEN, KVEC, load_golden, rel_fro, small_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sparc_b200.chefsi import ChefsiContext
+    c = ChefsiContext(0)
+    yield c
+    c.close()
+
+
+def _setup(ctx, g, veff, proj, kvec=None):
+    ctx.set_grid(g)
+    ctx.set_veff(veff)
+    ctx.set_projectors(proj)
+    ctx.set_kpoint(kvec if kvec is not None else (0, 0, 0))
+
+
+# ---------------------------------------------------------------- golden vectors (reference-made)
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_vectors(ctx, name):
+    g, veff, proj, d = load_golden(name)
+    _setup(ctx, g, veff, proj, tuple(d["kvec"]))
+    a, b, a0 = d["bounds"]
+    x = np.ascontiguousarray(d["X0"])
+    Hx = np.empty_like(x)
+    ctx.Hamiltonian_vectors_mult(float(d["c_shift"]), x, Hx)
+    assert rel_fro(Hx, d["Hx"]) < TOL
+    X = x.copy()
+    Y = np.empty_like(X)
+    ctx.ChebyshevFiltering(X, Y, int(d["m"]), a, b, a0)
+    assert rel_fro(Y, d["Y_out"]) < TOL
+    assert rel_fro(X, d["X_out"]) < TOL
+
+
+# ---------------------------------------------------------------- every cell type / BC vs the oracle
+@pytest.mark.parametrize("cell_typ", [0, 11, 12, 13, 14, 15, 16, 17])
+@pytest.mark.parametrize("BC", [(0, 0, 0), (0, 1, 0), (1, 1, 1)])
+@pytest.mark.parametrize("complex_", [False, True])
+def test_hamiltonian_all_cell_types(ctx, port, cell_typ, BC, complex_):
+    g, veff, proj, x = small_case(cell_typ, BC, complex_=complex_)
+    _setup(ctx, g, veff, proj, KVEC)
+    Hx = np.empty_like(x)
+    ctx.Hamiltonian_vectors_mult(-0.3, x, Hx)
+    want = port.hamiltonian_mult(g, proj, veff, -0.3, x, kvec=KVEC)
+    assert rel_fro(Hx, want) < TOL
+
+
+@pytest.mark.parametrize("cell_typ", [0, 14, 17])
+@pytest.mark.parametrize("complex_", [False, True])
+def test_chebyshev_filter_small(ctx, port, cell_typ, complex_):
+    g, veff, proj, x = small_case(cell_typ, complex_=complex_, ncol=5)
+    _setup(ctx, g, veff, proj, KVEC)
+    a, b, a0 = BOUNDS
+    X = x.copy()
+    Y = np.empty_like(X)
+    ctx.ChebyshevFiltering(X, Y, 12, a, b, a0)
+    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 12, a, b, a0, kvec=KVEC)
+    assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+
+
+def test_leading_dimension_larger_than_grid(ctx, port):
+    """ld != rows (collinear spin: ldi = DMnd * Nspinor_spincomm, eigenSolver.c:325-328)."""
+    g, veff, proj, x = small_case(0, ncol=3)
+    _setup(ctx, g, veff, proj)
+    ld = 2 * g.Nd + 3
+    X = np.full((3, ld), 7.0)
+    X[:, :g.Nd] = x
+    Y = np.full((3, ld), -3.0)
+    a, b, a0 = BOUNDS
+    ctx.ChebyshevFiltering(X, Y, 6, a, b, a0)
+    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 6, a, b, a0)
+    assert rel_fro(Y[:, :g.Nd], Yw) < TOL and rel_fro(X[:, :g.Nd], Xw) < TOL
+    assert (X[:, g.Nd:] == 7.0).all() and (Y[:, g.Nd:] == -3.0).all()
+
+
+def test_degree_one_and_no_x_copyback(ctx, port):
+    g, veff, proj, x = small_case(0, ncol=2)
+    _setup(ctx, g, veff, proj)
+    a, b, a0 = BOUNDS
+    X = x.copy()
+    Y = np.empty_like(X)
+    ctx.ChebyshevFiltering(X, Y, 1, a, b, a0, copy_back_x=False)
+    _, Yw = port.chebyshev_filter(g, proj, veff, x, 1, a, b, a0)
+    assert rel_fro(Y, Yw) < TOL
+    assert np.array_equal(X, x)  # untouched on the host when copy-back is off
+
+
+def test_no_projectors_no_veff_lanczos_style_call(ctx, port):
+    """ncol = 1, c = 0 as Lanczos calls Hamiltonian_vectors_mult (eigenSolver.c:2002)."""
+    g, veff, proj, x = small_case(17, ncol=1, with_proj=False)
+    _setup(ctx, g, veff, None)
+    Hx = np.empty_like(x)
+    ctx.Hamiltonian_vectors_mult(0.0, x, Hx)
+    assert rel_fro(Hx, port.hamiltonian_mult(g, None, veff, 0.0, x)) < TOL
+
+
+def test_fd_radius_four(ctx, port):
+    g, veff, proj, x = small_case(17, FDn=4)
+    _setup(ctx, g, veff, proj)
+    Hx = np.empty_like(x)
+    ctx.Hamiltonian_vectors_mult(0.1, x, Hx)
+    assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, 0.1, x)) < TOL
+
+
+# ---------------------------------------------------------------- streaming orthogonal kernel
+@pytest.mark.parametrize("N,BC", [((32, 32, 24), (0, 0, 0)), ((48, 40, 20), (0, 0, 0)), ((36, 24, 16), (0, 0, 0)),
+                                   ((32, 32, 16), (1, 0, 1)), ((64, 32, 16), (0, 1, 0)), ((32, 16, 12), (1, 1, 1))])
+def test_stream_kernel_vs_oracle(ctx, port, N, BC):
+    """Shapes that take the streaming path (incl. ragged tiles, Dirichlet faces)."""
+    g = P.make_grid(N, tuple(0.45 * n for n in N), BC=BC)
+    veff = P.synthetic_veff(g)
+    proj = P.make_projectors(g, np.array([[0.02, 0.5, 0.97], [0.5, 0.5, 0.5]]), rc=[2.4, 2.0], nproj=[18, 7])
+    x = P.random_columns(g.Nd, 3, seed=11)
+    _setup(ctx, g, veff, proj)
+    a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+    Hx = np.empty_like(x)
+    ctx.Hamiltonian_vectors_mult(-0.3, x, Hx)
+    assert ctx.stats()["last_path"] == 1
+    assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, -0.3, x)) < TOL
+    X = x.copy()
+    Y = np.empty_like(X)
+    ctx.ChebyshevFiltering(X, Y, 8, a, b, a0)
+    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 8, a, b, a0)
+    assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+
+
+def test_stream_and_general_kernels_agree(ctx):
+    import os
+    from sparc_b200.chefsi import ChefsiContext
+    g = P.make_grid((64, 48, 40), (20.0, 15.0, 12.5))
+    veff = P.synthetic_veff(g)
+    x = P.random_columns(g.Nd, 4, seed=2)
+    _setup(ctx, g, veff, None)
+    a, b, a0 = P.chebyshev_bounds(g)
+    X1, Y1 = x.copy(), np.empty_like(x)
+    ctx.ChebyshevFiltering(X1, Y1, 10, a, b, a0)
+    assert ctx.stats()["last_path"] == 1
+    os.environ["CHEFSI_B200_FORCE_GENERAL"] = "1"
+    try:
+        c2 = ChefsiContext(0)
+    finally:
+        del os.environ["CHEFSI_B200_FORCE_GENERAL"]
+    _setup(c2, g, veff, None)
+    X2, Y2 = x.copy(), np.empty_like(x)
+    c2.ChebyshevFiltering(X2, Y2, 10, a, b, a0)
+    assert c2.stats()["last_path"] == 0
+    c2.close()
+    assert rel_fro(Y1, Y2) < 1e-12 and rel_fro(X1, X2) < 1e-12
+
+
+# ---------------------------------------------------------------- full-size properties (160^3)
+def test_full_size_plane_wave_and_linearity(ctx):
+    """BASELINE.json's grid (160^3, FD order 12): a plane wave is an eigenvector of H when Veff is
+    constant, so the filter must return the scalar Chebyshev recurrence times the input; plus
+    linearity filter(x + 2y) = filter(x) + 2 filter(y) on random columns with the real Veff."""
+    import torch
+    N = 160
+    g = P.make_grid((N, N, N), (45.9, 45.9, 45.9))
+    ctx.set_grid(g)
+    ctx.set_projectors(None)
+    ctx.set_kpoint((0, 0, 0))
+    ax = 2 * np.pi * np.arange(N) / N
+    pw = np.cos(3 * ax[None, None, :] + 5 * ax[None, :, None] + 2 * ax[:, None, None]).reshape(1, -1)
+    lam = 0.0
+    for d, (name, mm) in enumerate((("D2_x", 3), ("D2_y", 5), ("D2_z", 2))):
+        w = g.coefs[name]
+        lam += w[0] + sum(2 * w[p] * np.cos(p * 2 * np.pi * mm / N) for p in range(1, 7))
+    lam = -0.5 * lam - 0.37
+    ctx.set_veff(np.full(g.Nd, -0.37))
+    a, b, a0 = P.chebyshev_bounds(g)
+    m = 20
+    e, c = 0.5 * (b - a), 0.5 * (b + a)
+    sigma = sigma1 = e / (a0 - c)
+    gamma = 2.0 / sigma1
+    t_prev, t = 1.0, (sigma1 / e) * (lam - c)
+    for _ in range(1, m):
+        sigma2 = 1.0 / (gamma - sigma)
+        t_prev, t = t, (2 * sigma2 / e) * (lam - c) * t - sigma * sigma2 * t_prev
+        sigma = sigma2
+    X = np.ascontiguousarray(pw)
+    Y = np.empty_like(X)
+    ctx.ChebyshevFiltering(X, Y, m, a, b, a0)
+    assert ctx.stats()["last_path"] == 1
+    assert rel_fro(Y, t * pw) < TOL and rel_fro(X, t_prev * pw) < TOL
+
+    ctx.set_veff(P.synthetic_veff(g))
+    r = P.random_columns(g.Nd, 2, seed=4)
+    Xs = np.ascontiguousarray(np.stack([r[0], r[1], r[0] + 2.0 * r[1]]))
+    Ys = np.empty_like(Xs)
+    ctx.ChebyshevFiltering(Xs, Ys, m, a, b, a0)
+    assert rel_fro(Ys[2], Ys[0] + 2.0 * Ys[1]) < TOL
+
+
+def test_device_resident_entry_point_and_rng(ctx, port):
+    import torch
+    g, veff, proj, _ = small_case(0, N=(32, 32, 16), L=(14.0, 14.0, 7.0))
+    _setup(ctx, g, veff, proj)
+    ld = ctx.device_ld
+    ncol = 4
+    bufs = [torch.zeros(ncol * ld, dtype=torch.float64, device="cuda") for _ in range(3)]
+    ctx.fill_random_device(bufs[0], ncol, first_col=7, seed=3)
+    ctx.synchronize()
+    x = bufs[0].view(ncol, ld)[:, :g.Nd].cpu().numpy()
+    assert np.array_equal(x, P.random_columns(g.Nd, ncol, first_col=7, seed=3))
+    a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+    ys, xs = ctx.filter_device(bufs[0], bufs[1], bufs[2], ncol, 7, a, b, a0)
+    ctx.synchronize()
+    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 7, a, b, a0)
+    assert rel_fro(bufs[ys].view(ncol, ld)[:, :g.Nd].cpu().numpy(), Yw) < TOL
+    assert rel_fro(bufs[xs].view(ncol, ld)[:, :g.Nd].cpu().numpy(), Xw) < TOL

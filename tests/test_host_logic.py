@@ -1,0 +1,59 @@
+"""Host-side logic that needs neither a GPU nor the reference: SPARC's FD tables, cell-type
+classification, the counter-based start-vector generator, band partitioning."""
+import numpy as np
+import pytest
+
+from sparc_b200 import problem as P
+from sparc_b200.partition import band_partition
+
+
+def test_fd_weights_order12():
+    w1, w2 = P.fd_weights(6)
+    # classic 12th-order central weights
+    assert w2[0] == pytest.approx(-5369.0 / 1800.0, rel=1e-14)
+    assert w2[1] == pytest.approx(12.0 / 7.0, rel=1e-14)
+    assert w2[6] == pytest.approx(-1.0 / 16632.0, rel=1e-13)
+    assert w1[1] == pytest.approx(6.0 / 7.0, rel=1e-14)
+    assert abs(w2[0] + 2 * w2[1:].sum()) < 1e-14  # constants are annihilated
+
+
+@pytest.mark.parametrize("ct", [0, 11, 12, 13, 14, 15, 16, 17])
+def test_cell_type_classification(ct):
+    g = P.make_grid((12, 12, 12), (6, 6, 6), latvec=P.LATVEC_BY_CELL_TYP[ct])
+    assert g.cell_typ == ct
+
+
+def test_si8_lattice_is_type_17():
+    """tests/Si8/standard/Si8.inpt:3-6 (Si8 is triclinic, cell_typ 17)."""
+    assert P.lattice_transforms(P.SI8_LATVEC)[4] == 17
+
+
+def test_random_columns_match_c_generator(port):
+    a = P.random_columns(1000, 3, first_col=5, seed=9)
+    b = port.fill_random(1000, 3, first_col=5, seed=9)
+    assert np.array_equal(a, b)
+    assert a.min() >= -0.5 and a.max() < 0.5 and abs(a.mean()) < 0.02
+    # column blocks are reproducible independently of how they are split
+    c = P.random_columns(1000, 1, first_col=6, seed=9)
+    assert np.array_equal(a[1], c[0])
+
+
+def test_band_partition_matches_sparc_npband_rule():
+    """parallelization.c:403-428: NB = ceil(Ns/npband); rank r owns [r*NB, min((r+1)NB, Ns))."""
+    for ns, p in [(4096, 8), (30, 6), (29, 8), (9, 4), (5, 8), (27, 9)]:
+        parts = [band_partition(ns, p, r) for r in range(p)]
+        nb = -(-ns // p)
+        covered = []
+        for r, (s, n) in enumerate(parts):
+            assert s == min(r * nb, ns)
+            assert n == max(0, min((r + 1) * nb, ns) - r * nb)
+            covered += list(range(s, s + n))
+        assert covered == list(range(ns))
+
+
+def test_projector_tables_are_consistent():
+    g = P.make_grid((14, 13, 15), (7.0, 6.5, 7.5), latvec=P.SI8_LATVEC)
+    pr = P.make_projectors(g, np.array([[0.05, 0.5, 0.5]]), rc=2.2, nproj=4)
+    assert pr.n_img >= 2  # atom near the x face: its periodic image reaches into the cell
+    assert pr.pos_off[-1] == pr.grid_pos.size and pr.chi_off[-1] == pr.chi.size
+    assert (pr.grid_pos >= 0).all() and (pr.grid_pos < g.Nd).all()
