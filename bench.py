@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--grid", type=int, default=160)
     ap.add_argument("--ncol", type=int, default=4096)
     ap.add_argument("--degree", type=int, default=20)
-    ap.add_argument("--block", type=int, default=256, help="columns filtered per launch group")
+    ap.add_argument("--block", type=int, default=128, help="columns filtered per launch group")
     ap.add_argument("--ncell", type=int, default=6, help="fcc conventional cells per axis (4 atoms each)")
     ap.add_argument("--no-nloc", action="store_true", help="stencil + Veff only (roofline study)")
     ap.add_argument("--e2e-cols", type=int, default=256)

@@ -118,8 +118,12 @@ int chefsi_hamiltonian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double c, const voi
                                 size_t ldi, void *Hx, size_t ldo);
 
 /* ---- device-resident entry points ---------------------------------------------------
- * Buffers are device pointers holding ncol columns with leading dimension
- * chefsi_device_ld(ctx) elements (doubles, or complex pairs for the _kpt variants).
+ * Buffers are device pointers (256-byte aligned) holding ncol columns in the library's INTERNAL
+ * layout: chefsi_device_ld(ctx) elements (doubles, or complex pairs for the _kpt variants) per
+ * column; for large orthogonal grids every xy-plane carries a halo pad that the TMA tiles of the
+ * streaming kernel read (DESIGN.md "Data layout in HBM").  chefsi_pack_device /
+ * chefsi_unpack_device convert from / to the reference's dense layout (column n at n*ld_dense,
+ * x fastest) on the device; chefsi_fill_random_device writes the internal layout directly.
  * The three buffers rotate through the recurrence; on return *y_slot / *x_slot say
  * which of {0:bufA, 1:bufB, 2:bufC} hold Y = p_m(H)X0 and X = p_{m-1}(H)X0.
  * bufA holds X0 on entry.  All work is enqueued on the context's stream and the call
@@ -136,6 +140,10 @@ int chefsi_hamiltonian_mult_device(chefsi_ctx_t *ctx, int ncol, double c, const 
 int chefsi_hamiltonian_mult_kpt_device(chefsi_ctx_t *ctx, int ncol, double c, const void *x,
                                        void *Hx);
 int chefsi_synchronize(chefsi_ctx_t *ctx);
+int chefsi_pack_device(chefsi_ctx_t *ctx, const void *dense, size_t ld_dense, void *packed, int ncol,
+                       int is_complex);
+int chefsi_unpack_device(chefsi_ctx_t *ctx, const void *packed, void *dense, size_t ld_dense, int ncol,
+                         int is_complex);
 
 /* Fill ncol device columns with the synthetic start vectors of SURVEY.md section 8(d):
  * U(-0.5,0.5) from a counter-based generator keyed on (seed, global column, grid index),

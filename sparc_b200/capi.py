@@ -21,7 +21,7 @@ EXPORTS = (
     "chefsi_device_ld",
     "chefsi_chebyshev_filter_device", "chefsi_chebyshev_filter_kpt_device",
     "chefsi_hamiltonian_mult_device", "chefsi_hamiltonian_mult_kpt_device",
-    "chefsi_synchronize", "chefsi_fill_random_device",
+    "chefsi_synchronize", "chefsi_fill_random_device", "chefsi_pack_device", "chefsi_unpack_device",
     "chefsi_get_stats", "chefsi_set_profiling", "chefsi_stream",
 )
 
@@ -78,6 +78,8 @@ def load_library() -> C.CDLL:
         getattr(lib, name).argtypes = [vp, i, d, dp, dp]
     lib.chefsi_synchronize.argtypes = [vp]
     lib.chefsi_fill_random_device.argtypes = [vp, dp, i, C.c_longlong, C.c_ulonglong, i]
+    lib.chefsi_pack_device.argtypes = [vp, dp, sz, dp, i, i]
+    lib.chefsi_unpack_device.argtypes = [vp, dp, dp, sz, i, i]
     lib.chefsi_get_stats.argtypes = [vp, C.POINTER(ChefsiStats)]
     lib.chefsi_set_profiling.argtypes = [vp, i]
     lib.chefsi_stream.argtypes = [vp]

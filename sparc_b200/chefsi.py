@@ -138,6 +138,15 @@ class ChefsiContext:
         self._check(self._lib.chefsi_fill_random_device(self._h, _addr(buf), int(ncol), int(first_col), int(seed),
                                                         int(bool(is_complex))))
 
+    def pack_device(self, dense, ld_dense, packed, ncol, is_complex=False):
+        """dense device block (column n at n*ld_dense) -> internal layout."""
+        self._check(self._lib.chefsi_pack_device(self._h, _addr(dense), int(ld_dense), _addr(packed), int(ncol),
+                                                 int(bool(is_complex))))
+
+    def unpack_device(self, packed, dense, ld_dense, ncol, is_complex=False):
+        self._check(self._lib.chefsi_unpack_device(self._h, _addr(packed), _addr(dense), int(ld_dense), int(ncol),
+                                                   int(bool(is_complex))))
+
     def synchronize(self):
         self._check(self._lib.chefsi_synchronize(self._h))
 

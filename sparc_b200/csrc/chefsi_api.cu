@@ -87,6 +87,7 @@ static void free_nloc(NlocDev &d)
     cudaFree(d.IP_displ); cudaFree(d.gamma); cudaFree(d.img_atom); cudaFree(d.img_ndc);
     cudaFree(d.pos_off); cudaFree(d.chi_off); cudaFree(d.grid_pos); cudaFree(d.chi);
     cudaFree(d.img_phase); cudaFree(d.atom_img_off); cudaFree(d.atom_img);
+    cudaFree(d.patch_src); cudaFree(d.patch_dst); cudaFree(d.patch_ph);
     free(d.h_img_coords);
     d = NlocDev();
 }
@@ -100,6 +101,7 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     cudaFree(ctx->d_veff);
     for (int i = 0; i < 3; i++) cudaFree(ctx->d_buf[i]);
     cudaFree(ctx->d_alpha);
+    cudaFree(ctx->d_stage);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
@@ -155,10 +157,23 @@ extern "C" int chefsi_set_grid(chefsi_ctx_t *ctx, const chefsi_grid_t *g)
         if (per[d] && N[d] < g->FDn) return chefsi_fail(ctx, "periodic axis %d has fewer points than the FD radius", d);
     ctx->grid = *g;
     ctx->Nd = (size_t)g->Nx * g->Ny * g->Nz;
-    ctx->ld = (ctx->Nd + 15) / 16 * 16;
+    {   /* internal layout: halo-padded planes when the streaming kernel applies (see Layout) */
+        Layout &L = ctx->lay;
+        const bool padded = stream_layout_wanted(*g) && !ctx->force_general;
+        L.Nx = g->Nx; L.Ny = g->Ny; L.Nz = g->Nz;
+        L.px = padded ? 8 : 0;
+        L.py = padded ? 6 : 0;
+        L.Nxp = g->Nx + 2 * L.px;
+        L.Nyp = g->Ny + 2 * L.py;
+        L.plane = (size_t)L.Nxp * L.Nyp;
+        L.ld = (L.plane * g->Nz + 15) / 16 * 16;
+        ctx->ld = L.ld;
+        if (L.ld > 0x7fffffffULL) return chefsi_fail(ctx, "grid too large for 32-bit sphere indices");
+    }
 
     StencilDesc &d = ctx->desc;
     memset(&d, 0, sizeof(d));
+    d.lay = ctx->lay;
     d.Nx = g->Nx; d.Ny = g->Ny; d.Nz = g->Nz;
     d.bc[0] = g->BCx; d.bc[1] = g->BCy; d.bc[2] = g->BCz;
     d.F = g->FDn;
@@ -196,10 +211,10 @@ extern "C" int chefsi_set_grid(chefsi_ctx_t *ctx, const chefsi_grid_t *g)
     }
     update_phases(ctx);
 
-    /* Veff buffer (+ a zero page behind it used as the source of Dirichlet halos) */
+    /* Veff buffer, internal layout */
     cudaFree(ctx->d_veff);
     ctx->d_veff = nullptr;
-    const size_t nv = ctx->ld + 4096;
+    const size_t nv = ctx->ld;
     CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_veff, nv * sizeof(double)));
     CHEFSI_CUDA(ctx, cudaMemsetAsync(ctx->d_veff, 0, nv * sizeof(double), ctx->stream));
     CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -226,8 +241,17 @@ extern "C" int chefsi_set_veff(chefsi_ctx_t *ctx, const double *veff_host)
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!veff_host) { ctx->have_veff = false; return 0; }
-    CHEFSI_CUDA(ctx, cudaMemcpyAsync(ctx->d_veff, veff_host, ctx->Nd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const Layout &L = ctx->lay;
+    if (L.px == 0 && L.py == 0) {
+        CHEFSI_CUDA(ctx, cudaMemcpyAsync(ctx->d_veff, veff_host, ctx->Nd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else { /* Nd doubles once per SCF step: repack on the host */
+        std::vector<double> tmp(L.ld, 0.0);
+        for (int k = 0; k < L.Nz; k++)
+            for (int j = 0; j < L.Ny; j++)
+                memcpy(&tmp[lay_pos(L, 0, j, k)], veff_host + ((size_t)k * L.Ny + j) * L.Nx, sizeof(double) * L.Nx);
+        CHEFSI_CUDA(ctx, cudaMemcpy(ctx->d_veff, tmp.data(), L.ld * sizeof(double), cudaMemcpyHostToDevice));
+    }
     ctx->have_veff = true;
     return 0;
 }
@@ -284,13 +308,38 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
         std::vector<int> cur(off.begin(), off.end() - 1);
         for (int J = 0; J < nl->n_img; J++) lst[cur[nl->img_atom[J]]++] = J;
     }
+    /* sphere indices in the internal layout, and the list of sphere points mirrored in halo pads */
+    const Layout &L = ctx->lay;
+    std::vector<int> ppos((size_t)npos);
+    std::vector<int> psrc, pdst;
+    std::vector<unsigned char> done(ctx->Nd, 0);
+    for (long long t = 0; t < npos; t++) {
+        const int p = nl->grid_pos[t];
+        const int i = p % L.Nx, j = (p / L.Nx) % L.Ny, k = p / (L.Nx * L.Ny);
+        const size_t q = lay_pos(L, i, j, k);
+        ppos[t] = (int)q;
+        if ((L.px || L.py) && !done[p]) {
+            done[p] = 1;
+            if (L.px && !ctx->grid.BCx) {
+                if (i < L.px) { psrc.push_back((int)q); pdst.push_back((int)(q + L.Nx)); }
+                else if (i >= L.Nx - L.px) { psrc.push_back((int)q); pdst.push_back((int)(q - L.Nx)); }
+            }
+            if (L.py && !ctx->grid.BCy) {
+                if (j < L.py) { psrc.push_back((int)q); pdst.push_back((int)(q + (size_t)L.Ny * L.Nxp)); }
+                else if (j >= L.Ny - L.py) { psrc.push_back((int)q); pdst.push_back((int)(q - (size_t)L.Ny * L.Nxp)); }
+            }
+        }
+    }
+    d.n_patch = (int)psrc.size();
+    if (upload(ctx, &d.patch_src, psrc.data(), psrc.size())) return 1;
+    if (upload(ctx, &d.patch_dst, pdst.data(), pdst.size())) return 1;
     if (upload(ctx, &d.IP_displ, nl->IP_displ, (size_t)nl->n_atom + 1)) return 1;
     if (upload(ctx, &d.gamma, nl->gamma, (size_t)d.ntot)) return 1;
     if (upload(ctx, &d.img_atom, nl->img_atom, (size_t)nl->n_img)) return 1;
     if (upload(ctx, &d.img_ndc, nl->img_ndc, (size_t)nl->n_img)) return 1;
     if (upload(ctx, &d.pos_off, nl->pos_off, (size_t)nl->n_img + 1)) return 1;
     if (upload(ctx, &d.chi_off, nl->chi_off, (size_t)nl->n_img + 1)) return 1;
-    if (upload(ctx, &d.grid_pos, nl->grid_pos, (size_t)npos)) return 1;
+    if (upload(ctx, &d.grid_pos, ppos.data(), (size_t)npos)) return 1;
     if (upload(ctx, &d.chi, nl->chi, (size_t)nchi)) return 1;
     if (upload(ctx, &d.atom_img_off, off.data(), off.size())) return 1;
     if (upload(ctx, &d.atom_img, lst.data(), lst.size())) return 1;
@@ -363,6 +412,10 @@ static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void
     ctx->stats.kernel_launches += n;
     prof.begin(1);
     n = launch_nloc_apply(ctx, x, out, ctx->ld, ncol, s1, is_complex);
+    if (n > 0 && ctx->stats.last_path == 1) {
+        const int m2 = launch_nloc_halo_patch(ctx, out, ctx->ld, ncol, is_complex);
+        n = (m2 < 0) ? -1 : n + m2;
+    }
     prof.end();
     if (n < 0) return 1;
     ctx->stats.kernel_launches += n;
@@ -383,6 +436,20 @@ static int filter_device(chefsi_ctx *ctx, void *bufs[3], int ncol, int m, double
     const double gamma = 2.0 / sigma1;
     int X = 0, Y = 1, W = 2;
     cudaEventRecord(ctx->ev[0], ctx->stream);
+    if (stream_orth_supported(ctx, is_complex)) {
+        /* the streaming kernel reads halos from the pads of the internal layout: images of X0 now, and
+           zeros on Dirichlet faces of the two buffers it will write (it only writes periodic images) */
+        int n = launch_halo_prepare(ctx, bufs[0], ncol, is_complex, 0);
+        if (n < 0) return 1;
+        ctx->stats.kernel_launches += n;
+        if (ctx->grid.BCx || ctx->grid.BCy) {
+            for (int t = 1; t < 3; t++) {
+                n = launch_halo_prepare(ctx, bufs[t], ncol, is_complex, 1);
+                if (n < 0) return 1;
+                ctx->stats.kernel_launches += n;
+            }
+        }
+    }
     if (apply_step(ctx, prof, bufs[X], nullptr, bufs[Y], ncol, -c, sigma1 / e, 0.0, is_complex)) return 1;
     for (int j = 1; j < m; j++) {
         const double sigma2 = 1.0 / (gamma - sigma);
@@ -419,6 +486,11 @@ static int hmult_device(chefsi_ctx *ctx, int ncol, double c, const void *x, void
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     Profiler prof(ctx);
+    if (stream_orth_supported(ctx, is_complex)) {
+        int n = launch_halo_prepare(ctx, const_cast<void *>(x), ncol, is_complex, 0);
+        if (n < 0) return 1;
+        ctx->stats.kernel_launches += n;
+    }
     const int rc = apply_step(ctx, prof, x, nullptr, Hx, ncol, c, 1.0, 0.0, is_complex);
     prof.finish();
     return rc;
@@ -444,6 +516,17 @@ extern "C" int chefsi_synchronize(chefsi_ctx_t *ctx)
 }
 
 /* ---- host-buffer entry points ---------------------------------------------------------------- */
+static int ensure_stage(chefsi_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->stage_bytes) return 0;
+    cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr;
+    ctx->stage_bytes = 0;
+    CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_stage, bytes));
+    ctx->stage_bytes = bytes;
+    return 0;
+}
+
 static int ensure_bufs(chefsi_ctx *ctx, size_t bytes_each)
 {
     if (bytes_each <= ctx->buf_bytes) return 0;
@@ -459,8 +542,8 @@ static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
 {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
-    free_b += 3 * ctx->buf_bytes + ctx->alpha_bytes; /* what we already hold can be reused */
-    const size_t per_col = 3 * ctx->ld * esz + (size_t)ctx->nl.ntot * esz;
+    free_b += 3 * ctx->buf_bytes + ctx->alpha_bytes + ctx->stage_bytes; /* what we already hold can be reused */
+    const size_t per_col = 3 * ctx->ld * esz + ctx->Nd * esz + (size_t)ctx->nl.ntot * esz;
     size_t budget = (size_t)(0.85 * (double)free_b);
     const char *env = getenv("CHEFSI_B200_MAX_CHUNK_BYTES");
     if (env) { size_t v = strtoull(env, nullptr, 10); if (v && v < budget) budget = v; }
@@ -468,6 +551,28 @@ static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
     if (n < 1) n = 1;
     if (n > (size_t)ncol) n = (size_t)ncol;
     return (int)n;
+}
+
+/* host block (dense, ld = ldh) -> staging (dense, ld = Nd) -> internal layout, and back */
+static int upload_block(chefsi_ctx *ctx, const void *host, size_t ldh, int c0, int nc, void *dev, size_t esz, bool is_complex)
+{
+    const size_t row = ctx->Nd * esz;
+    CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_stage, row, (const char *)host + (size_t)c0 * ldh * esz, ldh * esz, row, nc,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+    const int n = launch_pack(ctx, ctx->d_stage, ctx->Nd, dev, nc, is_complex);
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    return 0;
+}
+static int download_block(chefsi_ctx *ctx, const void *dev, void *host, size_t ldh, int c0, int nc, size_t esz, bool is_complex)
+{
+    const size_t row = ctx->Nd * esz;
+    const int n = launch_unpack(ctx, dev, ctx->d_stage, ctx->Nd, nc, is_complex);
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)host + (size_t)c0 * ldh * esz, ldh * esz, ctx->d_stage, row, row, nc,
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
 }
 
 static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo, int ncol, int m, double a, double b,
@@ -480,19 +585,16 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
     const int chunk = chunk_columns(ctx, ncol, esz);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
-    const size_t row = ctx->Nd * esz;
+    if (ensure_stage(ctx, (size_t)chunk * ctx->Nd * esz)) return 1;
     double total_ms = 0;
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_buf[0], ctx->ld * esz, (const char *)X + (size_t)c0 * ldi * esz, ldi * esz,
-                                           row, nc, cudaMemcpyHostToDevice, ctx->stream));
+        if (upload_block(ctx, X, ldi, c0, nc, ctx->d_buf[0], esz, is_complex)) return 1;
         int ys = 1, xs = 0;
         if (filter_device(ctx, ctx->d_buf, nc, m, a, b, a0, is_complex, &ys, &xs)) return 1;
-        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Y + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_buf[ys], ctx->ld * esz, row, nc,
-                                           cudaMemcpyDeviceToHost, ctx->stream));
+        if (download_block(ctx, ctx->d_buf[ys], Y, ldo, c0, nc, esz, is_complex)) return 1;
         if (!(flags & CHEFSI_FLAG_NO_X_COPYBACK))
-            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)X + (size_t)c0 * ldi * esz, ldi * esz, ctx->d_buf[xs], ctx->ld * esz, row,
-                                               nc, cudaMemcpyDeviceToHost, ctx->stream));
+            if (download_block(ctx, ctx->d_buf[xs], X, ldi, c0, nc, esz, is_complex)) return 1;
         CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) total_ms += ms; else cudaGetLastError();
@@ -521,14 +623,12 @@ static int hmult_host(chefsi_ctx *ctx, int ncol, double c, const void *x, size_t
     const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
     const int chunk = chunk_columns(ctx, ncol, esz);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
-    const size_t row = ctx->Nd * esz;
+    if (ensure_stage(ctx, (size_t)chunk * ctx->Nd * esz)) return 1;
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_buf[0], ctx->ld * esz, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz,
-                                           row, nc, cudaMemcpyHostToDevice, ctx->stream));
+        if (upload_block(ctx, x, ldi, c0, nc, ctx->d_buf[0], esz, is_complex)) return 1;
         if (hmult_device(ctx, nc, c, ctx->d_buf[0], ctx->d_buf[1], is_complex)) return 1;
-        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Hx + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_buf[1], ctx->ld * esz, row, nc,
-                                           cudaMemcpyDeviceToHost, ctx->stream));
+        if (download_block(ctx, ctx->d_buf[1], Hx, ldo, c0, nc, esz, is_complex)) return 1;
         CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return 0;
@@ -551,8 +651,32 @@ extern "C" int chefsi_fill_random_device(chefsi_ctx_t *ctx, void *buf, int ncol,
     if (!ctx) return 1;
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t mul = is_complex ? 2 : 1;
-    const int n = launch_fill_random(ctx, (double *)buf, ctx->Nd * mul, ctx->ld * mul, ncol, first_col, seed);
+    const int n = launch_fill_random(ctx, buf, ncol, first_col, seed, is_complex != 0);
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    return 0;
+}
+
+extern "C" int chefsi_pack_device(chefsi_ctx_t *ctx, const void *dense, size_t ld_dense, void *packed, int ncol,
+                                  int is_complex)
+{
+    if (!ctx) return 1;
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ld_dense < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = launch_pack(ctx, dense, ld_dense, packed, ncol, is_complex != 0);
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    return 0;
+}
+extern "C" int chefsi_unpack_device(chefsi_ctx_t *ctx, const void *packed, void *dense, size_t ld_dense, int ncol,
+                                    int is_complex)
+{
+    if (!ctx) return 1;
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ld_dense < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = launch_unpack(ctx, packed, dense, ld_dense, ncol, is_complex != 0);
     if (n < 0) return 1;
     ctx->stats.kernel_launches += n;
     return 0;

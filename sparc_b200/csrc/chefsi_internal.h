@@ -21,7 +21,25 @@ struct MixedComp {
     double wm[CHEFSI_MAXR + 1]; /* already scaled by a = -1/2 */
 };
 
+/* Device-resident layout of one orbital column ("internal layout").
+ * Grid point (i,j,k) lives at ((k*Nyp + j+py)*Nxp + i+px).  For grids that qualify for the streaming
+ * kernel the xy-planes carry a halo pad (px = 8, py = 6) that holds the periodic images (or zeros on
+ * Dirichlet faces), so that a haloed tile of a plane is ONE in-bounds TMA box; otherwise px = py = 0
+ * and the layout is the reference's dense x-fastest one.  Columns are ld elements apart. */
+struct Layout {
+    int Nx, Ny, Nz;
+    int px, py;
+    int Nxp, Nyp;
+    size_t plane;   /* Nxp * Nyp */
+    size_t ld;      /* elements between columns (>= plane * Nz, multiple of 16) */
+};
+__host__ __device__ __forceinline__ size_t lay_pos(const Layout &L, int i, int j, int k)
+{
+    return ((size_t)k * L.Nyp + (j + L.py)) * L.Nxp + (i + L.px);
+}
+
 struct StencilDesc {
+    Layout lay;
     int Nx, Ny, Nz;
     int bc[3];
     int F;
@@ -63,6 +81,9 @@ struct NlocDev {
     /* host copies needed to rebuild phases */
     double *h_img_coords = nullptr;
     long long total_pts = 0;
+    /* sphere points whose value is mirrored in a halo pad: (src, dst) positions in the internal layout */
+    int *patch_src = nullptr, *patch_dst = nullptr, *patch_ph = nullptr;
+    int n_patch = 0;
 };
 
 struct chefsi_ctx {
@@ -73,7 +94,11 @@ struct chefsi_ctx {
     chefsi_grid_t grid{};
     StencilDesc desc{};
     size_t Nd = 0, ld = 0;
-    double *d_veff = nullptr;
+    Layout lay{};
+    double *d_veff = nullptr;    /* Veff in the internal layout (one column) */
+    double *d_zero = nullptr;    /* unused spare */
+    void *d_stage = nullptr;     /* dense staging block for host<->device transfers */
+    size_t stage_bytes = 0;
     bool have_veff = false;
     NlocDev nl;
     double kvec[3] = {0, 0, 0};
@@ -103,6 +128,7 @@ int chefsi_fail(chefsi_ctx *ctx, const char *fmt, ...);
 
 /* ---- kernel launchers (each returns the number of kernels it launched, <0 on error) --- */
 int launch_stencil_general(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
+bool stream_layout_wanted(const chefsi_grid_t &g);
 bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex);
 int launch_stencil_stream_orth(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
 
@@ -111,7 +137,16 @@ int launch_stencil_stream_orth(chefsi_ctx *ctx, const StepArgs &a, bool is_compl
 int launch_nloc_apply(chefsi_ctx *ctx, const void *x, void *out, size_t ld, int ncol, double scale,
                       bool is_complex);
 
-int launch_fill_random(chefsi_ctx *ctx, double *buf, size_t n_per_col, size_t ld_doubles, int ncol,
-                       long long first_col, unsigned long long seed);
+int launch_nloc_halo_patch(chefsi_ctx *ctx, void *out, size_t ld, int ncol, bool is_complex);
+
+/* util.cu */
+int launch_fill_random(chefsi_ctx *ctx, void *buf, int ncol, long long first_col, unsigned long long seed,
+                       bool is_complex);
+/* dense (ld_dense elements between columns, Nd used) <-> internal layout */
+int launch_pack(chefsi_ctx *ctx, const void *dense, size_t ld_dense, void *packed, int ncol, bool is_complex);
+int launch_unpack(chefsi_ctx *ctx, const void *packed, void *dense, size_t ld_dense, int ncol, bool is_complex);
+/* fill the halo pads of ncol columns: periodic images (times Bloch phase if complex) or zeros;
+ * zero_only = 1 just clears them (scratch buffers on Dirichlet faces) */
+int launch_halo_prepare(chefsi_ctx *ctx, void *buf, int ncol, bool is_complex, int zero_only);
 
 #endif

@@ -59,7 +59,7 @@ stencil_general_kernel(const __grid_constant__ StencilDesc d, const StepArgs a, 
                           i < 0 || i >= Nx || j < 0 || j >= Ny || k < 0 || k >= Nz;
         T v = cplx::zero<T>();
         if (!dead) {
-            v = x[(size_t)k * Nx * Ny + (size_t)j * Nx + i];
+            v = x[lay_pos(d.lay, i, j, k)];
             if (cplx::is_complex<T>::value && (ox | oy | oz)) {
                 const int q = (oz + 1) * 9 + (oy + 1) * 3 + (ox + 1);
                 v = cplx::mul_phase(v, d.ph_re[q], d.ph_im[q]);
@@ -113,7 +113,7 @@ stencil_general_kernel(const __grid_constant__ StencilDesc d, const StepArgs a, 
         const int i = x0 + lx, j = y0 + ly, k = z0 + lz;
         if (i >= Nx || j >= Ny || k >= Nz) continue;
         const int p = (lz + F) * EXY + (ly + F) * EX + (lx + F);
-        const size_t g = (size_t)k * Nx * Ny + (size_t)j * Nx + i;
+        const size_t g = lay_pos(d.lay, i, j, k);
         const T xc = f[p];
         T res = cplx::mul(xc, diag0);
 #pragma unroll

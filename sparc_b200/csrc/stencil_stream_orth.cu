@@ -9,44 +9,54 @@
  * with ONE pass that reads x and xprev once and writes out once (24 B per grid point).
  *
  * Design (2.5-D streaming, one persistent CTA per SM):
+ *   - columns live in the halo-padded internal layout (chefsi_internal.h: Layout), so the haloed
+ *     TX+12 x TY+12 tile of any xy-plane is one in-bounds box of a 4-D tensor map (x, y, z, column);
  *   - a work item is (orbital column, TX x TY tile of the xy-plane); the CTA marches the whole z
  *     extent of the item, so halos are re-read only in x/y, and neighbouring tiles of a column are
  *     in flight on other SMs at the same time, which turns those re-reads into L2 hits;
- *   - a dedicated producer warp stages each z-plane of the tile (+6-point halo) in a 4-deep shared
- *     memory ring with TMA bulk copies (cp.async.bulk -> UBLKCP), one per row segment, completion
- *     on an mbarrier; periodic wrap is done by the copy addresses (no materialised halo array),
- *     Dirichlet faces copy from a zero page;
- *   - 16x8-point warps: a thread owns 4 consecutive x of one row (vectorised 16 B smem loads,
- *     32 B global accesses); the row pitch is padded so every LDS.128 wavefront is conflict free;
+ *   - a producer warp streams, per z-plane, three TMA boxes (cp.async.bulk.tensor -> UTMALDG) into a
+ *     kStages-deep shared-memory ring: the haloed x tile of plane p, the Veff tile of plane p and the
+ *     xprev tile of plane p-6 (the plane whose result is completed by plane p); completion is counted
+ *     on an mbarrier per stage, consumers release a stage through a second mbarrier;
+ *   - 16x8-point warps: a thread owns 4 consecutive x of one row (16 B shared loads, 32 B global
+ *     stores); box widths are chosen so that every row pitch is an odd number of 16-byte chunks, which
+ *     makes every LDS.128 wavefront of this thread layout bank-conflict free;
  *   - the z direction never touches shared memory: each thread keeps the last 6 input planes and
  *     7 partial output accumulators of its 4 points in registers (scatter form: a plane adds its
  *     own x/y terms and the z terms of the 6 planes behind it when it arrives, and is added into
  *     the 6 accumulators behind it); the plane loop is unrolled by 7 so the register queues rotate
  *     by renaming instead of moves;
  *   - Veff, c, the recurrence scale s1 and the -s2*xprev term are applied in registers; the result
- *     plane (6 behind the one just loaded) is written with 256-bit stores.
+ *     plane (6 behind the one just loaded) is written with 256-bit stores, together with its periodic
+ *     images in the halo pads (the next step's TMA boxes read them; Dirichlet pads stay zero).
  */
+#include <cuda.h>
+
 #include "chefsi_internal.h"
 
 namespace {
 
 constexpr int R = 6;        /* FD radius this kernel is specialised for (FD_ORDER 12) */
-constexpr int kStages = 4;  /* shared memory ring depth */
+constexpr int kStages = 5;  /* shared memory ring depth */
 
 template <int WX, int WY> struct TileCfg {
     static constexpr int TX = 16 * WX;           /* tile width  (points) */
     static constexpr int TY = 8 * WY;            /* tile height (points) */
-    static constexpr int PITCH = TX + 2 * R + 2; /* doubles; (PITCH/2) odd -> conflict-free LDS.128 */
-    static constexpr int ROWS = TY + 2 * R;
-    static constexpr int PLANE = PITCH * ROWS;   /* doubles per ring slot */
+    static constexpr int YP = TX + 2 * R + 2;    /* haloed tile pitch (doubles): odd number of 16 B chunks */
+    static constexpr int YROWS = TY + 2 * R;
+    static constexpr int XP = TX + 2;            /* xprev / Veff tile pitch */
+    static constexpr int Y_BYTES = ((YP * YROWS * 8 + 127) / 128) * 128;
+    static constexpr int X_BYTES = ((XP * TY * 8 + 127) / 128) * 128;
+    static constexpr int STAGE_BYTES = Y_BYTES + 2 * X_BYTES;
     static constexpr int CONSUMER_WARPS = WX * WY;
     static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
-    static constexpr size_t SMEM = (size_t)kStages * PLANE * sizeof(double) + 2 * kStages * sizeof(unsigned long long);
-    static_assert((PITCH / 2) % 2 == 1, "row pitch must be an odd number of 16-byte chunks");
+    static constexpr size_t SMEM = (size_t)kStages * STAGE_BYTES + 2 * kStages * sizeof(unsigned long long);
+    static_assert((YP / 2) % 2 == 1 && (XP / 2) % 2 == 1, "row pitches must be an odd number of 16-byte chunks");
 };
 
 struct StreamDesc {
     int Nx, Ny, Nz;
+    int Nxp, Nyp, px, py;
     int bc[3];
     int ntx, nty;
     double coef0;
@@ -81,76 +91,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}\n" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
-/* TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier */
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+/* TMA tiled load of one 4-D box (x, y, z, column), completion counted in bytes on an mbarrier */
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void ldg256(const double *p, double (&v)[4])
-{
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
-                 : "l"(p));
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void stg256(double *p, const double (&v)[4])
 {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 
-/* ---- producer: stage one haloed plane ---------------------------------------------------- */
-template <class Cfg>
-__device__ __forceinline__ void produce_plane(const StreamDesc &d, const double *__restrict__ col,
-                                              const double *__restrict__ zero_page, int x0, int y0, int kz,
-                                              int txe, double *slot, uint64_t *full, int lane)
-{
-    const int Lh = txe + 2 * R; /* haloed row length actually used */
-    const int nrows = min(Cfg::TY, d.Ny - y0) + 2 * R;
-    if (lane == 0) mbar_expect_tx(full, (uint32_t)(nrows * Lh * sizeof(double)));
-    __syncwarp();
-    for (int r = lane; r < nrows; r += 32) {
-        int j = y0 - R + r;
-        bool dead_row = false;
-        if (j < 0) { j += d.Ny; dead_row = d.bc[1]; } else if (j >= d.Ny) { j -= d.Ny; dead_row = d.bc[1]; }
-        const double *src_row = col + ((size_t)kz * d.Ny + j) * d.Nx;
-        double *dst = slot + r * Cfg::PITCH;
-        int t0 = 0;
-        while (t0 < Lh) {
-            int gx = x0 - R + t0;
-            bool dead = dead_row;
-            int len;
-            if (gx < 0) { len = min(Lh - t0, -gx); gx += d.Nx; dead |= (d.bc[0] != 0); }
-            else if (gx >= d.Nx) { len = Lh - t0; gx -= d.Nx; dead |= (d.bc[0] != 0); }
-            else { len = min(Lh - t0, d.Nx - gx); }
-            bulk_g2s(dst + t0, dead ? zero_page : src_row + gx, (uint32_t)(len * sizeof(double)), full);
-            t0 += len;
-        }
-    }
-}
-
 /* ---- one plane step of a consumer thread -------------------------------------------------- */
-/* U = p mod 7 (compile time): register-queue rotation by renaming.                            */
+/* U = (p + 7) mod 7 (compile time): register-queue rotation by renaming.                      */
 template <class Cfg, int U>
-__device__ __forceinline__ void consume_plane(const StreamDesc &d, const StepArgs &a, const double *slot, int p,
-                                              bool active, int qx, int ry, size_t gplane_off, size_t row_off,
-                                              const double *__restrict__ veff, const double *__restrict__ xprev,
-                                              double *__restrict__ out, double (&in)[7][4], double (&acc)[7][4],
-                                              bool plane_is_zero)
+__device__ __forceinline__ void consume_plane(const StreamDesc &d, const StepArgs &a, const unsigned char *stage, int p,
+                                              bool active, int qx, int ry, double *__restrict__ out_row,
+                                              size_t plane_elems, int img_x, int img_y, double (&in)[7][4],
+                                              double (&acc)[7][4], bool plane_is_zero)
 {
     const int Nz = d.Nz;
     const bool interior = (p >= 0) && (p < Nz);
-    /* issue the global loads of this step early */
-    double ve[4] = {0, 0, 0, 0}, xp[4] = {0, 0, 0, 0};
     const int o = p - R;
     const bool emit = active && o >= 0 && o < Nz;
-    if (active && interior && veff) ldg256(veff + (size_t)p * gplane_off + row_off, ve);
-    if (emit && a.s2 != 0.0) ldg256(xprev + (size_t)o * gplane_off + row_off, xp);
+    const double *ytile = reinterpret_cast<const double *>(stage);
+    const double *vtile = reinterpret_cast<const double *>(stage + Cfg::Y_BYTES);
+    const double *xtile = reinterpret_cast<const double *>(stage + Cfg::Y_BYTES + Cfg::X_BYTES);
 
     double v[4] = {0, 0, 0, 0};
     if (active && !plane_is_zero) {
-        const double *rowp = slot + (ry + R) * Cfg::PITCH + 4 * qx; /* haloed row, element 0 = x0-6+4qx */
+        const double *rowp = ytile + (ry + R) * Cfg::YP + 4 * qx; /* haloed row, element 0 = x0-6+4qx */
         if (interior) {
             double xr[16];
 #pragma unroll
@@ -159,33 +132,47 @@ __device__ __forceinline__ void consume_plane(const StreamDesc &d, const StepArg
                 xr[2 * t] = w.x;
                 xr[2 * t + 1] = w.y;
             }
-            double t4[4];
+            double ve[4] = {0, 0, 0, 0};
+            if (a.veff) {
+                const double2 w0 = *reinterpret_cast<const double2 *>(vtile + ry * Cfg::XP + 4 * qx);
+                const double2 w1 = *reinterpret_cast<const double2 *>(vtile + ry * Cfg::XP + 4 * qx + 2);
+                ve[0] = w0.x; ve[1] = w0.y; ve[2] = w1.x; ve[3] = w1.y;
+            }
+            double t4[4], sx[4], sy[4], sz[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 v[j] = xr[R + j];
                 t4[j] = (d.coef0 + a.c + ve[j]) * v[j];
+                sx[j] = d.wx[1] * (xr[R + j - 1] + xr[R + j + 1]);
+                sz[j] = d.wz[1] * in[(U - 1 + 7) % 7][j];
             }
 #pragma unroll
-            for (int r = 1; r <= R; r++)
+            for (int r = 2; r <= R; r++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) t4[j] = fma(d.wx[r], xr[R + j - r] + xr[R + j + r], t4[j]);
+                for (int j = 0; j < 4; j++) {
+                    sx[j] = fma(d.wx[r], xr[R + j - r] + xr[R + j + r], sx[j]);
+                    sz[j] = fma(d.wz[r], in[(U - r + 7) % 7][j], sz[j]);
+                }
 #pragma unroll
             for (int r = 1; r <= R; r++) {
-                const double2 u0 = *reinterpret_cast<const double2 *>(rowp - r * Cfg::PITCH + R);
-                const double2 u1 = *reinterpret_cast<const double2 *>(rowp - r * Cfg::PITCH + R + 2);
-                const double2 d0 = *reinterpret_cast<const double2 *>(rowp + r * Cfg::PITCH + R);
-                const double2 d1 = *reinterpret_cast<const double2 *>(rowp + r * Cfg::PITCH + R + 2);
-                t4[0] = fma(d.wy[r], u0.x + d0.x, t4[0]);
-                t4[1] = fma(d.wy[r], u0.y + d0.y, t4[1]);
-                t4[2] = fma(d.wy[r], u1.x + d1.x, t4[2]);
-                t4[3] = fma(d.wy[r], u1.y + d1.y, t4[3]);
+                const double2 u0 = *reinterpret_cast<const double2 *>(rowp - r * Cfg::YP + R);
+                const double2 u1 = *reinterpret_cast<const double2 *>(rowp - r * Cfg::YP + R + 2);
+                const double2 d0 = *reinterpret_cast<const double2 *>(rowp + r * Cfg::YP + R);
+                const double2 d1 = *reinterpret_cast<const double2 *>(rowp + r * Cfg::YP + R + 2);
+                if (r == 1) {
+                    sy[0] = d.wy[1] * (u0.x + d0.x);
+                    sy[1] = d.wy[1] * (u0.y + d0.y);
+                    sy[2] = d.wy[1] * (u1.x + d1.x);
+                    sy[3] = d.wy[1] * (u1.y + d1.y);
+                } else {
+                    sy[0] = fma(d.wy[r], u0.x + d0.x, sy[0]);
+                    sy[1] = fma(d.wy[r], u0.y + d0.y, sy[1]);
+                    sy[2] = fma(d.wy[r], u1.x + d1.x, sy[2]);
+                    sy[3] = fma(d.wy[r], u1.y + d1.y, sy[3]);
+                }
             }
 #pragma unroll
-            for (int r = 1; r <= R; r++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) t4[j] = fma(d.wz[r], in[(U - r + 7) % 7][j], t4[j]);
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[U][j] = t4[j];
+            for (int j = 0; j < 4; j++) acc[U][j] = (t4[j] + sx[j]) + (sy[j] + sz[j]);
         } else {
             const double2 w0 = *reinterpret_cast<const double2 *>(rowp + R);
             const double2 w1 = *reinterpret_cast<const double2 *>(rowp + R + 2);
@@ -203,21 +190,35 @@ __device__ __forceinline__ void consume_plane(const StreamDesc &d, const StepArg
 
     if (emit) {
         double res[4];
+        if (a.s2 != 0.0) {
+            const double2 w0 = *reinterpret_cast<const double2 *>(xtile + ry * Cfg::XP + 4 * qx);
+            const double2 w1 = *reinterpret_cast<const double2 *>(xtile + ry * Cfg::XP + 4 * qx + 2);
+            res[0] = fma(-a.s2, w0.x, a.s1 * acc[(U + 1) % 7][0]);
+            res[1] = fma(-a.s2, w0.y, a.s1 * acc[(U + 1) % 7][1]);
+            res[2] = fma(-a.s2, w1.x, a.s1 * acc[(U + 1) % 7][2]);
+            res[3] = fma(-a.s2, w1.y, a.s1 * acc[(U + 1) % 7][3]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) res[j] = fma(-a.s2, xp[j], a.s1 * acc[(U + 1) % 7][j]);
-        stg256(out + (size_t)o * gplane_off + row_off, res);
+            for (int j = 0; j < 4; j++) res[j] = a.s1 * acc[(U + 1) % 7][j];
+        }
+        double *dst = out_row + (size_t)o * plane_elems;
+        stg256(dst, res);
+        /* periodic images into the halo pads (img_x / img_y: element offsets, 0 = none) */
+        if (img_x) stg256(dst + img_x, res);
+        if (img_y) stg256(dst + img_y, res);
     }
 }
 
 template <int WX, int WY>
 __global__ void __launch_bounds__(TileCfg<WX, WY>::THREADS, 1)
-stream_orth_kernel(const __grid_constant__ StreamDesc d, const StepArgs a, const double *__restrict__ zero_page,
+stream_orth_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xprev,
+                   const __grid_constant__ CUtensorMap map_veff, const __grid_constant__ StreamDesc d, const StepArgs a,
                    const int nitems)
 {
     using Cfg = TileCfg<WX, WY>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *ring = reinterpret_cast<double *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kStages * Cfg::PLANE);
+    unsigned char *ring = smem_raw;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kStages * Cfg::STAGE_BYTES);
     uint64_t *empty = full + kStages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,24 +233,36 @@ stream_orth_kernel(const __grid_constant__ StreamDesc d, const StepArgs a, const
 
     const int Nz = d.Nz;
     const bool zper = (d.bc[2] == 0);
-    const size_t plane_elems = (size_t)d.Nx * d.Ny;
+    const size_t plane_elems = (size_t)d.Nxp * d.Nyp;
     uint32_t it = 0; /* ring position, continues across work items */
 
     if (warp == Cfg::CONSUMER_WARPS) {
-        /* ================= producer warp ================= */
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
-            const int x0 = (tile % d.ntx) * Cfg::TX, y0 = (tile / d.ntx) * Cfg::TY;
-            const int txe = min(Cfg::TX, d.Nx - x0);
-            const double *col = reinterpret_cast<const double *>(a.x) + (size_t)n * a.ld;
-            for (int p = -R; p < Nz + R; p++) {
-                int kz = p;
-                if (p < 0) { if (!zper) continue; kz += Nz; }
-                else if (p >= Nz) { if (!zper) continue; kz -= Nz; }
-                const int s = it % kStages;
-                mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
-                produce_plane<Cfg>(d, col, zero_page, x0, y0, kz, txe, ring + (size_t)s * Cfg::PLANE, &full[s], lane);
-                it++;
+        /* ================= producer warp (one elected lane issues the TMA boxes) ================= */
+        if (lane == 0) {
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
+                const int x0 = (tile % d.ntx) * Cfg::TX, y0 = (tile / d.ntx) * Cfg::TY;
+                for (int p = -R; p < Nz + R; p++) {
+                    int kz = p;
+                    const bool interior = (p >= 0 && p < Nz);
+                    if (p < 0) kz += Nz; else if (p >= Nz) kz -= Nz;
+                    const int o = p - R;
+                    const bool need_y = interior || zper;          /* Dirichlet z: planes outside are zero */
+                    const bool need_v = interior && a.veff != nullptr;
+                    const bool need_x = (o >= 0 && o < Nz) && a.s2 != 0.0;
+                    if (!need_y && !need_x) continue;
+                    const int s = it % kStages;
+                    unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
+                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], (uint32_t)((need_y ? Cfg::YP * Cfg::YROWS * 8 : 0) +
+                                                        (need_v ? Cfg::XP * Cfg::TY * 8 : 0) +
+                                                        (need_x ? Cfg::XP * Cfg::TY * 8 : 0)));
+                    if (need_y) tma_load_4d(stage, &map_x, d.px + x0 - R, d.py + y0 - R, kz, n, &full[s]);
+                    if (need_v) tma_load_4d(stage + Cfg::Y_BYTES, &map_veff, d.px + x0, d.py + y0, p, 0, &full[s]);
+                    if (need_x)
+                        tma_load_4d(stage + Cfg::Y_BYTES + Cfg::X_BYTES, &map_xprev, d.px + x0, d.py + y0, o, n, &full[s]);
+                    it++;
+                }
             }
         }
     } else {
@@ -257,16 +270,18 @@ stream_orth_kernel(const __grid_constant__ StreamDesc d, const StepArgs a, const
         const int wx = warp % WX, wy = warp / WX;
         const int qx = wx * 4 + (lane & 3); /* quad index along x inside the tile */
         const int ry = wy * 8 + (lane >> 2); /* row inside the tile                */
-        const double *veff = a.veff;
         double in[7][4], acc[7][4];
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
             const int x0 = (tile % d.ntx) * Cfg::TX, y0 = (tile / d.ntx) * Cfg::TY;
             const int gx = x0 + 4 * qx, gy = y0 + ry;
             const bool active = (gx < d.Nx) && (gy < d.Ny);
-            const size_t row_off = (size_t)gy * d.Nx + gx;
-            const double *xprev = reinterpret_cast<const double *>(a.xprev) + (size_t)n * a.ld;
-            double *out = reinterpret_cast<double *>(a.out) + (size_t)n * a.ld;
+            double *out_row = reinterpret_cast<double *>(a.out) + (size_t)n * a.ld +
+                              ((size_t)(gy + d.py)) * d.Nxp + (gx + d.px);
+            /* where this thread's quad is mirrored in the halo pads (periodic faces only) */
+            int img_x = 0, img_y = 0;
+            if (d.bc[0] == 0) { if (gx < d.px) img_x = d.Nx; else if (gx >= d.Nx - d.px) img_x = -d.Nx; }
+            if (d.bc[1] == 0) { if (gy < d.py) img_y = d.Ny * d.Nxp; else if (gy >= d.Ny - d.py) img_y = -d.Ny * d.Nxp; }
 #pragma unroll
             for (int u = 0; u < 7; u++)
 #pragma unroll
@@ -275,25 +290,26 @@ stream_orth_kernel(const __grid_constant__ StreamDesc d, const StepArgs a, const
 #define CHEFSI_STEP(U)                                                                                   \
     if (p + (U) < Nz + R) {                                                                              \
         const int pp = p + (U);                                                                          \
-        const bool zplane = !zper && (pp < 0 || pp >= Nz);                                               \
-        const double *slot = ring;                                                                       \
+        const bool zplane = !zper && (pp < 0 || pp >= Nz);   /* Dirichlet z: the plane is zero */        \
+        const bool use_stage = !zplane || (pp - R >= 0 && pp - R < Nz && a.s2 != 0.0);                   \
+        const unsigned char *stage = ring;                                                               \
         int s = 0;                                                                                       \
-        if (!zplane) {                                                                                   \
+        if (use_stage) {                                                                                 \
             s = it % kStages;                                                                            \
-            slot = ring + (size_t)s * Cfg::PLANE;                                                        \
+            stage = ring + (size_t)s * Cfg::STAGE_BYTES;                                                 \
             mbar_wait(&full[s], (it / kStages) & 1);                                                     \
         }                                                                                                \
-        consume_plane<Cfg, (U)>(d, a, slot, pp, active, qx, ry, plane_elems, row_off, veff, xprev, out,  \
+        consume_plane<Cfg, (U)>(d, a, stage, pp, active, qx, ry, out_row, plane_elems, img_x, img_y,     \
                                 in, acc, zplane);                                                        \
-        if (!zplane) {                                                                                   \
+        if (use_stage) {                                                                                 \
             __syncwarp();                                                                                \
             if (lane == 0) mbar_arrive(&empty[s]);                                                       \
             it++;                                                                                        \
         }                                                                                                \
     }
-            /* p runs over -6 .. Nz+5; the phase U = (p + 7) mod 7 is compile-time inside the unrolled body */
+            /* p runs over -6 .. Nz+5; groups start at p = -7 so that the phase U == (pp + 7) % 7 is
+               compile-time inside the unrolled body (pp = -7 itself is skipped) */
             for (int p = -R - 1; p < Nz + R; p += 7) {
-                /* first group starts at p = -7 so that U == (pp + 7) % 7; pp = -7 itself is skipped */
                 if (p + 0 >= -R) { CHEFSI_STEP(0) }
                 CHEFSI_STEP(1)
                 CHEFSI_STEP(2)
@@ -307,13 +323,47 @@ stream_orth_kernel(const __grid_constant__ StreamDesc d, const StepArgs a, const
     }
 }
 
+/* ---- host side ---------------------------------------------------------------------------- */
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+/* 4-D view (x, y, z, column) of a block of columns in the internal layout */
+bool make_map(CUtensorMap *map, const void *base, const Layout &L, int ncol, int box_x, int box_y)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)L.Nxp, (cuuint64_t)L.Nyp, (cuuint64_t)L.Nz, (cuuint64_t)(ncol > 0 ? ncol : 1)};
+    cuuint64_t strides[3] = {(cuuint64_t)L.Nxp * 8, (cuuint64_t)L.plane * 8, (cuuint64_t)L.ld * 8};
+    cuuint32_t box[4] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int WX, int WY>
-int launch_cfg(chefsi_ctx *ctx, const StepArgs &a, const double *zero_page)
+int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
 {
     using Cfg = TileCfg<WX, WY>;
     const chefsi_grid_t &g = ctx->grid;
+    const Layout &L = ctx->lay;
     StreamDesc d;
     d.Nx = g.Nx; d.Ny = g.Ny; d.Nz = g.Nz;
+    d.Nxp = L.Nxp; d.Nyp = L.Nyp; d.px = L.px; d.py = L.py;
     d.bc[0] = g.BCx; d.bc[1] = g.BCy; d.bc[2] = g.BCz;
     d.ntx = (g.Nx + Cfg::TX - 1) / Cfg::TX;
     d.nty = (g.Ny + Cfg::TY - 1) / Cfg::TY;
@@ -321,11 +371,19 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a, const double *zero_page)
     for (int r = 0; r <= R; r++) { d.wx[r] = ctx->desc.wx[r]; d.wy[r] = ctx->desc.wy[r]; d.wz[r] = ctx->desc.wz[r]; }
     const long long nitems = (long long)a.ncol * d.ntx * d.nty;
     if (nitems > 0x7fffffffLL) { chefsi_fail(ctx, "stream kernel: too many work items"); return -1; }
+
+    CUtensorMap mx, mp, mv;
+    const void *xp = a.xprev ? a.xprev : a.x; /* never dereferenced when s2 == 0 */
+    if (!make_map(&mx, a.x, L, a.ncol, Cfg::YP, Cfg::YROWS) || !make_map(&mp, xp, L, a.ncol, Cfg::XP, Cfg::TY) ||
+        !make_map(&mv, ctx->d_veff, L, 1, Cfg::XP, Cfg::TY)) {
+        chefsi_fail(ctx, "cuTensorMapEncodeTiled failed");
+        return -1;
+    }
     auto kern = stream_orth_kernel<WX, WY>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(stream): %s", cudaGetErrorString(e)); return -1; }
     const int grid = (int)((nitems < ctx->num_sms) ? nitems : ctx->num_sms);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(d, a, zero_page, (int)nitems);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(mx, mp, mv, d, a, (int)nitems);
     e = cudaGetLastError();
     if (e != cudaSuccess) { chefsi_fail(ctx, "stream kernel launch: %s", cudaGetErrorString(e)); return -1; }
     return 1;
@@ -334,25 +392,25 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a, const double *zero_page)
 }  // namespace
 
 /* The streaming kernel needs: orthogonal cell, FD radius 6, real data, Nx a multiple of 4 (each
- * thread owns an aligned quad and all TMA row segments must be 16-byte multiples), a leading
- * dimension that keeps columns 32-byte aligned, and a grid big enough that tiles are not mostly
- * halo.  Everything else goes through the general kernel. */
-bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex)
+ * thread owns an aligned quad; TMA strides must be 16-byte multiples), the halo-padded layout, and a
+ * grid big enough that tiles are not mostly halo.  Everything else goes through the general kernel. */
+bool stream_layout_wanted(const chefsi_grid_t &g)
 {
-    const chefsi_grid_t &g = ctx->grid;
-    if (ctx->force_general) return false;
-    if (is_complex) return false;
     if (g.cell_typ != 0 || g.FDn != R) return false;
-    if (g.Nx % 4 != 0 || ctx->ld % 4 != 0) return false;
+    if (g.Nx % 4 != 0) return false;
     if (g.Nx < 32 || g.Ny < 16 || g.Nz < 2 * R) return false;
     return true;
+}
+
+bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex)
+{
+    if (ctx->force_general || is_complex) return false;
+    return ctx->lay.px == 8 && ctx->lay.py == R && stream_layout_wanted(ctx->grid);
 }
 
 int launch_stencil_stream_orth(chefsi_ctx *ctx, const StepArgs &a, bool is_complex)
 {
     (void)is_complex;
     if (a.ncol <= 0) return 0;
-    /* zero page for Dirichlet halos: the tail of the Veff allocation is kept zeroed by set_grid */
-    const double *zero_page = ctx->d_veff + ctx->ld;
-    return launch_cfg<2, 4>(ctx, a, zero_page);
+    return launch_cfg<2, 4>(ctx, a);
 }

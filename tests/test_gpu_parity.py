@@ -192,7 +192,7 @@ def test_full_size_plane_wave_and_linearity(ctx):
         sigma2 = 1.0 / (gamma - sigma)
         t_prev, t = t, (2 * sigma2 / e) * (lam - c) * t - sigma * sigma2 * t_prev
         sigma = sigma2
-    X = np.ascontiguousarray(pw)
+    X = pw.copy()
     Y = np.empty_like(X)
     ctx.ChebyshevFiltering(X, Y, m, a, b, a0)
     assert ctx.stats()["last_path"] == 1
@@ -213,13 +213,22 @@ def test_device_resident_entry_point_and_rng(ctx, port):
     ld = ctx.device_ld
     ncol = 4
     bufs = [torch.zeros(ncol * ld, dtype=torch.float64, device="cuda") for _ in range(3)]
+    dense = torch.zeros((ncol, g.Nd), dtype=torch.float64, device="cuda")
+
+    def unpack(buf):
+        ctx.unpack_device(buf, dense, g.Nd, ncol)
+        ctx.synchronize()
+        return dense.cpu().numpy()
+
     ctx.fill_random_device(bufs[0], ncol, first_col=7, seed=3)
-    ctx.synchronize()
-    x = bufs[0].view(ncol, ld)[:, :g.Nd].cpu().numpy()
+    x = unpack(bufs[0])
     assert np.array_equal(x, P.random_columns(g.Nd, ncol, first_col=7, seed=3))
     a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
     ys, xs = ctx.filter_device(bufs[0], bufs[1], bufs[2], ncol, 7, a, b, a0)
     ctx.synchronize()
     Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 7, a, b, a0)
-    assert rel_fro(bufs[ys].view(ncol, ld)[:, :g.Nd].cpu().numpy(), Yw) < TOL
-    assert rel_fro(bufs[xs].view(ncol, ld)[:, :g.Nd].cpu().numpy(), Xw) < TOL
+    assert rel_fro(unpack(bufs[ys]), Yw) < TOL
+    assert rel_fro(unpack(bufs[xs]), Xw) < TOL
+    # pack is the inverse of unpack
+    ctx.pack_device(dense, g.Nd, bufs[2], ncol)
+    assert np.array_equal(unpack(bufs[2]), dense.cpu().numpy())
