@@ -85,7 +85,7 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
 static void free_nloc(NlocDev &d)
 {
     cudaFree(d.IP_displ); cudaFree(d.gamma); cudaFree(d.img_atom); cudaFree(d.img_ndc);
-    cudaFree(d.pos_off); cudaFree(d.chi_off); cudaFree(d.grid_pos); cudaFree(d.chi);
+    cudaFree(d.pos_off); cudaFree(d.chiT_off); cudaFree(d.grid_pos); cudaFree(d.chiT); cudaFree(d.img_aoff);
     cudaFree(d.img_phase); cudaFree(d.atom_img_off); cudaFree(d.atom_img);
     cudaFree(d.patch_src); cudaFree(d.patch_dst); cudaFree(d.patch_ph);
     free(d.h_img_coords);
@@ -100,7 +100,8 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     free_nloc(ctx->nl);
     cudaFree(ctx->d_veff);
     for (int i = 0; i < 3; i++) cudaFree(ctx->d_buf[i]);
-    cudaFree(ctx->d_alpha);
+    cudaFree(ctx->d_alpha[0]);
+    cudaFree(ctx->d_alpha[1]);
     cudaFree(ctx->d_stage);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -282,7 +283,9 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
         const int np = nl->IP_displ[a + 1] - nl->IP_displ[a];
         if (np > d.max_nproj) d.max_nproj = np;
     }
-    const long long npos = nl->pos_off[nl->n_img], nchi = nl->chi_off[nl->n_img];
+    const long long npos = nl->pos_off[nl->n_img];
+    d.np_pad = nloc_padded_nproj(d.max_nproj);
+    if (d.np_pad < 0) return chefsi_fail(ctx, "projectors: more than 32 projectors per atom not supported");
     d.total_pts = npos;
     /* validate + overlap detection (decides whether the scatter needs atomics) */
     std::vector<unsigned char> seen(ctx->Nd, 0);
@@ -338,9 +341,30 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
     if (upload(ctx, &d.img_atom, nl->img_atom, (size_t)nl->n_img)) return 1;
     if (upload(ctx, &d.img_ndc, nl->img_ndc, (size_t)nl->n_img)) return 1;
     if (upload(ctx, &d.pos_off, nl->pos_off, (size_t)nl->n_img + 1)) return 1;
-    if (upload(ctx, &d.chi_off, nl->chi_off, (size_t)nl->n_img + 1)) return 1;
     if (upload(ctx, &d.grid_pos, ppos.data(), (size_t)npos)) return 1;
-    if (upload(ctx, &d.chi, nl->chi, (size_t)nchi)) return 1;
+    {   /* Chi per image transposed to point-major and zero-padded to np_pad projectors (what the nloc
+           kernel streams with 16-byte cp.async); per-image offsets of the alpha partials */
+        std::vector<long long> toff((size_t)nl->n_img + 1, 0);
+        std::vector<int> aoff((size_t)nl->n_img + 1, 0);
+        for (int J = 0; J < nl->n_img; J++) {
+            const int np = nl->IP_displ[nl->img_atom[J] + 1] - nl->IP_displ[nl->img_atom[J]];
+            toff[J + 1] = toff[J] + (long long)nl->img_ndc[J] * d.np_pad;
+            aoff[J + 1] = aoff[J] + np;
+        }
+        d.img_proj_total = aoff[nl->n_img];
+        std::vector<double> chiT((size_t)toff[nl->n_img], 0.0);
+        for (int J = 0; J < nl->n_img; J++) {
+            const int np = nl->IP_displ[nl->img_atom[J] + 1] - nl->IP_displ[nl->img_atom[J]];
+            const int ndc = nl->img_ndc[J];
+            const double *src = nl->chi + nl->chi_off[J];
+            double *dst = chiT.data() + toff[J];
+            for (int p = 0; p < np; p++)
+                for (int i = 0; i < ndc; i++) dst[(size_t)i * d.np_pad + p] = src[(size_t)p * ndc + i];
+        }
+        if (upload(ctx, &d.chiT_off, toff.data(), toff.size())) return 1;
+        if (upload(ctx, &d.img_aoff, aoff.data(), aoff.size())) return 1;
+        if (upload(ctx, &d.chiT, chiT.data(), chiT.size())) return 1;
+    }
     if (upload(ctx, &d.atom_img_off, off.data(), off.size())) return 1;
     if (upload(ctx, &d.atom_img, lst.data(), lst.size())) return 1;
     CHEFSI_CUDA(ctx, cudaMalloc((void **)&d.img_phase, sizeof(double2) * nl->n_img));
@@ -391,14 +415,26 @@ struct Profiler {
     }
 };
 
+/* One fused step  out = s1 * ((H_local + c) x + Vnl x) - s2 * xprev.
+ * nl_in : the alpha partials of x are already in ctx->d_alpha[cur] (left there by the previous step's
+ *         fused projector kernel); otherwise they are computed here from x.
+ * nl_out: after adding Vnl x, also project `out` for the next step (only legal when spheres are disjoint). */
 static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void *xprev, void *out, int ncol, double c,
-                      double s1, double s2, bool is_complex)
+                      double s1, double s2, bool is_complex, bool nl_in, bool nl_out)
 {
     StepArgs a;
     a.x = x; a.xprev = xprev; a.out = out;
     a.veff = ctx->have_veff ? ctx->d_veff : nullptr;
     a.ld = ctx->ld; a.ncol = ncol; a.c = c; a.s1 = s1; a.s2 = s2;
     int n;
+    const bool have_nl = ctx->nl.n_img > 0 && ctx->nl.ntot > 0;
+    if (have_nl && !nl_in) {
+        prof.begin(1);
+        n = launch_nloc(ctx, NLOC_PROJECT, const_cast<void *>(x), ctx->ld, ncol, 0.0, is_complex);
+        prof.end();
+        if (n < 0) return 1;
+        ctx->stats.kernel_launches += n;
+    }
     prof.begin(0);
     if (stream_orth_supported(ctx, is_complex)) {
         n = launch_stencil_stream_orth(ctx, a, is_complex);
@@ -410,15 +446,17 @@ static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void
     prof.end();
     if (n < 0) return 1;
     ctx->stats.kernel_launches += n;
-    prof.begin(1);
-    n = launch_nloc_apply(ctx, x, out, ctx->ld, ncol, s1, is_complex);
-    if (n > 0 && ctx->stats.last_path == 1) {
-        const int m2 = launch_nloc_halo_patch(ctx, out, ctx->ld, ncol, is_complex);
-        n = (m2 < 0) ? -1 : n + m2;
+    if (have_nl) {
+        prof.begin(1);
+        n = launch_nloc(ctx, nl_out ? NLOC_FUSED : NLOC_EXPAND, out, ctx->ld, ncol, s1, is_complex);
+        if (n > 0 && ctx->nl.overlap && ctx->stats.last_path == 1) { /* atomics path: refresh the pad images */
+            const int m2 = launch_nloc_halo_patch(ctx, out, ctx->ld, ncol, is_complex);
+            n = (m2 < 0) ? -1 : n + m2;
+        }
+        prof.end();
+        if (n < 0) return 1;
+        ctx->stats.kernel_launches += n;
     }
-    prof.end();
-    if (n < 0) return 1;
-    ctx->stats.kernel_launches += n;
     return 0;
 }
 
@@ -450,10 +488,14 @@ static int filter_device(chefsi_ctx *ctx, void *bufs[3], int ncol, int m, double
             }
         }
     }
-    if (apply_step(ctx, prof, bufs[X], nullptr, bufs[Y], ncol, -c, sigma1 / e, 0.0, is_complex)) return 1;
+    /* with disjoint spheres every step's projector kernel also projects its (final) output, so the
+       next step starts with alpha in hand: one stencil launch + one projector launch per degree */
+    const bool chain = !ctx->nl.overlap;
+    if (apply_step(ctx, prof, bufs[X], nullptr, bufs[Y], ncol, -c, sigma1 / e, 0.0, is_complex, false, chain && m > 1)) return 1;
     for (int j = 1; j < m; j++) {
         const double sigma2 = 1.0 / (gamma - sigma);
-        if (apply_step(ctx, prof, bufs[Y], bufs[X], bufs[W], ncol, -c, 2.0 * sigma2 / e, sigma * sigma2, is_complex)) return 1;
+        if (apply_step(ctx, prof, bufs[Y], bufs[X], bufs[W], ncol, -c, 2.0 * sigma2 / e, sigma * sigma2, is_complex,
+                       chain, chain && j < m - 1)) return 1;
         const int t = X; X = Y; Y = W; W = t;
         sigma = sigma2;
     }
@@ -491,7 +533,7 @@ static int hmult_device(chefsi_ctx *ctx, int ncol, double c, const void *x, void
         if (n < 0) return 1;
         ctx->stats.kernel_launches += n;
     }
-    const int rc = apply_step(ctx, prof, x, nullptr, Hx, ncol, c, 1.0, 0.0, is_complex);
+    const int rc = apply_step(ctx, prof, x, nullptr, Hx, ncol, c, 1.0, 0.0, is_complex, false, false);
     prof.finish();
     return rc;
 }
@@ -542,8 +584,8 @@ static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
 {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
-    free_b += 3 * ctx->buf_bytes + ctx->alpha_bytes + ctx->stage_bytes; /* what we already hold can be reused */
-    const size_t per_col = 3 * ctx->ld * esz + ctx->Nd * esz + (size_t)ctx->nl.ntot * esz;
+    free_b += 3 * ctx->buf_bytes + 2 * ctx->alpha_bytes + ctx->stage_bytes; /* what we already hold can be reused */
+    const size_t per_col = 3 * ctx->ld * esz + ctx->Nd * esz + 2 * (size_t)ctx->nl.img_proj_total * esz;
     size_t budget = (size_t)(0.85 * (double)free_b);
     const char *env = getenv("CHEFSI_B200_MAX_CHUNK_BYTES");
     if (env) { size_t v = strtoull(env, nullptr, 10); if (v && v < budget) budget = v; }

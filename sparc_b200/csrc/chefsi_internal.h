@@ -72,9 +72,12 @@ struct NlocDev {
     double *gamma = nullptr;   /* [ntot]     */
     int *img_atom = nullptr;   /* [n_img]    */
     int *img_ndc = nullptr;
-    long long *pos_off = nullptr, *chi_off = nullptr;
+    long long *pos_off = nullptr, *chiT_off = nullptr;
     int *grid_pos = nullptr;
-    double *chi = nullptr;
+    double *chiT = nullptr;       /* per image: ndc x np_pad, POINT-major (projector fastest), zero padded */
+    int *img_aoff = nullptr;      /* [n_img+1] prefix sum of nproj over images: per-image alpha partials */
+    int np_pad = 0;               /* projector padding the nloc kernels are instantiated for */
+    long long img_proj_total = 0; /* img_aoff[n_img] */
     double2 *img_phase = nullptr; /* [n_img] (cos theta, sin theta) for the current k-point */
     int *atom_img_off = nullptr;  /* CSR atom -> images */
     int *atom_img = nullptr;
@@ -105,7 +108,8 @@ struct chefsi_ctx {
     /* scratch owned by the host entry points */
     void *d_buf[3] = {nullptr, nullptr, nullptr};
     size_t buf_bytes = 0;
-    void *d_alpha = nullptr;
+    void *d_alpha[2] = {nullptr, nullptr}; /* per-image alpha partials: [cur] belongs to the current input */
+    int alpha_cur = 0;
     size_t alpha_bytes = 0;
     /* stats */
     chefsi_stats_t stats{};
@@ -132,10 +136,10 @@ bool stream_layout_wanted(const chefsi_grid_t &g);
 bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex);
 int launch_stencil_stream_orth(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
 
-/* alpha = dV * phase * Chi^T x   (per atom, summed over its images), then
- * out += scale * conj(phase) * Chi (Gamma .* alpha)                                         */
-int launch_nloc_apply(chefsi_ctx *ctx, const void *x, void *out, size_t ld, int ncol, double scale,
-                      bool is_complex);
+/* nloc.cu: see launch_nloc for the three modes */
+enum { NLOC_PROJECT = 0, NLOC_FUSED = 1, NLOC_EXPAND = 2 };
+int launch_nloc(chefsi_ctx *ctx, int mode, void *vec, size_t ld, int ncol, double scale, bool is_complex);
+int nloc_padded_nproj(int max_nproj);
 
 int launch_nloc_halo_patch(chefsi_ctx *ctx, void *out, size_t ld, int ncol, bool is_complex);
 

@@ -3,203 +3,275 @@
  *
  *   out += scale * Vnl x ,   Vnl x = sum_J conj(b_J) Chi_J Gamma ( sum_{J' of atom(J)} b_J' dV Chi_J'^T x[sphere_J'] )
  *
- * replacing Vnl_vec_mult (nlocVecRoutines.c:798-883) and Vnl_vec_mult_kpt (:889-999).  Both halves are
- * dense FP64 contractions (the reference calls dgemm/zgemm, :821,:872,:931,:988), so they run on the FP64
- * tensor cores (mma.sync m8n8k4 -> DMMA.8x8x4) with operand fragments loaded straight from global / L2:
- * the fragment shapes (8 rows x 4 consecutive elements) are exactly sector-sized runs of Chi and of the
- * gathered sphere points, so no shared-memory staging is needed.
+ * replacing Vnl_vec_mult (nlocVecRoutines.c:798-883) and Vnl_vec_mult_kpt (:889-999).
  *
- *   project  alpha[atom][col][proj] = dV * sum_images phase * Chi^T x[sphere]        (:807-831 / :908-941)
- *            one CTA per (atom, 64 columns); a warp owns 8 real (4 complex) columns and all projectors:
- *            C(8 proj x 8 col) += A(8 proj x 4 pts) * B(4 pts x 8 col) per DMMA.  All periodic images of an
- *            atom are reduced by the same warp, so alpha needs no atomics and is deterministic.
- *   expand   out[sphere] += scale * conj(phase) * Chi (Gamma .* alpha)     (:841-881 / :951-997)
- *            one CTA per (image, 64 columns); C(8 pts x 8 col) = sum_k A(8 pts x 4 proj) * B(4 proj x 8 col)
- *            with the Gamma-scaled alpha fragments preloaded in registers; results are added into `out`
- *            with FP64 atomics only when the setup pass found overlapping spheres (small cells, Si8).
- *   patch    sphere points that are mirrored in the halo pads of the internal layout get their image
- *            refreshed (only with the streaming layout on periodic faces).
+ * The first ncu capture of round 1 (profiles/r1_ncu_stream_nloc_summary.md) showed that the projector
+ * step is NOT compute-limited (FP64 pipe < 1 % active with the DMMA kernels of the first draft) but
+ * latency- and sector-limited by the sphere gather/scatter, and that the separate project and expand
+ * passes touched the sphere points three times per Chebyshev step.  So the contraction runs on the
+ * plain FP64 FMA pipe and the kernel is organised around the memory access instead:
  *
- * Complex data (k-points) reuses the same kernels: Chi is real (nlocVecRoutines.c:731), so a complex
- * column is two real MMA columns (re, im); the per-image Bloch factor is applied lane-locally because one
- * lane holds the (re, im) pair of an accumulator element.
+ *   one kernel, one CTA per (sphere image J, 32 real columns), marching the sphere in chunks of 64 points:
+ *     A  gather   lanes <-> sphere points (runs along x are contiguous), cp.async 8 B elements into a
+ *                 double-buffered shared tile V[column][point]; the Chi chunk (stored point-major,
+ *                 zero-padded to NP projectors at set_projectors time) arrives with 16 B cp.async;
+ *     B  contract lanes <-> columns, warps <-> points: a lane keeps beta[NP] = scale*Gamma*alpha_prev and
+ *                 acc[NP] in registers; per point one conflict-free LDS of V, NP/2 broadcast LDS.128 of
+ *                 Chi, NP FMAs "expand" (v += Chi beta), NP FMAs "project" (acc += Chi v);
+ *     C  scatter  lanes <-> points again, the updated tile goes back with coalesced stores, together
+ *                 with the periodic images in the halo pads of the streaming layout.
+ *   Modes: PROJECT (alpha of the input only), FUSED (expand with alpha_prev into `out`, then project the
+ *   now final `out` for the NEXT Chebyshev step: one read + one write of the sphere points per step),
+ *   EXPAND (last step / single H apply), EXPAND_ATOMIC (spheres overlap: FP64 atomics, no read).
+ *
+ * alpha is kept per IMAGE (a partial sum over that image's points, already times dV and the Bloch
+ * factor); the consumer adds the partials of all images of the atom in a fixed order, so the result is
+ * deterministic and needs no atomics or zero fill (the reference accumulates images with beta = 1,
+ * nlocVecRoutines.c:821-827).
+ *
+ * Complex data (k-points): Chi is real (nlocVecRoutines.c:731), so a complex column is two real "word"
+ * columns (re, im); the Bloch factors (nlocVecRoutines.c:911-921, :982-989) are applied where beta is
+ * formed and where alpha is written.
  */
 #include "chefsi_internal.h"
 
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kColsPerCta = 64; /* real columns (32 complex) */
-constexpr int kMaxMT = 4;       /* projector tiles of 8  -> nproj <= 32 */
-constexpr int kMaxKT = 8;       /* projector chunks of 4 */
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCols = 32;            /* real word columns per CTA (lanes) */
+constexpr int kP = 64;               /* sphere points per chunk */
+constexpr int kPitch = kP + 1;       /* odd pitch: conflict-free column-strided LDS */
+constexpr int kPtsPerWarp = kP / kWarps;
+
+enum { MODE_PROJECT = 0, MODE_FUSED = 1, MODE_EXPAND = 2, MODE_EXPAND_ATOMIC = 3 };
 
 struct NlocView {
     const int *IP_displ;
     const double *gamma;
-    const int *img_atom, *img_ndc;
-    const long long *pos_off, *chi_off;
+    const int *img_atom, *img_ndc, *img_aoff;
+    const long long *pos_off, *chiT_off;
     const int *grid_pos;
-    const double *chi;
+    const double *chiT;
     const double2 *img_phase;
     const int *atom_img_off, *atom_img;
+    int Nxp, Nyp, px, py, Nx, Ny, mirx, miry; /* halo-pad geometry (mirx/miry: periodic pads present) */
 };
 
-__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-
-/* x is addressed as real words: element (col, pos) of a complex block is at 2*(col*ld + pos) + {0,1}.
- * WORDS = 1 (real) or 2 (complex); the warp's 8 MMA columns are 8/WORDS data columns. */
-template <int WORDS>
-__global__ void __launch_bounds__(kWarps * 32)
-nloc_project_kernel(const NlocView nl, const double *__restrict__ x, const size_t ld, const int ncol,
-                    double *__restrict__ alpha, const double dV)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
-    const int atom = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lr = lane >> 2, lc = lane & 3;
-    /* MMA column j (0..7) of this warp -> data column and word */
-    const int mcol0 = blockIdx.y * kColsPerCta + warp * 8;        /* in MMA (real-word) columns */
-    if (mcol0 / WORDS >= ncol) return;                            /* warp-uniform */
-    const int bcol = mcol0 + lr;                                  /* B fragment: column index lr */
-    const int bdata = bcol / WORDS, bword = bcol % WORDS;
-    const bool bvalid = bdata < ncol;
-    const double *__restrict__ xb = x + ((size_t)bdata * ld) * WORDS + bword;
-
-    const int ip0 = nl.IP_displ[atom];
-    const int nproj = nl.IP_displ[atom + 1] - ip0;
-    const int MT = (nproj + 7) >> 3;
-    const int j0 = nl.atom_img_off[atom], j1 = nl.atom_img_off[atom + 1];
-
-    double tot[kMaxMT][2];
-#pragma unroll
-    for (int m = 0; m < kMaxMT; m++) tot[m][0] = tot[m][1] = 0.0;
-
-    for (int jj = j0; jj < j1; jj++) {
-        const int J = nl.atom_img[jj];
-        const int ndc = nl.img_ndc[J];
-        const int *__restrict__ pos = nl.grid_pos + nl.pos_off[J];
-        const double *__restrict__ chi = nl.chi + nl.chi_off[J];
-        double c[kMaxMT][2];
-#pragma unroll
-        for (int m = 0; m < kMaxMT; m++) c[m][0] = c[m][1] = 0.0;
-#pragma unroll 2
-        for (int i0 = 0; i0 < ndc; i0 += 4) {
-            const int pt = i0 + lc;
-            const bool pv = pt < ndc;
-            double b = 0.0;
-            if (pv && bvalid) b = xb[(size_t)pos[pt] * WORDS];
-#pragma unroll
-            for (int m = 0; m < kMaxMT; m++) {
-                if (m < MT) {
-                    const int pr = 8 * m + lr;
-                    const double a = (pv && pr < nproj) ? chi[(size_t)pr * ndc + pt] : 0.0;
-                    dmma(c[m][0], c[m][1], a, b);
-                }
-            }
-        }
-        if (WORDS == 2) { /* (c0, c1) = (re, im) of one complex accumulator: multiply by the Bloch factor */
-            const double2 ph = nl.img_phase[J];
-#pragma unroll
-            for (int m = 0; m < kMaxMT; m++) {
-                tot[m][0] += c[m][0] * ph.x - c[m][1] * ph.y;
-                tot[m][1] += c[m][0] * ph.y + c[m][1] * ph.x;
-            }
-        } else {
-#pragma unroll
-            for (int m = 0; m < kMaxMT; m++) { tot[m][0] += c[m][0]; tot[m][1] += c[m][1]; }
-        }
-    }
-    /* C fragment: row lr (projector), MMA columns 2*lc, 2*lc+1 */
-#pragma unroll
-    for (int m = 0; m < kMaxMT; m++) {
-        const int pr = 8 * m + lr;
-        if (m < MT && pr < nproj) {
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int mc = mcol0 + 2 * lc + e;
-                const int dc = mc / WORDS, w = mc % WORDS;
-                if (dc < ncol) alpha[(((size_t)ip0 * ncol + (size_t)dc * nproj + pr)) * WORDS + w] = tot[m][e] * dV;
-            }
-        }
-    }
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int WORDS>
-__global__ void __launch_bounds__(kWarps * 32)
-nloc_expand_kernel(const NlocView nl, const double *__restrict__ alpha, double *__restrict__ out, const size_t ld,
-                   const int ncol, const double scale, const int use_atomics)
+template <int NP> struct Smem {
+    double V[2][kCols][kPitch];
+    double chi[2][kP][NP];
+    int pos[2][kP];
+    int mx[2][kP];
+    int my[2][kP];
+};
+
+/* vec: MODE_PROJECT -> the input block x (read only); otherwise the output block (read-modify-write).
+ * Word column wc of the block lives at vec + (wc / WORDS) * ld * WORDS + (wc % WORDS), element stride WORDS. */
+template <int NP, int WORDS, int MODE>
+__global__ void __launch_bounds__(kThreads, (NP <= 20) ? 2 : 1)
+nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__restrict__ alpha_next,
+            double *__restrict__ vec, const size_t ld, const int ncol, const int ngroups, const double scale,
+            const double dV)
 {
-    const int J = blockIdx.x;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<NP> &S = *reinterpret_cast<Smem<NP> *>(smem_raw);
+
+    const int J = blockIdx.x / ngroups, grp = blockIdx.x % ngroups;
     const int atom = nl.img_atom[J];
     const int ip0 = nl.IP_displ[atom];
     const int nproj = nl.IP_displ[atom + 1] - ip0;
-    if (nproj == 0) return;
-    const int KT = (nproj + 3) >> 2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lr = lane >> 2, lc = lane & 3;
-    const int mcol0 = blockIdx.y * kColsPerCta + warp * 8;
-    if (mcol0 / WORDS >= ncol) return;
     const int ndc = nl.img_ndc[J];
+    if (nproj == 0 || ndc == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwc = ncol * WORDS;                /* word columns in the block */
+    const int wc0 = grp * kCols;                 /* first word column of this CTA */
+    const int *__restrict__ pos = nl.grid_pos + nl.pos_off[J];
+    const double *__restrict__ chiT = nl.chiT + nl.chiT_off[J];
+    const int nchunks = (ndc + kP - 1) / kP;
 
-    /* B fragments: row lc (projector 4k+lc), column lr.  beta = scale * conj(phase) * Gamma * alpha */
-    double bf[kMaxKT];
-    {
-        const int mc = mcol0 + lr;
-        const int dc = mc / WORDS, w = mc % WORDS;
+    /* ---- beta = scale * conj(phase_J) * Gamma * sum_{images of the atom} alpha_prev ------------------ */
+    double beta[NP], acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) { beta[p] = 0.0; acc[p] = 0.0; }
+    const int mywc = wc0 + lane;
+    const bool colvalid = mywc < nwc;
+    if (MODE != MODE_PROJECT && colvalid) {
+        const int dc = mywc / WORDS, w = mywc % WORDS;
+        double sre[NP], sim[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) { sre[p] = 0.0; sim[p] = 0.0; }
+        for (int jj = nl.atom_img_off[atom]; jj < nl.atom_img_off[atom + 1]; jj++) {
+            const int J2 = nl.atom_img[jj];
+            const double *ap = alpha_prev + ((size_t)nl.img_aoff[J2] * ncol + (size_t)dc * nproj) * WORDS;
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+                if (p < nproj) {
+                    sre[p] += ap[p * WORDS];
+                    if (WORDS == 2) sim[p] += ap[p * WORDS + 1];
+                }
+        }
         double2 ph = make_double2(1.0, 0.0);
         if (WORDS == 2) ph = nl.img_phase[J];
 #pragma unroll
-        for (int k = 0; k < kMaxKT; k++) {
-            const int pr = 4 * k + lc;
-            double v = 0.0;
-            if (k < KT && pr < nproj && dc < ncol) {
-                const double g = nl.gamma[ip0 + pr] * scale;
-                const size_t ai = ((size_t)ip0 * ncol + (size_t)dc * nproj + pr) * WORDS;
-                if (WORDS == 2) {
-                    const double ar = alpha[ai], aim = alpha[ai + 1];
-                    /* (ar + i aim) * (cos - i sin), nlocVecRoutines.c:982 */
-                    v = (w == 0) ? g * (ar * ph.x + aim * ph.y) : g * (aim * ph.x - ar * ph.y);
-                } else {
-                    v = g * alpha[ai];
+        for (int p = 0; p < NP; p++)
+            if (p < nproj) {
+                const double g = nl.gamma[ip0 + p] * scale;
+                /* (ar + i ai) * (cos - i sin), nlocVecRoutines.c:982 */
+                if (WORDS == 2) beta[p] = (w == 0) ? g * (sre[p] * ph.x + sim[p] * ph.y) : g * (sim[p] * ph.x - sre[p] * ph.y);
+                else beta[p] = g * sre[p];
+            }
+    }
+
+    /* ---- chunk pipeline ------------------------------------------------------------------------------ */
+    /* phase A/C mapping: lane <-> points (lane, lane+32), warp <-> 4 word columns */
+    auto issue_chunk = [&](int k, int buf) {
+        const int pt0 = k * kP;
+        int ps[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int pt = pt0 + lane + 32 * h;
+            ps[h] = (pt < ndc) ? pos[pt] : -1;
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int mx = 0, my = 0;
+                if (ps[h] >= 0 && (nl.mirx | nl.miry)) {
+                    const int i = ps[h] % nl.Nxp - nl.px, j = (ps[h] / nl.Nxp) % nl.Nyp - nl.py;
+                    if (nl.mirx) { if (i < nl.px) mx = nl.Nx; else if (i >= nl.Nx - nl.px) mx = -nl.Nx; }
+                    if (nl.miry) { if (j < nl.py) my = nl.Ny * nl.Nxp; else if (j >= nl.Ny - nl.py) my = -nl.Ny * nl.Nxp; }
+                }
+                S.pos[buf][lane + 32 * h] = ps[h];
+                S.mx[buf][lane + 32 * h] = mx;
+                S.my[buf][lane + 32 * h] = my;
+            }
+        }
+        if (MODE != MODE_EXPAND_ATOMIC) {
+#pragma unroll
+            for (int c = 0; c < kCols / kWarps; c++) {
+                const int cl = warp * (kCols / kWarps) + c;
+                const int wc = wc0 + cl;
+                const double *base = vec + ((size_t)(wc / WORDS) * ld) * WORDS + (wc % WORDS);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    double *dst = &S.V[buf][cl][lane + 32 * h];
+                    if (ps[h] >= 0 && wc < nwc) cp_async8(dst, base + (size_t)ps[h] * WORDS);
+                    else *dst = 0.0;
                 }
             }
-            bf[k] = v;
         }
-    }
-    const int *__restrict__ pos = nl.grid_pos + nl.pos_off[J];
-    const double *__restrict__ chi = nl.chi + nl.chi_off[J];
-    /* this lane's two output MMA columns */
-    const int oc0 = mcol0 + 2 * lc;
-    const int od0 = oc0 / WORDS, ow0 = oc0 % WORDS;
-    const int od1 = (oc0 + 1) / WORDS, ow1 = (oc0 + 1) % WORDS;
-    double *__restrict__ o0 = out + ((size_t)od0 * ld) * WORDS + ow0;
-    double *__restrict__ o1 = out + ((size_t)od1 * ld) * WORDS + ow1;
-    const bool v0 = od0 < ncol, v1 = od1 < ncol;
+        /* Chi chunk: kP x NP doubles, contiguous in the point-major table */
+        const int npts = (ndc - pt0 < kP) ? ndc - pt0 : kP;
+        const double *src = chiT + (size_t)pt0 * NP;
+        double *dstc = &S.chi[buf][0][0];
+        for (int t = threadIdx.x; t < kP * NP / 2; t += kThreads) {
+            if (2 * t < npts * NP) cp_async16(dstc + 2 * t, src + 2 * t);
+            else { dstc[2 * t] = 0.0; dstc[2 * t + 1] = 0.0; }
+        }
+        cp_async_commit();
+    };
 
-    for (int i0 = 0; i0 < ndc; i0 += 8) {
-        const int pt = i0 + lr;
-        const bool pv = pt < ndc;
-        double c0 = 0.0, c1 = 0.0;
+    issue_chunk(0, 0);
+    for (int k = 0; k < nchunks; k++) {
+        const int buf = k & 1;
+        cp_async_wait<0>();
+        __syncthreads(); /* chunk k has landed; everybody is done with phase C of chunk k-1 (buffer buf^1) */
+        if (k + 1 < nchunks) issue_chunk(k + 1, buf ^ 1); /* in flight during phases B and C of chunk k */
+
+        /* ---- B: lanes <-> columns, warp handles points warp*kPtsPerWarp .. ---- */
+#pragma unroll 1
+        for (int i = 0; i < kPtsPerWarp; i++) {
+            const int pt = warp * kPtsPerWarp + i;
+            const double2 *ch = reinterpret_cast<const double2 *>(&S.chi[buf][pt][0]);
+            double v = (MODE == MODE_EXPAND_ATOMIC) ? 0.0 : S.V[buf][lane][pt];
+            if (MODE != MODE_PROJECT) {
+                double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < kMaxKT; k++) {
-            if (k < KT) {
-                const int pr = 4 * k + lc;
-                const double a = (pv && pr < nproj) ? chi[(size_t)pr * ndc + pt] : 0.0;
-                dmma(c0, c1, a, bf[k]);
+                for (int p = 0; p < NP / 2; p++) {
+                    const double2 c2 = ch[p];
+                    d0 = fma(c2.x, beta[2 * p], d0);
+                    d1 = fma(c2.y, beta[2 * p + 1], d1);
+                }
+                v += d0 + d1;
+                S.V[buf][lane][pt] = v;
+            }
+            if (MODE == MODE_PROJECT || MODE == MODE_FUSED) {
+#pragma unroll
+                for (int p = 0; p < NP / 2; p++) {
+                    const double2 c2 = ch[p];
+                    acc[2 * p] = fma(c2.x, v, acc[2 * p]);
+                    acc[2 * p + 1] = fma(c2.y, v, acc[2 * p + 1]);
+                }
             }
         }
-        if (pv) {
-            const size_t g = (size_t)pos[pt] * WORDS;
-            if (use_atomics) {
-                if (v0) atomicAdd(o0 + g, c0);
-                if (v1) atomicAdd(o1 + g, c1);
+        __syncthreads();
+
+        /* ---- C: scatter back (lanes <-> points) ---- */
+        if (MODE != MODE_PROJECT) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int pl = lane + 32 * h;
+                const int ps = S.pos[buf][pl];
+                if (ps < 0) continue;
+                const int mx = S.mx[buf][pl], my = S.my[buf][pl];
+#pragma unroll
+                for (int c = 0; c < kCols / kWarps; c++) {
+                    const int cl = warp * (kCols / kWarps) + c;
+                    const int wc = wc0 + cl;
+                    if (wc >= nwc) continue;
+                    double *base = vec + ((size_t)(wc / WORDS) * ld) * WORDS + (wc % WORDS);
+                    const double v = S.V[buf][cl][pl];
+                    if (MODE == MODE_EXPAND_ATOMIC) {
+                        atomicAdd(base + (size_t)ps * WORDS, v);
+                    } else {
+                        base[(size_t)ps * WORDS] = v;
+                        if (mx) base[(size_t)(ps + mx) * WORDS] = v;
+                        if (my) base[(size_t)(ps + my) * WORDS] = v;
+                    }
+                }
+            }
+        }
+    }
+
+    /* ---- alpha_next[J] = dV * phase_J * sum over warps of acc ----------------------------------------- */
+    if (MODE == MODE_PROJECT || MODE == MODE_FUSED) {
+        __syncthreads();
+        double *red = reinterpret_cast<double *>(smem_raw); /* [kWarps][NP][kCols+1] */
+#pragma unroll
+        for (int p = 0; p < NP; p++) red[(warp * NP + p) * (kCols + 1) + lane] = acc[p];
+        __syncthreads();
+        double2 ph = make_double2(1.0, 0.0);
+        if (WORDS == 2) ph = nl.img_phase[J];
+        double *an = alpha_next + (size_t)nl.img_aoff[J] * ncol * WORDS;
+        for (int t = threadIdx.x; t < nproj * (kCols / WORDS); t += kThreads) {
+            const int p = t % nproj, cl = t / nproj; /* cl: data column inside the CTA */
+            const int dc = wc0 / WORDS + cl;
+            if (dc >= ncol) continue;
+            double sr = 0.0, si = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < kWarps; w8++) {
+                sr += red[(w8 * NP + p) * (kCols + 1) + cl * WORDS];
+                if (WORDS == 2) si += red[(w8 * NP + p) * (kCols + 1) + cl * WORDS + 1];
+            }
+            double *dst = an + ((size_t)dc * nproj + p) * WORDS;
+            if (WORDS == 2) {
+                dst[0] = dV * (sr * ph.x - si * ph.y);
+                dst[1] = dV * (sr * ph.y + si * ph.x);
             } else {
-                if (v0) o0[g] += c0;
-                if (v1) o1[g] += c1;
+                dst[0] = dV * sr;
             }
         }
     }
@@ -216,41 +288,103 @@ __global__ void nloc_patch_kernel(double *__restrict__ out, const size_t ld, con
     }
 }
 
-template <int WORDS>
-int launch_t(chefsi_ctx *ctx, const void *x, void *out, size_t ld, int ncol, double scale)
+template <int NP, int WORDS, int MODE>
+int launch_mode(chefsi_ctx *ctx, const NlocView &v, const double *aprev, double *anext, double *vec, size_t ld, int ncol,
+                double scale)
 {
-    NlocDev &d = ctx->nl;
-    const size_t need = (size_t)d.ntot * ncol * sizeof(double) * WORDS;
-    if (need > ctx->alpha_bytes) {
-        if (ctx->d_alpha) cudaFree(ctx->d_alpha);
-        ctx->d_alpha = nullptr;
-        ctx->alpha_bytes = 0;
-        cudaError_t e = cudaMalloc(&ctx->d_alpha, need);
-        if (e != cudaSuccess) { chefsi_fail(ctx, "cudaMalloc(alpha, %zu): %s", need, cudaGetErrorString(e)); return -1; }
-        ctx->alpha_bytes = need;
+    constexpr size_t red_bytes = (size_t)kWarps * NP * (kCols + 1) * sizeof(double);
+    constexpr size_t smem = sizeof(Smem<NP>) > red_bytes ? sizeof(Smem<NP>) : red_bytes;
+    auto kern = nloc_kernel<NP, WORDS, MODE>;
+    {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(nloc): %s", cudaGetErrorString(e)); return -1; }
     }
-    if (d.max_nproj > 8 * kMaxMT) { chefsi_fail(ctx, "nloc: more than %d projectors per atom not supported", 8 * kMaxMT); return -1; }
-    NlocView v{d.IP_displ, d.gamma, d.img_atom, d.img_ndc, d.pos_off, d.chi_off,
-               d.grid_pos, d.chi, d.img_phase, d.atom_img_off, d.atom_img};
-    const int mma_cols = ncol * WORDS;
-    const unsigned gy = (unsigned)((mma_cols + kColsPerCta - 1) / kColsPerCta);
-    if (gy > 65535) { chefsi_fail(ctx, "nloc: too many columns per call"); return -1; }
-    nloc_project_kernel<WORDS><<<dim3((unsigned)d.n_atom, gy), kWarps * 32, 0, ctx->stream>>>(
-        v, reinterpret_cast<const double *>(x), ld, ncol, reinterpret_cast<double *>(ctx->d_alpha), ctx->grid.dV);
-    nloc_expand_kernel<WORDS><<<dim3((unsigned)d.n_img, gy), kWarps * 32, 0, ctx->stream>>>(
-        v, reinterpret_cast<const double *>(ctx->d_alpha), reinterpret_cast<double *>(out), ld, ncol, scale, d.overlap);
+    const int ngroups = (ncol * WORDS + kCols - 1) / kCols;
+    const long long nblk = (long long)ctx->nl.n_img * ngroups;
+    if (nblk > 0x7fffffffLL) { chefsi_fail(ctx, "nloc: too many CTAs"); return -1; }
+    kern<<<(unsigned)nblk, kThreads, smem, ctx->stream>>>(v, aprev, anext, vec, ld, ncol, ngroups, scale, ctx->grid.dV);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { chefsi_fail(ctx, "nloc launch: %s", cudaGetErrorString(e)); return -1; }
-    return 2;
+    return 1;
+}
+
+template <int NP, int WORDS>
+int launch_np(chefsi_ctx *ctx, int mode, const NlocView &v, const double *aprev, double *anext, double *vec, size_t ld,
+              int ncol, double scale)
+{
+    switch (mode) {
+    case MODE_PROJECT: return launch_mode<NP, WORDS, MODE_PROJECT>(ctx, v, aprev, anext, vec, ld, ncol, scale);
+    case MODE_FUSED: return launch_mode<NP, WORDS, MODE_FUSED>(ctx, v, aprev, anext, vec, ld, ncol, scale);
+    case MODE_EXPAND: return launch_mode<NP, WORDS, MODE_EXPAND>(ctx, v, aprev, anext, vec, ld, ncol, scale);
+    default: return launch_mode<NP, WORDS, MODE_EXPAND_ATOMIC>(ctx, v, aprev, anext, vec, ld, ncol, scale);
+    }
 }
 
 }  // namespace
 
-int launch_nloc_apply(chefsi_ctx *ctx, const void *x, void *out, size_t ld, int ncol, double scale,
-                      bool is_complex)
+/* projector padding the kernels are instantiated for (chosen from the largest nproj of any atom) */
+int nloc_padded_nproj(int max_nproj)
 {
-    if (ctx->nl.n_img == 0 || ctx->nl.ntot == 0 || ncol <= 0) return 0;
-    return is_complex ? launch_t<2>(ctx, x, out, ld, ncol, scale) : launch_t<1>(ctx, x, out, ld, ncol, scale);
+    if (max_nproj <= 8) return 8;
+    if (max_nproj <= 14) return 14;
+    if (max_nproj <= 20) return 20;
+    if (max_nproj <= 26) return 26;
+    if (max_nproj <= 32) return 32;
+    return -1;
+}
+
+static int ensure_alpha(chefsi_ctx *ctx, int ncol, int words)
+{
+    const size_t need = (size_t)ctx->nl.img_proj_total * ncol * sizeof(double) * words;
+    if (need <= ctx->alpha_bytes) return 0;
+    for (int i = 0; i < 2; i++) { cudaFree(ctx->d_alpha[i]); ctx->d_alpha[i] = nullptr; }
+    ctx->alpha_bytes = 0;
+    for (int i = 0; i < 2; i++) {
+        cudaError_t e = cudaMalloc(&ctx->d_alpha[i], need);
+        if (e != cudaSuccess) { chefsi_fail(ctx, "cudaMalloc(alpha, %zu): %s", need, cudaGetErrorString(e)); return -1; }
+    }
+    ctx->alpha_bytes = need;
+    return 0;
+}
+
+/* mode: NLOC_PROJECT  alpha(cur) = dV * phase * Chi^T vec                       (vec is read only)
+ *       NLOC_FUSED    vec += scale * Chi Gamma alpha(cur); alpha(next) = proj(vec); cur <-> next
+ *       NLOC_EXPAND   vec += scale * Chi Gamma alpha(cur)   (atomics when spheres overlap)            */
+int launch_nloc(chefsi_ctx *ctx, int mode, void *vec, size_t ld, int ncol, double scale, bool is_complex)
+{
+    NlocDev &d = ctx->nl;
+    if (d.n_img == 0 || d.ntot == 0 || ncol <= 0) return 0;
+    const int words = is_complex ? 2 : 1;
+    if (ensure_alpha(ctx, ncol, words)) return -1;
+    const Layout &L = ctx->lay;
+    NlocView v{d.IP_displ, d.gamma, d.img_atom, d.img_ndc, d.img_aoff, d.pos_off, d.chiT_off, d.grid_pos, d.chiT,
+               d.img_phase, d.atom_img_off, d.atom_img,
+               L.Nxp, L.Nyp, L.px, L.py, L.Nx, L.Ny,
+               (L.px && !ctx->grid.BCx) ? 1 : 0, (L.py && !ctx->grid.BCy) ? 1 : 0};
+    int kmode = mode;
+    if (mode == NLOC_FUSED && d.overlap) { chefsi_fail(ctx, "nloc: fused mode needs disjoint spheres"); return -1; }
+    if (mode == NLOC_EXPAND && d.overlap) kmode = MODE_EXPAND_ATOMIC;
+    const double *aprev = reinterpret_cast<const double *>(ctx->d_alpha[ctx->alpha_cur]);
+    double *anext = reinterpret_cast<double *>(ctx->d_alpha[mode == NLOC_FUSED ? ctx->alpha_cur ^ 1 : ctx->alpha_cur]);
+    double *p = reinterpret_cast<double *>(vec);
+    int n = -1;
+#define CHEFSI_NLOC_CASE(NP)                                                                              \
+    case NP:                                                                                              \
+        n = is_complex ? launch_np<NP, 2>(ctx, kmode, v, aprev, anext, p, ld, ncol, scale)                \
+                       : launch_np<NP, 1>(ctx, kmode, v, aprev, anext, p, ld, ncol, scale);               \
+        break;
+    switch (d.np_pad) {
+        CHEFSI_NLOC_CASE(8)
+        CHEFSI_NLOC_CASE(14)
+        CHEFSI_NLOC_CASE(20)
+        CHEFSI_NLOC_CASE(26)
+        CHEFSI_NLOC_CASE(32)
+    default: chefsi_fail(ctx, "nloc: more than 32 projectors per atom not supported"); return -1;
+    }
+#undef CHEFSI_NLOC_CASE
+    if (n < 0) return -1;
+    if (mode == NLOC_FUSED) ctx->alpha_cur ^= 1;
+    return n;
 }
 
 int launch_nloc_halo_patch(chefsi_ctx *ctx, void *out, size_t ld, int ncol, bool is_complex)
