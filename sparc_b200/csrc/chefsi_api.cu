@@ -78,6 +78,8 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
     cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->force_general = getenv("CHEFSI_B200_FORCE_GENERAL") ? atoi(getenv("CHEFSI_B200_FORCE_GENERAL")) : 0;
+    if (getenv("CHEFSI_B200_GRIDSYNC")) ctx->stream_gridsync = atoi(getenv("CHEFSI_B200_GRIDSYNC"));
+    if (getenv("CHEFSI_B200_TMA_L2PROMO")) ctx->tma_l2promo = atoi(getenv("CHEFSI_B200_TMA_L2PROMO")) & 3;
     *out = ctx;
     return 0;
 }
@@ -103,6 +105,7 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     cudaFree(ctx->d_alpha[0]);
     cudaFree(ctx->d_alpha[1]);
     cudaFree(ctx->d_stage);
+    cudaFree(ctx->d_sync);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);

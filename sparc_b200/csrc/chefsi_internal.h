@@ -118,6 +118,10 @@ struct chefsi_ctx {
     int num_sms = 148;
     size_t max_smem_optin = 0;
     int force_general = 0;
+    int stream_gridsync = 1;       /* round barrier between the streaming kernel's producers */
+    int tma_l2promo = 3;           /* CUtensorMapL2promotion of the streaming kernel's tensor maps */
+    unsigned int *d_sync = nullptr;
+    unsigned int sync_arrivals = 0;
     char err[512] = {0};
 };
 

@@ -213,7 +213,7 @@ template <int WX, int WY>
 __global__ void __launch_bounds__(TileCfg<WX, WY>::THREADS, 1)
 stream_orth_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xprev,
                    const __grid_constant__ CUtensorMap map_veff, const __grid_constant__ StreamDesc d, const StepArgs a,
-                   const int nitems)
+                   const int nitems, unsigned int *__restrict__ sync_counter, const unsigned int sync_base)
 {
     using Cfg = TileCfg<WX, WY>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -239,9 +239,25 @@ stream_orth_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (warp == Cfg::CONSUMER_WARPS) {
         /* ================= producer warp (one elected lane issues the TMA boxes) ================= */
         if (lane == 0) {
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            unsigned int round = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, round++) {
                 const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
                 const int x0 = (tile % d.ntx) * Cfg::TX, y0 = (tile / d.ntx) * Cfg::TY;
+                if (sync_counter) {
+                    /* Round barrier between the producers of all (co-resident) CTAs: neighbouring tiles of a
+                       column are marched by neighbouring CTAs in the same round; starting them together keeps
+                       their z positions within the L2 residence time of a line (~20 us at 5.6 TB/s), so the
+                       xy-halo of a tile is an L2 hit on the plane its neighbour fetched (a CTA that runs
+                       ahead misses and is slowed down, one that lags hits: the skew is self-correcting).
+                       Only the CTAs that have an item in this round take part; the spin is bounded. */
+                    const unsigned int in_round = (unsigned int)min((long long)gridDim.x, (long long)nitems - (long long)round * gridDim.x);
+                    const unsigned int done_before = round * gridDim.x; /* arrivals of the earlier (full) rounds */
+                    __threadfence();
+                    atomicAdd(sync_counter, 1u);
+                    const unsigned int target = sync_base + done_before + in_round;
+                    unsigned int spins = 0;
+                    while ((int)(*(volatile unsigned int *)sync_counter - target) < 0 && ++spins < (1u << 22)) __nanosleep(64);
+                }
                 for (int p = -R; p < Nz + R; p++) {
                     int kz = p;
                     const bool interior = (p >= 0 && p < Nz);
@@ -342,7 +358,7 @@ PFN_encodeTiled get_encode()
 }
 
 /* 4-D view (x, y, z, column) of a block of columns in the internal layout */
-bool make_map(CUtensorMap *map, const void *base, const Layout &L, int ncol, int box_x, int box_y)
+bool make_map(CUtensorMap *map, const void *base, const Layout &L, int ncol, int box_x, int box_y, int promo)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return false;
@@ -351,7 +367,7 @@ bool make_map(CUtensorMap *map, const void *base, const Layout &L, int ncol, int
     cuuint32_t box[4] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, es,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)promo,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -374,8 +390,9 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
 
     CUtensorMap mx, mp, mv;
     const void *xp = a.xprev ? a.xprev : a.x; /* never dereferenced when s2 == 0 */
-    if (!make_map(&mx, a.x, L, a.ncol, Cfg::YP, Cfg::YROWS) || !make_map(&mp, xp, L, a.ncol, Cfg::XP, Cfg::TY) ||
-        !make_map(&mv, ctx->d_veff, L, 1, Cfg::XP, Cfg::TY)) {
+    const int promo = ctx->tma_l2promo;
+    if (!make_map(&mx, a.x, L, a.ncol, Cfg::YP, Cfg::YROWS, promo) || !make_map(&mp, xp, L, a.ncol, Cfg::XP, Cfg::TY, promo) ||
+        !make_map(&mv, ctx->d_veff, L, 1, Cfg::XP, Cfg::TY, promo)) {
         chefsi_fail(ctx, "cuTensorMapEncodeTiled failed");
         return -1;
     }
@@ -383,7 +400,27 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(stream): %s", cudaGetErrorString(e)); return -1; }
     const int grid = (int)((nitems < ctx->num_sms) ? nitems : ctx->num_sms);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(mx, mp, mv, d, a, (int)nitems);
+    unsigned int *counter = nullptr;
+    unsigned int base = 0;
+    if (ctx->stream_gridsync && nitems > grid) {
+        if (!ctx->d_sync) {
+            if (cudaMalloc((void **)&ctx->d_sync, 256) != cudaSuccess || cudaMemset(ctx->d_sync, 0, 256) != cudaSuccess) {
+                chefsi_fail(ctx, "stream kernel: cannot allocate the round-barrier counter");
+                return -1;
+            }
+        }
+        counter = ctx->d_sync;
+        base = ctx->sync_arrivals;
+        ctx->sync_arrivals += (unsigned int)nitems; /* every item arrives exactly once (wraps mod 2^32) */
+    }
+    int nit = (int)nitems;
+    if (counter) { /* the barrier needs all CTAs co-resident: cooperative launch refuses otherwise */
+        void *args[] = {(void *)&mx, (void *)&mp, (void *)&mv, (void *)&d, (void *)&a, (void *)&nit, (void *)&counter, (void *)&base};
+        e = cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Cfg::THREADS), args, Cfg::SMEM, ctx->stream);
+        if (e != cudaSuccess) { chefsi_fail(ctx, "stream kernel cooperative launch: %s", cudaGetErrorString(e)); return -1; }
+    } else {
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(mx, mp, mv, d, a, nit, counter, base);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) { chefsi_fail(ctx, "stream kernel launch: %s", cudaGetErrorString(e)); return -1; }
     return 1;
