@@ -104,7 +104,8 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     for (int i = 0; i < 3; i++) cudaFree(ctx->d_buf[i]);
     cudaFree(ctx->d_alpha[0]);
     cudaFree(ctx->d_alpha[1]);
-    cudaFree(ctx->d_stage);
+    for (int i = 0; i < 2; i++) { cudaFree(ctx->d_stage_in[i]); cudaFree(ctx->d_stage_out[i]); }
+    for (int i = 0; i < 8; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     cudaFree(ctx->d_sync);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -560,14 +561,24 @@ extern "C" int chefsi_synchronize(chefsi_ctx_t *ctx)
     return 0;
 }
 
-/* ---- host-buffer entry points ---------------------------------------------------------------- */
+/* ---- host-buffer entry points ----------------------------------------------------------------
+ * What the reference's ChebyshevFiltering / Hamiltonian_vectors_mult bind to: X and Y live in host
+ * memory (SPARC's Xorb / Yorb).  The block is cut into column chunks that flow through a three-stage
+ * pipeline on three streams -- H2D copy of chunk k+1, filter of chunk k, D2H copy of chunk k-1 -- so
+ * the call costs about max(PCIe in, compute, PCIe out) instead of their sum.  Dense staging buffers on
+ * the device (two in, two out) decouple the copies from the internal (halo-padded) layout. */
 static int ensure_stage(chefsi_ctx *ctx, size_t bytes)
 {
     if (bytes <= ctx->stage_bytes) return 0;
-    cudaFree(ctx->d_stage);
-    ctx->d_stage = nullptr;
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ctx->d_stage_in[i]); ctx->d_stage_in[i] = nullptr;
+        cudaFree(ctx->d_stage_out[i]); ctx->d_stage_out[i] = nullptr;
+    }
     ctx->stage_bytes = 0;
-    CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_stage, bytes));
+    for (int i = 0; i < 2; i++) {
+        CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_stage_in[i], bytes));
+        CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_stage_out[i], bytes));
+    }
     ctx->stage_bytes = bytes;
     return 0;
 }
@@ -582,41 +593,37 @@ static int ensure_bufs(chefsi_ctx *ctx, size_t bytes_each)
     return 0;
 }
 
-/* columns per chunk so that three blocks + alpha fit in the free device memory */
+/* columns per chunk: small enough that the pipeline has ~8 chunks to overlap and that three blocks,
+ * four staging blocks and alpha fit in the free device memory; large enough to fill the GPU */
 static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
 {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
-    free_b += 3 * ctx->buf_bytes + 2 * ctx->alpha_bytes + ctx->stage_bytes; /* what we already hold can be reused */
-    const size_t per_col = 3 * ctx->ld * esz + ctx->Nd * esz + 2 * (size_t)ctx->nl.img_proj_total * esz;
+    free_b += 3 * ctx->buf_bytes + 2 * ctx->alpha_bytes + 4 * ctx->stage_bytes; /* what we already hold can be reused */
+    const size_t per_col = 3 * ctx->ld * esz + 4 * ctx->Nd * esz + 2 * (size_t)ctx->nl.img_proj_total * esz;
     size_t budget = (size_t)(0.85 * (double)free_b);
     const char *env = getenv("CHEFSI_B200_MAX_CHUNK_BYTES");
     if (env) { size_t v = strtoull(env, nullptr, 10); if (v && v < budget) budget = v; }
     size_t n = budget / (per_col ? per_col : 1);
     if (n < 1) n = 1;
     if (n > (size_t)ncol) n = (size_t)ncol;
+    /* pipeline granularity: only worth it when the block is big enough for the copies to matter */
+    const size_t block_bytes = (size_t)ncol * ctx->Nd * esz;
+    if (block_bytes > ((size_t)64 << 20)) {
+        size_t want = ((size_t)ncol + 7) / 8;
+        if (want < 32) want = 32;
+        if (want > 128) want = 128;
+        const char *e2 = getenv("CHEFSI_B200_HOST_CHUNK");
+        if (e2 && atoi(e2) > 0) want = (size_t)atoi(e2);
+        if (want < n) n = want;
+    }
     return (int)n;
 }
 
-/* host block (dense, ld = ldh) -> staging (dense, ld = Nd) -> internal layout, and back */
-static int upload_block(chefsi_ctx *ctx, const void *host, size_t ldh, int c0, int nc, void *dev, size_t esz, bool is_complex)
+static int ensure_pipe_events(chefsi_ctx *ctx)
 {
-    const size_t row = ctx->Nd * esz;
-    CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_stage, row, (const char *)host + (size_t)c0 * ldh * esz, ldh * esz, row, nc,
-                                       cudaMemcpyHostToDevice, ctx->stream));
-    const int n = launch_pack(ctx, ctx->d_stage, ctx->Nd, dev, nc, is_complex);
-    if (n < 0) return 1;
-    ctx->stats.kernel_launches += n;
-    return 0;
-}
-static int download_block(chefsi_ctx *ctx, const void *dev, void *host, size_t ldh, int c0, int nc, size_t esz, bool is_complex)
-{
-    const size_t row = ctx->Nd * esz;
-    const int n = launch_unpack(ctx, dev, ctx->d_stage, ctx->Nd, nc, is_complex);
-    if (n < 0) return 1;
-    ctx->stats.kernel_launches += n;
-    CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)host + (size_t)c0 * ldh * esz, ldh * esz, ctx->d_stage, row, row, nc,
-                                       cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->pipe_ev[0]) return 0;
+    for (int i = 0; i < 8; i++) CHEFSI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
     return 0;
 }
 
@@ -631,20 +638,55 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     const int chunk = chunk_columns(ctx, ncol, esz);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
     if (ensure_stage(ctx, (size_t)chunk * ctx->Nd * esz)) return 1;
-    double total_ms = 0;
-    for (int c0 = 0; c0 < ncol; c0 += chunk) {
+    if (ensure_pipe_events(ctx)) return 1;
+    cudaEvent_t *ev_h2d = ctx->pipe_ev, *ev_in_free = ctx->pipe_ev + 2, *ev_out = ctx->pipe_ev + 4, *ev_d2h = ctx->pipe_ev + 6;
+    const bool copy_x = !(flags & CHEFSI_FLAG_NO_X_COPYBACK);
+    const size_t row = ctx->Nd * esz;
+    cudaEvent_t t0 = ctx->ev[2], t1 = ctx->ev[3];
+    CHEFSI_CUDA(ctx, cudaEventRecord(t0, ctx->stream));
+    CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, t0, 0)); /* order after earlier work of this context */
+    int k = 0;
+    for (int c0 = 0; c0 < ncol; c0 += chunk, k++) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-        if (upload_block(ctx, X, ldi, c0, nc, ctx->d_buf[0], esz, is_complex)) return 1;
+        const int s = k & 1;
+        /* -- H2D: X chunk -> dense staging (needs stage_in[s] free: packed, and X copy-back of chunk k-2 done) */
+        if (k >= 2) CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, copy_x ? ev_d2h[s] : ev_in_free[s], 0));
+        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_stage_in[s], row, (const char *)X + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
+                                           cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CHEFSI_CUDA(ctx, cudaEventRecord(ev_h2d[s], ctx->h2d_stream));
+        /* -- compute: pack, filter, unpack into the out staging */
+        CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[s], 0));
+        int n = launch_pack(ctx, ctx->d_stage_in[s], ctx->Nd, ctx->d_buf[0], nc, is_complex);
+        if (n < 0) return 1;
+        ctx->stats.kernel_launches += n;
+        CHEFSI_CUDA(ctx, cudaEventRecord(ev_in_free[s], ctx->stream));
         int ys = 1, xs = 0;
         if (filter_device(ctx, ctx->d_buf, nc, m, a, b, a0, is_complex, &ys, &xs)) return 1;
-        if (download_block(ctx, ctx->d_buf[ys], Y, ldo, c0, nc, esz, is_complex)) return 1;
-        if (!(flags & CHEFSI_FLAG_NO_X_COPYBACK))
-            if (download_block(ctx, ctx->d_buf[xs], X, ldi, c0, nc, esz, is_complex)) return 1;
-        CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) total_ms += ms; else cudaGetLastError();
+        if (k >= 2) CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[s], 0)); /* stage_out[s] drained */
+        n = launch_unpack(ctx, ctx->d_buf[ys], ctx->d_stage_out[s], ctx->Nd, nc, is_complex);
+        if (n < 0) return 1;
+        ctx->stats.kernel_launches += n;
+        if (copy_x) {
+            n = launch_unpack(ctx, ctx->d_buf[xs], ctx->d_stage_in[s], ctx->Nd, nc, is_complex);
+            if (n < 0) return 1;
+            ctx->stats.kernel_launches += n;
+        }
+        CHEFSI_CUDA(ctx, cudaEventRecord(ev_out[s], ctx->stream));
+        /* -- D2H */
+        CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev_out[s], 0));
+        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Y + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_stage_out[s], row, row, nc,
+                                           cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (copy_x)
+            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)X + (size_t)c0 * ldi * esz, ldi * esz, ctx->d_stage_in[s], row, row, nc,
+                                               cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        CHEFSI_CUDA(ctx, cudaEventRecord(ev_d2h[s], ctx->d2h_stream));
     }
-    ctx->stats.last_filter_ms = total_ms;
+    /* join: the compute stream waits for the last copies, then the host waits for it */
+    for (int s = 0; s < 2 && s < k; s++) CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[s], 0));
+    CHEFSI_CUDA(ctx, cudaEventRecord(t1, ctx->stream));
+    CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) ctx->stats.last_filter_ms = ms; else cudaGetLastError();
     return 0;
 }
 
@@ -669,11 +711,20 @@ static int hmult_host(chefsi_ctx *ctx, int ncol, double c, const void *x, size_t
     const int chunk = chunk_columns(ctx, ncol, esz);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
     if (ensure_stage(ctx, (size_t)chunk * ctx->Nd * esz)) return 1;
+    const size_t row = ctx->Nd * esz;
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-        if (upload_block(ctx, x, ldi, c0, nc, ctx->d_buf[0], esz, is_complex)) return 1;
+        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_stage_in[0], row, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
+                                           cudaMemcpyHostToDevice, ctx->stream));
+        int n = launch_pack(ctx, ctx->d_stage_in[0], ctx->Nd, ctx->d_buf[0], nc, is_complex);
+        if (n < 0) return 1;
+        ctx->stats.kernel_launches += n;
         if (hmult_device(ctx, nc, c, ctx->d_buf[0], ctx->d_buf[1], is_complex)) return 1;
-        if (download_block(ctx, ctx->d_buf[1], Hx, ldo, c0, nc, esz, is_complex)) return 1;
+        n = launch_unpack(ctx, ctx->d_buf[1], ctx->d_stage_out[0], ctx->Nd, nc, is_complex);
+        if (n < 0) return 1;
+        ctx->stats.kernel_launches += n;
+        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Hx + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_stage_out[0], row, row, nc,
+                                           cudaMemcpyDeviceToHost, ctx->stream));
         CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return 0;

@@ -100,7 +100,9 @@ struct chefsi_ctx {
     Layout lay{};
     double *d_veff = nullptr;    /* Veff in the internal layout (one column) */
     double *d_zero = nullptr;    /* unused spare */
-    void *d_stage = nullptr;     /* dense staging block for host<->device transfers */
+    void *d_stage_in[2] = {nullptr, nullptr};  /* dense staging blocks of the host entry points' pipeline */
+    void *d_stage_out[2] = {nullptr, nullptr};
+    cudaEvent_t pipe_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes = 0;
     bool have_veff = false;
     NlocDev nl;
