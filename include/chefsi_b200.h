@@ -140,6 +140,11 @@ int chefsi_hamiltonian_mult_device(chefsi_ctx_t *ctx, int ncol, double c, const 
 int chefsi_hamiltonian_mult_kpt_device(chefsi_ctx_t *ctx, int ncol, double c, const void *x,
                                        void *Hx);
 int chefsi_synchronize(chefsi_ctx_t *ctx);
+/* Page-lock / unlock a caller-owned host range so the host entry points' chunk pipeline copies at
+ * full PCIe rate and overlaps with the kernels (cudaHostRegister; the caller's malloc'd orbital
+ * arrays, src/orbitalElecDensInit.c:364).  Optional: pageable memory works, only slower.  */
+int chefsi_host_register(chefsi_ctx_t *ctx, void *ptr, size_t bytes);
+int chefsi_host_unregister(chefsi_ctx_t *ctx, void *ptr);
 int chefsi_pack_device(chefsi_ctx_t *ctx, const void *dense, size_t ld_dense, void *packed, int ncol,
                        int is_complex);
 int chefsi_unpack_device(chefsi_ctx_t *ctx, const void *packed, void *dense, size_t ld_dense, int ncol,

@@ -1,5 +1,5 @@
 /*
- * cblas.h -- TEST INFRASTRUCTURE ONLY (oracle build).
+ * cblas.h -- ENVIRONMENT SHIM (see shims/README.md).
  *
  * Minimal CBLAS declaration shim used when the unmodified reference sources
  * under /root/reference/src are compiled into oracle/_ref/.  The image has no

@@ -1,5 +1,5 @@
 /*
- * lapacke.h -- TEST INFRASTRUCTURE ONLY (oracle build).
+ * lapacke.h -- ENVIRONMENT SHIM (see shims/README.md).
  *
  * LAPACKE declaration shim for compiling the unmodified reference sources into
  * oracle/_ref/.  Maps each LAPACKE routine the reference calls onto the

@@ -1,5 +1,5 @@
 /*
- * mpi.h -- TEST INFRASTRUCTURE ONLY (oracle build).
+ * mpi.h -- ENVIRONMENT SHIM (neither product nor oracle).
  *
  * Single-process ("np = 1") MPI declaration shim.  The image ships no MPI, so
  * the unmodified reference sources under /root/reference/src are compiled

@@ -1,5 +1,5 @@
 /*
- * mpi_serial.c -- TEST INFRASTRUCTURE ONLY (oracle build).
+ * mpi_serial.c -- ENVIRONMENT SHIM (see shims/README.md).
  *
  * One-rank implementation of the MPI subset the reference (SPARC) calls.
  * Every collective degenerates to a local copy; point-to-point traffic can

@@ -22,7 +22,7 @@ EXPORTS = (
     "chefsi_chebyshev_filter_device", "chefsi_chebyshev_filter_kpt_device",
     "chefsi_hamiltonian_mult_device", "chefsi_hamiltonian_mult_kpt_device",
     "chefsi_synchronize", "chefsi_fill_random_device", "chefsi_pack_device", "chefsi_unpack_device",
-    "chefsi_get_stats", "chefsi_set_profiling", "chefsi_stream",
+    "chefsi_get_stats", "chefsi_set_profiling", "chefsi_stream", "chefsi_host_register", "chefsi_host_unregister",
 )
 
 
@@ -82,6 +82,8 @@ def load_library() -> C.CDLL:
     lib.chefsi_unpack_device.argtypes = [vp, dp, dp, sz, i, i]
     lib.chefsi_get_stats.argtypes = [vp, C.POINTER(ChefsiStats)]
     lib.chefsi_set_profiling.argtypes = [vp, i]
+    lib.chefsi_host_register.argtypes = [vp, vp, sz]
+    lib.chefsi_host_unregister.argtypes = [vp, vp]
     lib.chefsi_stream.argtypes = [vp]
     lib.chefsi_stream.restype = vp
     _lib = lib

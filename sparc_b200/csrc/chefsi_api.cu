@@ -778,6 +778,22 @@ extern "C" int chefsi_unpack_device(chefsi_ctx_t *ctx, const void *packed, void 
     return 0;
 }
 
+extern "C" int chefsi_host_register(chefsi_ctx_t *ctx, void *ptr, size_t bytes)
+{
+    if (!ctx || !ptr || !bytes) return 1;
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return chefsi_fail(ctx, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e)); }
+    return 0;
+}
+extern "C" int chefsi_host_unregister(chefsi_ctx_t *ctx, void *ptr)
+{
+    if (!ctx || !ptr) return 1;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return chefsi_fail(ctx, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
 extern "C" int chefsi_get_stats(const chefsi_ctx_t *ctx, chefsi_stats_t *out)
 {
     if (!ctx || !out) return 1;

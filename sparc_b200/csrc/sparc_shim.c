@@ -1,0 +1,372 @@
+/*
+ * sparc_shim.c -- the reference-side binding of libchefsi_b200.so.
+ *
+ * Exports, with the reference's own C signatures, the four functions of SPARC's Chebyshev-filter
+ * path, so that the rest of SPARC (SCF loop, Lanczos, projection, Rayleigh-Ritz, density, forces)
+ * stays the unmodified reference C code and reaches the sm_100a CUDA path through them:
+ *
+ *   ChebyshevFiltering            src/eigenSolver.c:722-798      (decl. src/include/eigenSolver.h:93-97)
+ *   ChebyshevFiltering_kpt        src/eigenSolverKpt.c:458-535   (decl. src/include/eigenSolverKpt.h:41-45)
+ *   Hamiltonian_vectors_mult      src/hamiltonianVecRoutines.c:45-121
+ *   Hamiltonian_vectors_mult_kpt  src/hamiltonianVecRoutines.c:132-242 (decl. hamiltonianVecRoutines.h:30-47)
+ *
+ * It is compiled against the reference's headers (SPARC_OBJ layout, isddft.h:280-1216) and the same
+ * mpi.h as the host executable, flattens the fields the path reads into the POD structs of
+ * include/chefsi_b200.h and calls the C ABI.  The reference's own definitions of the four functions
+ * are kept in the executable under the names *_ref (integration/Makefile renames them with objcopy;
+ * INTEGRATION.md shows the two-line source alternative); calls that use a feature outside this
+ * library's scope (exact exchange, meta-GGA, DFT+U, spin-orbit / non-collinear spin, cyclix cells, a
+ * split domain) are forwarded to them unchanged -- the same cut as the reference's own accelerator
+ * guard (eigenSolver.c:315, eigenSolverKpt.c:236).  That is dispatch to the REFERENCE for features this
+ * library does not claim; there is no CPU implementation of the path in here.
+ *
+ * Error convention follows the reference (void functions; fatal errors print and exit).
+ */
+#include <complex.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mpi.h>
+
+#include "isddft.h"
+#include "eigenSolver.h"
+#include "eigenSolverKpt.h"
+#include "hamiltonianVecRoutines.h"
+
+#include "chefsi_b200.h"
+
+/* the reference's own implementations, renamed at link time */
+void ChebyshevFiltering_ref(SPARC_OBJ *pSPARC, int *DMVertices, double *X, int ldi, double *Y, int ldo, int ncol,
+                            int m, double a, double b, double a0, int k, int spn_i, MPI_Comm comm, double *time_info);
+void ChebyshevFiltering_kpt_ref(SPARC_OBJ *pSPARC, int *DMVertices, double _Complex *X, int ldi, double _Complex *Y,
+                                int ldo, int ncol, int m, double a, double b, double a0, int kpt, int spn_i,
+                                MPI_Comm comm, double *time_info);
+void Hamiltonian_vectors_mult_ref(const SPARC_OBJ *pSPARC, int DMnd, int *DMVertices, double *Veff_loc,
+                                  ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc, NLOC_PROJ_OBJ *nlocProj, int ncol,
+                                  double c, double *x, const int ldi, double *Hx, const int ldo, int spin, MPI_Comm comm);
+void Hamiltonian_vectors_mult_kpt_ref(const SPARC_OBJ *pSPARC, int DMnd, int *DMVertices, double *Veff_loc,
+                                      ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc, NLOC_PROJ_OBJ *nlocProj, int ncol,
+                                      double c, double _Complex *x, const int ldi, double _Complex *Hx, const int ldo,
+                                      int spin, int kpt, MPI_Comm comm);
+
+/* ------------------------------------------------------------------------------------------------ */
+static struct {
+    chefsi_ctx_t *ctx;
+    uint64_t grid_key;       /* fingerprint of the discretisation currently on the device */
+    uint64_t proj_key;       /* fingerprint of the projector tables currently on the device */
+    int have_proj_key;
+    int verbose;
+    /* host registration of the caller's orbital arrays (pinned for full-rate async copies) */
+    struct { void *base; size_t bytes; } pinned[8];
+    int npinned;
+    unsigned long long n_filter, n_hmult, n_forward;
+    double t_filter;
+} G;
+
+static void shim_fatal(const char *what)
+{
+    fprintf(stderr, "[chefsi_b200 shim] %s: %s\n", what, chefsi_last_error(G.ctx));
+    exit(EXIT_FAILURE);
+}
+
+static uint64_t fnv(uint64_t h, const void *p, size_t n)
+{
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
+static void shim_report(void)
+{
+    if (G.verbose)
+        fprintf(stderr, "[chefsi_b200 shim] %llu ChebyshevFiltering calls (%.3f s), %llu Hamiltonian_vectors_mult calls, "
+                        "%llu calls forwarded to the reference\n", G.n_filter, G.t_filter, G.n_hmult, G.n_forward);
+    if (G.ctx) { chefsi_destroy(G.ctx); G.ctx = NULL; }
+}
+
+static void shim_init(void)
+{
+    if (G.ctx) return;
+    const char *dev = getenv("CHEFSI_B200_DEVICE");
+    int device = dev ? atoi(dev) : 0;
+    /* one rank <-> one GPU when launched under a real MPI (local-rank env of the common launchers) */
+    const char *lr = getenv("OMPI_COMM_WORLD_LOCAL_RANK");
+    if (!lr) lr = getenv("MV2_COMM_WORLD_LOCAL_RANK");
+    if (!lr) lr = getenv("SLURM_LOCALID");
+    if (!dev && lr) device = atoi(lr);
+    G.verbose = getenv("CHEFSI_B200_SHIM_VERBOSE") ? atoi(getenv("CHEFSI_B200_SHIM_VERBOSE")) : 0;
+    if (chefsi_create(&G.ctx, device) != 0) {
+        fprintf(stderr, "[chefsi_b200 shim] cannot create the CUDA context: %s\n", chefsi_last_error(NULL));
+        exit(EXIT_FAILURE);
+    }
+    atexit(shim_report);
+    if (G.verbose) fprintf(stderr, "[chefsi_b200 shim] %s on device %d\n", chefsi_version(), device);
+}
+
+/* features handled natively; everything else goes to the reference routine (SURVEY.md 8b "Feature guard") */
+static int shim_supported(const SPARC_OBJ *S, int DMnd, const int *DMV, MPI_Comm comm, const NLOC_PROJ_OBJ *nlocProj)
+{
+    if (getenv("CHEFSI_B200_DISABLE")) return 0;
+    if (!(S->cell_typ == 0 || (S->cell_typ >= 11 && S->cell_typ <= 17))) return 0;
+    if (S->CyclixFlag) return 0;
+    if (S->spin_typ > 1 || S->SOC_Flag || S->Nspinor_eig != 1) return 0;
+    if (S->usefock > 0 && S->usefock % 2 == 0) return 0;
+    if (S->ixc[2] && S->countPotentialCalculate > 1) return 0;
+    if (S->is_hubbard) return 0;
+    if (S->order / 2 > CHEFSI_MAX_FDN) return 0;
+    int nproc = 1;
+    MPI_Comm_size(comm, &nproc);
+    if (nproc != 1) return 0;
+    if (DMnd != S->Nd || DMV[0] != 0 || DMV[1] != S->Nx - 1 || DMV[2] != 0 || DMV[3] != S->Ny - 1 || DMV[4] != 0 ||
+        DMV[5] != S->Nz - 1)
+        return 0;
+    for (int t = 0; t < S->Ntypes; t++)
+        if (nlocProj[t].nproj > 32) return 0;
+    return 1;
+}
+
+static void shim_sync_grid(const SPARC_OBJ *S)
+{
+    chefsi_grid_t g;
+    memset(&g, 0, sizeof(g));
+    g.Nx = S->Nx; g.Ny = S->Ny; g.Nz = S->Nz;
+    g.BCx = S->BCx; g.BCy = S->BCy; g.BCz = S->BCz;
+    g.FDn = S->order / 2;
+    g.cell_typ = S->cell_typ;
+    g.dV = S->dV;
+    g.range_x = S->range_x; g.range_y = S->range_y; g.range_z = S->range_z;
+    const size_t n = sizeof(double) * (size_t)(g.FDn + 1);
+    memcpy(g.D2_x, S->D2_stencil_coeffs_x, n);
+    memcpy(g.D2_y, S->D2_stencil_coeffs_y, n);
+    memcpy(g.D2_z, S->D2_stencil_coeffs_z, n);
+    memcpy(g.D1_x, S->D1_stencil_coeffs_x, n);
+    memcpy(g.D1_y, S->D1_stencil_coeffs_y, n);
+    memcpy(g.D1_z, S->D1_stencil_coeffs_z, n);
+    if (S->cell_typ != 0) { /* allocated only for non-orthogonal cells, initialization.c:2150-2162 */
+        memcpy(g.D2_xy, S->D2_stencil_coeffs_xy, n);
+        memcpy(g.D2_xz, S->D2_stencil_coeffs_xz, n);
+        memcpy(g.D2_yz, S->D2_stencil_coeffs_yz, n);
+        memcpy(g.D1_xy, S->D1_stencil_coeffs_xy, n);
+        memcpy(g.D1_yx, S->D1_stencil_coeffs_yx, n);
+        memcpy(g.D1_xz, S->D1_stencil_coeffs_xz, n);
+        memcpy(g.D1_zx, S->D1_stencil_coeffs_zx, n);
+        memcpy(g.D1_yz, S->D1_stencil_coeffs_yz, n);
+        memcpy(g.D1_zy, S->D1_stencil_coeffs_zy, n);
+    }
+    const uint64_t key = fnv(1469598103934665603ULL, &g, sizeof(g));
+    if (key == G.grid_key) return;
+    if (chefsi_set_grid(G.ctx, &g) != 0) shim_fatal("chefsi_set_grid");
+    G.grid_key = key;
+    G.have_proj_key = 0; /* set_grid drops the projector tables */
+    if (G.verbose) fprintf(stderr, "[chefsi_b200 shim] grid %dx%dx%d cell_typ %d FDn %d uploaded\n", g.Nx, g.Ny, g.Nz, g.cell_typ, g.FDn);
+}
+
+/* Flatten ATOM_NLOC_INFLUENCE_OBJ / NLOC_PROJ_OBJ / PSD_OBJ.Gamma / IP_displ (isddft.h:202-265,126-150,460)
+ * into chefsi_nloc_t, in the image order of Vnl_vec_mult's loops (nlocVecRoutines.c:807-831).  The device
+ * copy is keyed on a fingerprint of the image list (atom indices, coordinates, sphere sizes): the tables
+ * are re-made by the reference once per ionic step, and the psi-domain and kptcomm_topo sets coincide on
+ * an unsplit domain, so Lanczos' calls (eigenSolver.c:2002) reuse the upload. */
+static void shim_sync_projectors(const SPARC_OBJ *S, const ATOM_NLOC_INFLUENCE_OBJ *AI, const NLOC_PROJ_OBJ *NP, int is_kpt)
+{
+    uint64_t key = 1469598103934665603ULL;
+    int n_img = 0;
+    long long npos = 0, nchi = 0;
+    for (int t = 0; t < S->Ntypes; t++) {
+        key = fnv(key, &NP[t].nproj, sizeof(int));
+        if (!NP[t].nproj) continue;
+        key = fnv(key, &AI[t].n_atom, sizeof(int));
+        key = fnv(key, AI[t].coords, sizeof(double) * 3 * (size_t)AI[t].n_atom);
+        key = fnv(key, AI[t].atom_index, sizeof(int) * (size_t)AI[t].n_atom);
+        key = fnv(key, AI[t].ndc, sizeof(int) * (size_t)AI[t].n_atom);
+        for (int i = 0; i < AI[t].n_atom; i++) {
+            n_img++;
+            npos += AI[t].ndc[i];
+            nchi += (long long)AI[t].ndc[i] * NP[t].nproj;
+        }
+    }
+    key = fnv(key, &S->elecgs_Count, sizeof(int));
+    key = fnv(key, &S->dV, sizeof(double));
+    if (G.have_proj_key && key == G.proj_key) return;
+
+    chefsi_nloc_t nl;
+    memset(&nl, 0, sizeof(nl));
+    nl.n_atom = S->n_atom;
+    nl.IP_displ = S->IP_displ;
+    const int ntot = S->IP_displ[S->n_atom];
+    double *gamma = (double *)malloc(sizeof(double) * (size_t)(ntot > 0 ? ntot : 1));
+    {   /* one Gamma per (atom, projector) in alpha order: the loop nest of nlocVecRoutines.c:841-863 */
+        int count = 0;
+        for (int t = 0; t < S->Ntypes; t++) {
+            const int lloc = S->localPsd[t], lmax = S->psd[t].lmax;
+            for (int iat = 0; iat < S->nAtomv[t]; iat++) {
+                int ldispl = 0;
+                for (int l = 0; l <= lmax; l++) {
+                    if (l == lloc) { ldispl += S->psd[t].ppl[l]; continue; }
+                    for (int np = 0; np < S->psd[t].ppl[l]; np++)
+                        for (int mm = -l; mm <= l; mm++) gamma[count++] = S->psd[t].Gamma[ldispl + np];
+                    ldispl += S->psd[t].ppl[l];
+                }
+            }
+        }
+        if (count != ntot) {
+            fprintf(stderr, "[chefsi_b200 shim] projector count mismatch (%d vs IP_displ %d)\n", count, ntot);
+            exit(EXIT_FAILURE);
+        }
+    }
+    int *img_atom = (int *)malloc(sizeof(int) * (size_t)(n_img + 1));
+    int *img_ndc = (int *)malloc(sizeof(int) * (size_t)(n_img + 1));
+    double *img_coords = (double *)malloc(sizeof(double) * 3 * (size_t)(n_img + 1));
+    long long *pos_off = (long long *)malloc(sizeof(long long) * (size_t)(n_img + 1));
+    long long *chi_off = (long long *)malloc(sizeof(long long) * (size_t)(n_img + 1));
+    int *grid_pos = (int *)malloc(sizeof(int) * (size_t)(npos + 1));
+    double *chi = (double *)malloc(sizeof(double) * (size_t)(nchi + 1));
+    int J = 0;
+    pos_off[0] = chi_off[0] = 0;
+    for (int t = 0; t < S->Ntypes; t++) {
+        if (!NP[t].nproj) continue;
+        for (int i = 0; i < AI[t].n_atom; i++, J++) {
+            const int ndc = AI[t].ndc[i];
+            img_atom[J] = AI[t].atom_index[i];
+            img_ndc[J] = ndc;
+            memcpy(img_coords + 3 * J, AI[t].coords + 3 * i, 3 * sizeof(double));
+            memcpy(grid_pos + pos_off[J], AI[t].grid_pos[i], sizeof(int) * (size_t)ndc);
+            const size_t nc = (size_t)ndc * NP[t].nproj;
+            if (is_kpt) { /* Chi_c holds the same real values stored as complex, nlocVecRoutines.c:731 */
+                const double _Complex *src = NP[t].Chi_c[i];
+                for (size_t q = 0; q < nc; q++) chi[chi_off[J] + q] = creal(src[q]);
+            } else {
+                memcpy(chi + chi_off[J], NP[t].Chi[i], sizeof(double) * nc);
+            }
+            pos_off[J + 1] = pos_off[J] + ndc;
+            chi_off[J + 1] = chi_off[J] + (long long)nc;
+        }
+    }
+    nl.gamma = gamma;
+    nl.n_img = n_img;
+    nl.img_atom = img_atom; nl.img_ndc = img_ndc; nl.img_coords = img_coords;
+    nl.pos_off = pos_off; nl.chi_off = chi_off; nl.grid_pos = grid_pos; nl.chi = chi;
+    if (chefsi_set_projectors(G.ctx, n_img ? &nl : NULL) != 0) shim_fatal("chefsi_set_projectors");
+    free(gamma); free(img_atom); free(img_ndc); free(img_coords); free(pos_off); free(chi_off); free(grid_pos); free(chi);
+    G.proj_key = key;
+    G.have_proj_key = 1;
+    if (G.verbose) fprintf(stderr, "[chefsi_b200 shim] projectors uploaded: %d atoms, %d images, %lld sphere points\n", S->n_atom, n_img, npos);
+}
+
+/* SPARC's orbital arrays are plain malloc memory that lives for the whole run (orbitalElecDensInit.c:364);
+ * page-lock them once so the chunk pipeline's async copies run at full PCIe rate.  Best effort. */
+static void shim_pin(void *p, size_t bytes)
+{
+    if (getenv("CHEFSI_B200_NO_PIN") || bytes < ((size_t)8 << 20)) return;
+    for (int i = 0; i < G.npinned; i++)
+        if ((char *)p >= (char *)G.pinned[i].base && (char *)p + bytes <= (char *)G.pinned[i].base + G.pinned[i].bytes) return;
+    if (G.npinned == 8) return;
+    if (chefsi_host_register(G.ctx, p, bytes) == 0) {
+        G.pinned[G.npinned].base = p;
+        G.pinned[G.npinned].bytes = bytes;
+        G.npinned++;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+void ChebyshevFiltering(SPARC_OBJ *pSPARC, int *DMVertices, double *X, int ldi, double *Y, int ldo, int ncol, int m,
+                        double a, double b, double a0, int k, int spn_i, MPI_Comm comm, double *time_info)
+{
+    if (comm == MPI_COMM_NULL || pSPARC->bandcomm_index < 0) return; /* eigenSolver.c:728 */
+    const int DMnd = (1 - DMVertices[0] + DMVertices[1]) * (1 - DMVertices[2] + DMVertices[3]) *
+                     (1 - DMVertices[4] + DMVertices[5]);
+    if (!shim_supported(pSPARC, DMnd, DMVertices, comm, pSPARC->nlocProj)) {
+        G.n_forward++;
+        ChebyshevFiltering_ref(pSPARC, DMVertices, X, ldi, Y, ldo, ncol, m, a, b, a0, k, spn_i, comm, time_info);
+        return;
+    }
+    const double t1 = MPI_Wtime();
+    shim_init();
+    shim_sync_grid(pSPARC);
+    shim_sync_projectors(pSPARC, pSPARC->Atom_Influence_nloc, pSPARC->nlocProj, 0);
+    const int sg = pSPARC->spin_start_indx + spn_i; /* eigenSolver.c:756 */
+    if (chefsi_set_veff(G.ctx, pSPARC->Veff_loc_dmcomm + (size_t)sg * pSPARC->Nd_d_dmcomm) != 0) shim_fatal("chefsi_set_veff");
+    if (ncol > 0) {
+        shim_pin(X, sizeof(double) * (size_t)ldi * ncol);
+        shim_pin(Y, sizeof(double) * (size_t)ldo * ncol);
+    }
+    /* X is in/out in the reference (ends as p_{m-1}(H) X0, :787-794); CheFSI only consumes Y and reuses X
+       as scratch (eigenSolver.c:364-365), so the copy-back can be switched off */
+    const int flags = getenv("CHEFSI_B200_NO_X_COPYBACK") ? CHEFSI_FLAG_NO_X_COPYBACK : 0;
+    if (chefsi_chebyshev_filter(G.ctx, X, (size_t)ldi, Y, (size_t)ldo, ncol, m, a, b, a0, flags) != 0)
+        shim_fatal("chefsi_chebyshev_filter");
+    *time_info = MPI_Wtime() - t1;
+    G.n_filter++;
+    G.t_filter += *time_info;
+}
+
+void ChebyshevFiltering_kpt(SPARC_OBJ *pSPARC, int *DMVertices, double _Complex *X, int ldi, double _Complex *Y, int ldo,
+                            int ncol, int m, double a, double b, double a0, int kpt, int spn_i, MPI_Comm comm,
+                            double *time_info)
+{
+    if (comm == MPI_COMM_NULL || pSPARC->bandcomm_index < 0) return; /* eigenSolverKpt.c:464 */
+    const int DMnd = (1 - DMVertices[0] + DMVertices[1]) * (1 - DMVertices[2] + DMVertices[3]) *
+                     (1 - DMVertices[4] + DMVertices[5]);
+    if (!shim_supported(pSPARC, DMnd, DMVertices, comm, pSPARC->nlocProj)) {
+        G.n_forward++;
+        ChebyshevFiltering_kpt_ref(pSPARC, DMVertices, X, ldi, Y, ldo, ncol, m, a, b, a0, kpt, spn_i, comm, time_info);
+        return;
+    }
+    const double t1 = MPI_Wtime();
+    shim_init();
+    shim_sync_grid(pSPARC);
+    shim_sync_projectors(pSPARC, pSPARC->Atom_Influence_nloc, pSPARC->nlocProj, 1);
+    const int sg = pSPARC->spin_start_indx + spn_i;
+    if (chefsi_set_veff(G.ctx, pSPARC->Veff_loc_dmcomm + (size_t)sg * pSPARC->Nd_d_dmcomm) != 0) shim_fatal("chefsi_set_veff");
+    if (chefsi_set_kpoint(G.ctx, pSPARC->k1_loc[kpt], pSPARC->k2_loc[kpt], pSPARC->k3_loc[kpt]) != 0) shim_fatal("chefsi_set_kpoint");
+    if (ncol > 0) {
+        shim_pin(X, sizeof(double _Complex) * (size_t)ldi * ncol);
+        shim_pin(Y, sizeof(double _Complex) * (size_t)ldo * ncol);
+    }
+    const int flags = getenv("CHEFSI_B200_NO_X_COPYBACK") ? CHEFSI_FLAG_NO_X_COPYBACK : 0;
+    if (chefsi_chebyshev_filter_kpt(G.ctx, X, (size_t)ldi, Y, (size_t)ldo, ncol, m, a, b, a0, flags) != 0)
+        shim_fatal("chefsi_chebyshev_filter_kpt");
+    *time_info = MPI_Wtime() - t1;
+    G.n_filter++;
+    G.t_filter += *time_info;
+}
+
+void Hamiltonian_vectors_mult(const SPARC_OBJ *pSPARC, int DMnd, int *DMVertices, double *Veff_loc,
+                              ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc, NLOC_PROJ_OBJ *nlocProj, int ncol, double c,
+                              double *x, const int ldi, double *Hx, const int ldo, int spin, MPI_Comm comm)
+{
+    if (!shim_supported(pSPARC, DMnd, DMVertices, comm, nlocProj)) {
+        G.n_forward++;
+        Hamiltonian_vectors_mult_ref(pSPARC, DMnd, DMVertices, Veff_loc, Atom_Influence_nloc, nlocProj, ncol, c, x, ldi,
+                                     Hx, ldo, spin, comm);
+        return;
+    }
+    shim_init();
+    shim_sync_grid(pSPARC);
+    shim_sync_projectors(pSPARC, Atom_Influence_nloc, nlocProj, 0);
+    if (chefsi_set_veff(G.ctx, Veff_loc) != 0) shim_fatal("chefsi_set_veff");
+    if (chefsi_hamiltonian_mult(G.ctx, ncol, c, x, (size_t)ldi, Hx, (size_t)ldo) != 0) shim_fatal("chefsi_hamiltonian_mult");
+    G.n_hmult++;
+}
+
+void Hamiltonian_vectors_mult_kpt(const SPARC_OBJ *pSPARC, int DMnd, int *DMVertices, double *Veff_loc,
+                                  ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc, NLOC_PROJ_OBJ *nlocProj, int ncol,
+                                  double c, double _Complex *x, const int ldi, double _Complex *Hx, const int ldo,
+                                  int spin, int kpt, MPI_Comm comm)
+{
+    if (!shim_supported(pSPARC, DMnd, DMVertices, comm, nlocProj)) {
+        G.n_forward++;
+        Hamiltonian_vectors_mult_kpt_ref(pSPARC, DMnd, DMVertices, Veff_loc, Atom_Influence_nloc, nlocProj, ncol, c, x,
+                                         ldi, Hx, ldo, spin, kpt, comm);
+        return;
+    }
+    shim_init();
+    shim_sync_grid(pSPARC);
+    shim_sync_projectors(pSPARC, Atom_Influence_nloc, nlocProj, 1);
+    if (chefsi_set_veff(G.ctx, Veff_loc) != 0) shim_fatal("chefsi_set_veff");
+    if (chefsi_set_kpoint(G.ctx, pSPARC->k1_loc[kpt], pSPARC->k2_loc[kpt], pSPARC->k3_loc[kpt]) != 0) shim_fatal("chefsi_set_kpoint");
+    if (chefsi_hamiltonian_mult_kpt(G.ctx, ncol, c, x, (size_t)ldi, Hx, (size_t)ldo) != 0) shim_fatal("chefsi_hamiltonian_mult_kpt");
+    G.n_hmult++;
+}
