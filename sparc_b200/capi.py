@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libchefsi_b200.so")
+LIB_PATH = os.environ.get("CHEFSI_B200_LIB") or os.path.join(HERE, "libchefsi_b200.so")  # override: A/B builds only
 
 # every symbol include/chefsi_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = (
