@@ -313,6 +313,7 @@ def run_ours(args):
         "peak_source": peak_src, "avg_launch_ms": st_ms / st_n if st_n else None,
         "algorithmic_bytes_per_launch": alg_bytes_block / m,
         "stencil_share_of_filter": st_ms / (st_ms + nl_ms) if st_ms + nl_ms > 0 else None,
+        "nloc_ms_per_degree": nl_ms / st_n if st_n else None,
     }
 
     # ---- e2e: the same metric through the host-buffer C-ABI call (H2D + D2H inside the timed region) ----

@@ -79,6 +79,8 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
     for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->force_general = getenv("CHEFSI_B200_FORCE_GENERAL") ? atoi(getenv("CHEFSI_B200_FORCE_GENERAL")) : 0;
     if (getenv("CHEFSI_B200_GRIDSYNC")) ctx->stream_gridsync = atoi(getenv("CHEFSI_B200_GRIDSYNC"));
+    if (getenv("CHEFSI_B200_DENSE")) ctx->dense_stream = atoi(getenv("CHEFSI_B200_DENSE"));
+    if (getenv("CHEFSI_B200_NLOC_SHAPE")) ctx->nloc_shape = atoi(getenv("CHEFSI_B200_NLOC_SHAPE"));
     if (getenv("CHEFSI_B200_TMA_L2PROMO")) ctx->tma_l2promo = atoi(getenv("CHEFSI_B200_TMA_L2PROMO")) & 3;
     *out = ctx;
     return 0;
@@ -164,7 +166,7 @@ extern "C" int chefsi_set_grid(chefsi_ctx_t *ctx, const chefsi_grid_t *g)
     ctx->Nd = (size_t)g->Nx * g->Ny * g->Nz;
     {   /* internal layout: halo-padded planes when the streaming kernel applies (see Layout) */
         Layout &L = ctx->lay;
-        const bool padded = stream_layout_wanted(*g) && !ctx->force_general;
+        const bool padded = stream_layout_wanted(*g) && !ctx->force_general && !ctx->dense_stream;
         L.Nx = g->Nx; L.Ny = g->Ny; L.Nz = g->Nz;
         L.px = padded ? 8 : 0;
         L.py = padded ? 6 : 0;

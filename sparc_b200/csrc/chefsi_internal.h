@@ -122,6 +122,8 @@ struct chefsi_ctx {
     int force_general = 0;
     int stream_gridsync = 1;       /* round barrier between the streaming kernel's producers */
     int tma_l2promo = 3;           /* CUtensorMapL2promotion of the streaming kernel's tensor maps */
+    int dense_stream = 0;          /* 1: dense column layout + stencil_stream_dense.cu; 0: halo-padded layout */
+    int nloc_shape = 0;            /* pipeline shape of the fused projector kernel (nloc.cu: launch_mode) */
     unsigned int *d_sync = nullptr;
     unsigned int sync_arrivals = 0;
     char err[512] = {0};
@@ -141,6 +143,8 @@ int launch_stencil_general(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
 bool stream_layout_wanted(const chefsi_grid_t &g);
 bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex);
 int launch_stencil_stream_orth(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
+bool stream_dense_wanted(const chefsi_grid_t &g);
+int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a);
 
 /* nloc.cu: see launch_nloc for the three modes */
 enum { NLOC_PROJECT = 0, NLOC_FUSED = 1, NLOC_EXPAND = 2 };

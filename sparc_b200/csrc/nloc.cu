@@ -37,12 +37,20 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kCols = 32;            /* real word columns per CTA (lanes) */
-constexpr int kP = 64;               /* sphere points per chunk */
-constexpr int kPitch = kP + 1;       /* odd pitch: conflict-free column-strided LDS */
-constexpr int kPtsPerWarp = kP / kWarps;
+
+/* Pipeline shape: T threads per CTA, S-deep ring of KP-point chunks.  The gather is latency-bound
+ * (ncu: long_scoreboard + barrier stalls dominate, FP64 pipe ~20 % busy), so what matters is how many
+ * gather bytes an SM keeps in flight: CTAs per SM x (S-1) chunks x KP x 32 columns x 8 B. */
+template <int T_, int S_, int KP_> struct Shape {
+    static constexpr int T = T_, S = S_, KP = KP_;
+    static constexpr int kWarps = T / 32;
+    static constexpr int kPitch = KP + 1;       /* odd pitch: conflict-free column-strided LDS */
+    static constexpr int kPtsPerWarp = KP / kWarps;
+    static constexpr int H = KP / 32;           /* points per lane in the gather / scatter phases */
+    static constexpr int kColsPerWarp = kCols / kWarps;
+    static_assert(KP % 32 == 0 && KP % kWarps == 0 && kCols % kWarps == 0, "shape");
+};
 
 enum { MODE_PROJECT = 0, MODE_FUSED = 1, MODE_EXPAND = 2, MODE_EXPAND_ATOMIC = 3 };
 
@@ -70,24 +78,26 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int NP> struct Smem {
-    double V[2][kCols][kPitch];
-    double chi[2][kP][NP];
-    int pos[2][kP];
-    int mx[2][kP];
-    int my[2][kP];
+template <int NP, class SH> struct Smem {
+    double V[SH::S][kCols][SH::kPitch];
+    double chi[SH::S][SH::KP][NP];
+    int pos[SH::S][SH::KP];
+    int mx[SH::S][SH::KP];
+    int my[SH::S][SH::KP];
 };
 
 /* vec: MODE_PROJECT -> the input block x (read only); otherwise the output block (read-modify-write).
  * Word column wc of the block lives at vec + (wc / WORDS) * ld * WORDS + (wc % WORDS), element stride WORDS. */
-template <int NP, int WORDS, int MODE>
-__global__ void __launch_bounds__(kThreads, (NP <= 20) ? 2 : 1)
+template <int NP, int WORDS, int MODE, class SH>
+__global__ void __launch_bounds__(SH::T, ((NP <= 20) ? 2 : 1) * (256 / SH::T))
 nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__restrict__ alpha_next,
             double *__restrict__ vec, const size_t ld, const int ncol, const int ngroups, const double scale,
             const double dV)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<NP> &S = *reinterpret_cast<Smem<NP> *>(smem_raw);
+    constexpr int kThreads = SH::T, kWarps = SH::kWarps, kP = SH::KP, kPtsPerWarp = SH::kPtsPerWarp, NS = SH::S;
+    constexpr int H = SH::H, kCPW = SH::kColsPerWarp;
+    Smem<NP, SH> &S = *reinterpret_cast<Smem<NP, SH> *>(smem_raw);
 
     const int J = blockIdx.x / ngroups, grp = blockIdx.x % ngroups;
     const int atom = nl.img_atom[J];
@@ -136,18 +146,26 @@ nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__
     }
 
     /* ---- chunk pipeline ------------------------------------------------------------------------------ */
-    /* phase A/C mapping: lane <-> points (lane, lane+32), warp <-> 4 word columns */
+    /* phase A/C mapping: lane <-> points (lane, lane+32, ..), warp <-> kCPW word columns.  The grid
+       positions of the chunk after the one being issued are prefetched into registers (psn) so the
+       cp.async addresses never wait on a dependent global load. */
+    int psn[H];
+    auto load_pos = [&](int k) {
+#pragma unroll
+        for (int h = 0; h < H; h++) {
+            const int pt = k * kP + lane + 32 * h;
+            psn[h] = (k < nchunks && pt < ndc) ? __ldg(pos + pt) : -1;
+        }
+    };
     auto issue_chunk = [&](int k, int buf) {
         const int pt0 = k * kP;
-        int ps[2];
+        int ps[H];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int pt = pt0 + lane + 32 * h;
-            ps[h] = (pt < ndc) ? pos[pt] : -1;
-        }
+        for (int h = 0; h < H; h++) ps[h] = psn[h];
+        load_pos(k + 1);
         if (warp == 0) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < H; h++) {
                 int mx = 0, my = 0;
                 if (ps[h] >= 0 && (nl.mirx | nl.miry)) {
                     const int i = ps[h] % nl.Nxp - nl.px, j = (ps[h] / nl.Nxp) % nl.Nyp - nl.py;
@@ -161,12 +179,12 @@ nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__
         }
         if (MODE != MODE_EXPAND_ATOMIC) {
 #pragma unroll
-            for (int c = 0; c < kCols / kWarps; c++) {
-                const int cl = warp * (kCols / kWarps) + c;
+            for (int c = 0; c < kCPW; c++) {
+                const int cl = warp * kCPW + c;
                 const int wc = wc0 + cl;
                 const double *base = vec + ((size_t)(wc / WORDS) * ld) * WORDS + (wc % WORDS);
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
+                for (int h = 0; h < H; h++) {
                     double *dst = &S.V[buf][cl][lane + 32 * h];
                     if (ps[h] >= 0 && wc < nwc) cp_async8(dst, base + (size_t)ps[h] * WORDS);
                     else *dst = 0.0;
@@ -181,15 +199,20 @@ nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__
             if (2 * t < npts * NP) cp_async16(dstc + 2 * t, src + 2 * t);
             else { dstc[2 * t] = 0.0; dstc[2 * t + 1] = 0.0; }
         }
-        cp_async_commit();
     };
 
-    issue_chunk(0, 0);
+    load_pos(0);
+#pragma unroll
+    for (int s = 0; s < NS - 1; s++) {
+        if (s < nchunks) issue_chunk(s, s);
+        cp_async_commit();
+    }
     for (int k = 0; k < nchunks; k++) {
-        const int buf = k & 1;
-        cp_async_wait<0>();
-        __syncthreads(); /* chunk k has landed; everybody is done with phase C of chunk k-1 (buffer buf^1) */
-        if (k + 1 < nchunks) issue_chunk(k + 1, buf ^ 1); /* in flight during phases B and C of chunk k */
+        const int buf = k % NS;
+        cp_async_wait<NS - 2>();
+        __syncthreads(); /* chunk k has landed; everybody is done with phase C of chunk k-1 (its buffer is refilled now) */
+        if (k + NS - 1 < nchunks) issue_chunk(k + NS - 1, (k + NS - 1) % NS); /* in flight during phases B and C */
+        cp_async_commit();
 
         /* ---- B: lanes <-> columns, warp handles points warp*kPtsPerWarp .. ---- */
 #pragma unroll 1
@@ -222,14 +245,14 @@ nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__
         /* ---- C: scatter back (lanes <-> points) ---- */
         if (MODE != MODE_PROJECT) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < H; h++) {
                 const int pl = lane + 32 * h;
                 const int ps = S.pos[buf][pl];
                 if (ps < 0) continue;
                 const int mx = S.mx[buf][pl], my = S.my[buf][pl];
 #pragma unroll
-                for (int c = 0; c < kCols / kWarps; c++) {
-                    const int cl = warp * (kCols / kWarps) + c;
+                for (int c = 0; c < kCPW; c++) {
+                    const int cl = warp * kCPW + c;
                     const int wc = wc0 + cl;
                     if (wc >= nwc) continue;
                     double *base = vec + ((size_t)(wc / WORDS) * ld) * WORDS + (wc % WORDS);
@@ -245,6 +268,7 @@ nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__
             }
         }
     }
+    cp_async_wait<0>();
 
     /* ---- alpha_next[J] = dV * phase_J * sum over warps of acc ----------------------------------------- */
     if (MODE == MODE_PROJECT || MODE == MODE_FUSED) {
@@ -288,13 +312,14 @@ __global__ void nloc_patch_kernel(double *__restrict__ out, const size_t ld, con
     }
 }
 
-template <int NP, int WORDS, int MODE>
-int launch_mode(chefsi_ctx *ctx, const NlocView &v, const double *aprev, double *anext, double *vec, size_t ld, int ncol,
-                double scale)
+template <int NP, int WORDS, int MODE, class SH>
+int launch_shape(chefsi_ctx *ctx, const NlocView &v, const double *aprev, double *anext, double *vec, size_t ld, int ncol,
+                 double scale)
 {
-    constexpr size_t red_bytes = (size_t)kWarps * NP * (kCols + 1) * sizeof(double);
-    constexpr size_t smem = sizeof(Smem<NP>) > red_bytes ? sizeof(Smem<NP>) : red_bytes;
-    auto kern = nloc_kernel<NP, WORDS, MODE>;
+    constexpr int kThreads = SH::T;
+    constexpr size_t red_bytes = (size_t)SH::kWarps * NP * (kCols + 1) * sizeof(double);
+    constexpr size_t smem = sizeof(Smem<NP, SH>) > red_bytes ? sizeof(Smem<NP, SH>) : red_bytes;
+    auto kern = nloc_kernel<NP, WORDS, MODE, SH>;
     {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(nloc): %s", cudaGetErrorString(e)); return -1; }
@@ -306,6 +331,25 @@ int launch_mode(chefsi_ctx *ctx, const NlocView &v, const double *aprev, double 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { chefsi_fail(ctx, "nloc launch: %s", cudaGetErrorString(e)); return -1; }
     return 1;
+}
+
+template <int NP, int WORDS, int MODE>
+int launch_mode(chefsi_ctx *ctx, const NlocView &v, const double *aprev, double *anext, double *vec, size_t ld, int ncol,
+                double scale)
+{
+    /* pipeline shape: CHEFSI_B200_NLOC_SHAPE selects among the instantiated ones (default chosen by measurement,
+       profiles/r1_exp_nloc_shapes.log); only the FUSED mode (the one the filter runs per degree) has alternatives */
+    if (MODE == MODE_FUSED && WORDS == 1) {
+        switch (ctx->nloc_shape) {
+        case 1: return launch_shape<NP, WORDS, MODE, Shape<128, 2, 64>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
+        case 2: return launch_shape<NP, WORDS, MODE, Shape<256, 3, 64>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
+        case 3: return launch_shape<NP, WORDS, MODE, Shape<128, 3, 64>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
+        case 4: return launch_shape<NP, WORDS, MODE, Shape<128, 4, 32>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
+        case 5: return launch_shape<NP, WORDS, MODE, Shape<256, 2, 128>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
+        default: break;
+        }
+    }
+    return launch_shape<NP, WORDS, MODE, Shape<256, 2, 64>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
 }
 
 template <int NP, int WORDS>

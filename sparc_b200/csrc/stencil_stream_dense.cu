@@ -1,34 +1,32 @@
 /*
- * stencil_stream_orth.cu -- streaming fused Chebyshev step for orthogonal cells (sm_100a).
+ * stencil_stream_dense.cu -- streaming fused Chebyshev step for orthogonal cells on the DENSE
+ * (reference) column layout (sm_100a).
  *
  *   out = s1 * ( (-1/2 Lap + Veff + c) x ) - s2 * xprev          (FP64, radius-6 star stencil)
  *
- * This is the kernel the 160^3 x 4096 workload runs on; it replaces, per Chebyshev degree, the
- * reference's haloed copy + stencil_3axis_thread_radius6 (lapVecRoutines.c:185-227, called from
- * :586) + the three scale/axpy/swap passes of ChebyshevFiltering (eigenSolver.c:764-768,787-794)
- * with ONE pass that reads x and xprev once and writes out once (24 B per grid point).
+ * Same job and same consumer arithmetic as stencil_stream_orth.cu (it replaces, per Chebyshev degree,
+ * the reference's haloed copy + stencil_3axis_thread_radius6, lapVecRoutines.c:185-227 called from
+ * :586, + the three scale/axpy/swap passes of ChebyshevFiltering, eigenSolver.c:764-768,787-794), but
+ * the columns are stored exactly as the reference stores them (x fastest, no halo pads), so
+ *   - the DRAM traffic of a step is the algorithmic 24 B per grid point plus halo misses -- the padded
+ *     layout read 18 % pad bytes with every plane and wrote the periodic images back;
+ *   - nothing has to be packed, unpacked or patched around the step (util.cu pack/halo kernels and the
+ *     image stores of the projector kernel drop out).
  *
- * Design (2.5-D streaming, one persistent CTA per SM):
- *   - columns live in the halo-padded internal layout (chefsi_internal.h: Layout), so the haloed
- *     TX+12 x TY+12 tile of any xy-plane is one in-bounds box of a 4-D tensor map (x, y, z, column);
- *   - a work item is (orbital column, TX x TY tile of the xy-plane); the CTA marches the whole z
- *     extent of the item, so halos are re-read only in x/y, and neighbouring tiles of a column are
- *     in flight on other SMs at the same time, which turns those re-reads into L2 hits;
- *   - a producer warp streams, per z-plane, three TMA boxes (cp.async.bulk.tensor -> UTMALDG) into a
- *     kStages-deep shared-memory ring: the haloed x tile of plane p, the Veff tile of plane p and the
- *     xprev tile of plane p-6 (the plane whose result is completed by plane p); completion is counted
- *     on an mbarrier per stage, consumers release a stage through a second mbarrier;
- *   - 16x8-point warps: a thread owns 4 consecutive x of one row (16 B shared loads, 32 B global
- *     stores); box widths are chosen so that every row pitch is an odd number of 16-byte chunks, which
- *     makes every LDS.128 wavefront of this thread layout bank-conflict free;
- *   - the z direction never touches shared memory: each thread keeps the last 6 input planes and
- *     7 partial output accumulators of its 4 points in registers (scatter form: a plane adds its
- *     own x/y terms and the z terms of the 6 planes behind it when it arrives, and is added into
- *     the 6 accumulators behind it); the plane loop is unrolled by 7 so the register queues rotate
- *     by renaming instead of moves;
- *   - Veff, c, the recurrence scale s1 and the -s2*xprev term are applied in registers; the result
- *     plane (6 behind the one just loaded) is written with 256-bit stores, together with its periodic
- *     images in the halo pads (the next step's TMA boxes read them; Dirichlet pads stay zero).
+ * What replaces the pads: the haloed (TX+12+2) x (8+TY+6) tile of a plane is still fetched by TMA, but
+ *   - Dirichlet faces and tile parts outside the grid come from the TMA out-of-bounds zero fill;
+ *   - a periodic y face splits the tile into up to three boxes (top halo rows / body / bottom halo rows)
+ *     whose y coordinates are wrapped separately; they land in consecutive rows of the same shared tile
+ *     (8 top rows instead of 6 keep every box start 128-byte aligned);
+ *   - a periodic x face adds a 10-column strip box from the other side of the grid; the consumer
+ *     threads whose +-6 window crosses the face read those 16-byte chunks from the strip through
+ *     per-thread offsets computed once per work item (6 registers, 6 integer adds per plane).
+ * Tiles never hang over the grid edge: the last tile of a row/column is shifted inwards (x0 = Nx - TX)
+ * and the threads that would recompute its neighbour's points are masked.
+ *
+ * Everything else (persistent CTA per SM, producer warp + 5-stage mbarrier ring, 4 points per thread,
+ * z in registers, round barrier between producers so xy-halos hit L2) is as described in
+ * stencil_stream_orth.cu and DESIGN.md section 4.
  */
 #include <cuda.h>
 
@@ -38,29 +36,46 @@ namespace {
 
 constexpr int R = 6;        /* FD radius this kernel is specialised for (FD_ORDER 12) */
 constexpr int kStages = 5;  /* shared memory ring depth */
+constexpr int HT = 8;       /* top halo rows held in the tile (6 used) */
+constexpr int SW = 10;      /* width of the periodic-x strips: 5 x 16 B, an odd number of chunks */
 
 template <int WX, int WY> struct TileCfg {
     static constexpr int TX = 16 * WX;           /* tile width  (points) */
     static constexpr int TY = 8 * WY;            /* tile height (points) */
     static constexpr int YP = TX + 2 * R + 2;    /* haloed tile pitch (doubles): odd number of 16 B chunks */
-    static constexpr int YROWS = TY + 2 * R;
+    static constexpr int YROWS = HT + TY + R;
     static constexpr int XP = TX + 2;            /* xprev / Veff tile pitch */
     static constexpr int Y_BYTES = ((YP * YROWS * 8 + 127) / 128) * 128;
+    static constexpr int S_BYTES = ((SW * TY * 8 + 127) / 128) * 128;
     static constexpr int X_BYTES = ((XP * TY * 8 + 127) / 128) * 128;
-    static constexpr int STAGE_BYTES = Y_BYTES + 2 * X_BYTES;
+    static constexpr int OFF_L = Y_BYTES;
+    static constexpr int OFF_R = OFF_L + S_BYTES;
+    static constexpr int OFF_V = OFF_R + S_BYTES;
+    static constexpr int OFF_X = OFF_V + X_BYTES;
+    static constexpr int STAGE_BYTES = OFF_X + X_BYTES;
     static constexpr int CONSUMER_WARPS = WX * WY;
     static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
     static constexpr size_t SMEM = (size_t)kStages * STAGE_BYTES + 2 * kStages * sizeof(unsigned long long);
     static_assert((YP / 2) % 2 == 1 && (XP / 2) % 2 == 1, "row pitches must be an odd number of 16-byte chunks");
+    static_assert((YP * HT * 8) % 128 == 0 && (YP * TY * 8) % 128 == 0, "box starts must be 128-byte aligned");
 };
 
-struct StreamDesc {
+struct DenseDesc {
     int Nx, Ny, Nz;
-    int Nxp, Nyp, px, py;
     int bc[3];
     int ntx, nty;
     double coef0;
     double wx[R + 1], wy[R + 1], wz[R + 1];
+};
+
+struct DenseMaps {
+    CUtensorMap y_full;   /* YP x YROWS : the whole haloed tile in one box        */
+    CUtensorMap y_top;    /* YP x HT                                               */
+    CUtensorMap y_body;   /* YP x TY                                               */
+    CUtensorMap y_bot;    /* YP x R                                                */
+    CUtensorMap y_strip;  /* SW x TY    : periodic-x strips                        */
+    CUtensorMap xprev;    /* XP x TY                                               */
+    CUtensorMap veff;     /* XP x TY                                               */
 };
 
 /* ---- PTX helpers ---------------------------------------------------------------------- */
@@ -105,30 +120,34 @@ __device__ __forceinline__ void stg256(double *p, const double (&v)[4])
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 
+/* origin of tile t along an axis of N points tiled by T: the last tile is shifted inwards */
+__device__ __forceinline__ int tile_origin(int t, int T, int N) { return min(t * T, N - T); }
+
 /* ---- one plane step of a consumer thread -------------------------------------------------- */
 /* U = (p + 7) mod 7 (compile time): register-queue rotation by renaming.                      */
 template <class Cfg, int U>
-__device__ __forceinline__ void consume_plane(const StreamDesc &d, const StepArgs &a, const unsigned char *stage, int p,
-                                              bool active, int qx, int ry, double *__restrict__ out_row,
-                                              size_t plane_elems, int img_x, int img_y, double (&in)[7][4],
-                                              double (&acc)[7][4], bool plane_is_zero)
+__device__ __forceinline__ void consume_plane(const DenseDesc &d, const StepArgs &a, const unsigned char *stage, int p,
+                                              bool active, int qx, int ry, const int (&xo)[6], double *__restrict__ out_row,
+                                              size_t plane_elems, double (&in)[7][4], double (&acc)[7][4], bool plane_is_zero)
 {
     const int Nz = d.Nz;
     const bool interior = (p >= 0) && (p < Nz);
     const int o = p - R;
     const bool emit = active && o >= 0 && o < Nz;
     const double *ytile = reinterpret_cast<const double *>(stage);
-    const double *vtile = reinterpret_cast<const double *>(stage + Cfg::Y_BYTES);
-    const double *xtile = reinterpret_cast<const double *>(stage + Cfg::Y_BYTES + Cfg::X_BYTES);
+    const double *vtile = reinterpret_cast<const double *>(stage + Cfg::OFF_V);
+    const double *xtile = reinterpret_cast<const double *>(stage + Cfg::OFF_X);
 
     double v[4] = {0, 0, 0, 0};
     if (active && !plane_is_zero) {
-        const double *rowp = ytile + (ry + R) * Cfg::YP + 4 * qx; /* haloed row, element 0 = x0-6+4qx */
+        const double *rowp = ytile + (ry + HT) * Cfg::YP + 4 * qx; /* haloed row, element 0 = x0-6+4qx */
         if (interior) {
             double xr[16];
 #pragma unroll
             for (int t = 0; t < 8; t++) {
-                const double2 w = *reinterpret_cast<const double2 *>(rowp + 2 * t);
+                /* chunks 0..2 / 5..7 may lie across a periodic x face: their address was resolved per item */
+                const double2 w = (t == 3 || t == 4) ? *reinterpret_cast<const double2 *>(rowp + 2 * t)
+                                                     : *reinterpret_cast<const double2 *>(stage + xo[t < 3 ? t : t - 2]);
                 xr[2 * t] = w.x;
                 xr[2 * t + 1] = w.y;
             }
@@ -201,19 +220,14 @@ __device__ __forceinline__ void consume_plane(const StreamDesc &d, const StepArg
 #pragma unroll
             for (int j = 0; j < 4; j++) res[j] = a.s1 * acc[(U + 1) % 7][j];
         }
-        double *dst = out_row + (size_t)o * plane_elems;
-        stg256(dst, res);
-        /* periodic images into the halo pads (img_x / img_y: element offsets, 0 = none) */
-        if (img_x) stg256(dst + img_x, res);
-        if (img_y) stg256(dst + img_y, res);
+        stg256(out_row + (size_t)o * plane_elems, res);
     }
 }
 
 template <int WX, int WY>
 __global__ void __launch_bounds__(TileCfg<WX, WY>::THREADS, 1)
-stream_orth_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xprev,
-                   const __grid_constant__ CUtensorMap map_veff, const __grid_constant__ StreamDesc d, const StepArgs a,
-                   const int nitems, unsigned int *__restrict__ sync_counter, const unsigned int sync_base)
+stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constant__ DenseDesc d, const StepArgs a,
+                    const int nitems, unsigned int *__restrict__ sync_counter, const unsigned int sync_base)
 {
     using Cfg = TileCfg<WX, WY>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -231,9 +245,9 @@ stream_orth_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
     __syncthreads();
 
-    const int Nz = d.Nz;
-    const bool zper = (d.bc[2] == 0);
-    const size_t plane_elems = (size_t)d.Nxp * d.Nyp;
+    const int Nx = d.Nx, Ny = d.Ny, Nz = d.Nz;
+    const bool xper = (d.bc[0] == 0), yper = (d.bc[1] == 0), zper = (d.bc[2] == 0);
+    const size_t plane_elems = (size_t)Nx * Ny;
     uint32_t it = 0; /* ring position, continues across work items */
 
     if (warp == Cfg::CONSUMER_WARPS) {
@@ -242,16 +256,19 @@ stream_orth_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             unsigned int round = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, round++) {
                 const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
-                const int x0 = (tile % d.ntx) * Cfg::TX, y0 = (tile / d.ntx) * Cfg::TY;
+                const int x0 = tile_origin(tile % d.ntx, Cfg::TX, Nx), y0 = tile_origin(tile / d.ntx, Cfg::TY, Ny);
+                /* which pieces this tile's haloed plane consists of (constant over z) */
+                const bool wrap_top = yper && (y0 - R < 0), wrap_bot = yper && (y0 + Cfg::TY + R > Ny);
+                const bool split_y = wrap_top || wrap_bot;
+                const int ytop = wrap_top ? y0 - HT + Ny : y0 - HT;
+                const int ybot = wrap_bot ? y0 + Cfg::TY - Ny : y0 + Cfg::TY;
+                const bool need_l = xper && (x0 - R < 0), need_r = xper && (x0 + Cfg::TX + R > Nx);
+                const uint32_t ybytes = (uint32_t)(Cfg::YP * Cfg::YROWS * 8 + (need_l ? SW * Cfg::TY * 8 : 0) +
+                                                   (need_r ? SW * Cfg::TY * 8 : 0));
                 if (sync_counter) {
-                    /* Round barrier between the producers of all (co-resident) CTAs: neighbouring tiles of a
-                       column are marched by neighbouring CTAs in the same round; starting them together keeps
-                       their z positions within the L2 residence time of a line (~20 us at 5.6 TB/s), so the
-                       xy-halo of a tile is an L2 hit on the plane its neighbour fetched (a CTA that runs
-                       ahead misses and is slowed down, one that lags hits: the skew is self-correcting).
-                       Only the CTAs that have an item in this round take part; the spin is bounded. */
+                    /* round barrier between the producers of all (co-resident) CTAs: see stencil_stream_orth.cu */
                     const unsigned int in_round = (unsigned int)min((long long)gridDim.x, (long long)nitems - (long long)round * gridDim.x);
-                    const unsigned int done_before = round * gridDim.x; /* arrivals of the earlier (full) rounds */
+                    const unsigned int done_before = round * gridDim.x;
                     __threadfence();
                     atomicAdd(sync_counter, 1u);
                     const unsigned int target = sync_base + done_before + in_round;
@@ -270,13 +287,21 @@ stream_orth_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     const int s = it % kStages;
                     unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
                     mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
-                    mbar_expect_tx(&full[s], (uint32_t)((need_y ? Cfg::YP * Cfg::YROWS * 8 : 0) +
-                                                        (need_v ? Cfg::XP * Cfg::TY * 8 : 0) +
-                                                        (need_x ? Cfg::XP * Cfg::TY * 8 : 0)));
-                    if (need_y) tma_load_4d(stage, &map_x, d.px + x0 - R, d.py + y0 - R, kz, n, &full[s]);
-                    if (need_v) tma_load_4d(stage + Cfg::Y_BYTES, &map_veff, d.px + x0, d.py + y0, p, 0, &full[s]);
-                    if (need_x)
-                        tma_load_4d(stage + Cfg::Y_BYTES + Cfg::X_BYTES, &map_xprev, d.px + x0, d.py + y0, o, n, &full[s]);
+                    mbar_expect_tx(&full[s], (need_y ? ybytes : 0u) + (uint32_t)((need_v ? Cfg::XP * Cfg::TY * 8 : 0) +
+                                                                                (need_x ? Cfg::XP * Cfg::TY * 8 : 0)));
+                    if (need_y) {
+                        if (!split_y) {
+                            tma_load_4d(stage, &maps.y_full, x0 - R, y0 - HT, kz, n, &full[s]);
+                        } else {
+                            tma_load_4d(stage, &maps.y_top, x0 - R, ytop, kz, n, &full[s]);
+                            tma_load_4d(stage + Cfg::YP * HT * 8, &maps.y_body, x0 - R, y0, kz, n, &full[s]);
+                            tma_load_4d(stage + Cfg::YP * (HT + Cfg::TY) * 8, &maps.y_bot, x0 - R, ybot, kz, n, &full[s]);
+                        }
+                        if (need_l) tma_load_4d(stage + Cfg::OFF_L, &maps.y_strip, Nx - SW, y0, kz, n, &full[s]);
+                        if (need_r) tma_load_4d(stage + Cfg::OFF_R, &maps.y_strip, 0, y0, kz, n, &full[s]);
+                    }
+                    if (need_v) tma_load_4d(stage + Cfg::OFF_V, &maps.veff, x0, y0, p, 0, &full[s]);
+                    if (need_x) tma_load_4d(stage + Cfg::OFF_X, &maps.xprev, x0, y0, o, n, &full[s]);
                     it++;
                 }
             }
@@ -289,15 +314,25 @@ stream_orth_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         double in[7][4], acc[7][4];
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
-            const int x0 = (tile % d.ntx) * Cfg::TX, y0 = (tile / d.ntx) * Cfg::TY;
+            const int tx = tile % d.ntx, ty = tile / d.ntx;
+            const int x0 = tile_origin(tx, Cfg::TX, Nx), y0 = tile_origin(ty, Cfg::TY, Ny);
             const int gx = x0 + 4 * qx, gy = y0 + ry;
-            const bool active = (gx < d.Nx) && (gy < d.Ny);
-            double *out_row = reinterpret_cast<double *>(a.out) + (size_t)n * a.ld +
-                              ((size_t)(gy + d.py)) * d.Nxp + (gx + d.px);
-            /* where this thread's quad is mirrored in the halo pads (periodic faces only) */
-            int img_x = 0, img_y = 0;
-            if (d.bc[0] == 0) { if (gx < d.px) img_x = d.Nx; else if (gx >= d.Nx - d.px) img_x = -d.Nx; }
-            if (d.bc[1] == 0) { if (gy < d.py) img_y = d.Ny * d.Nxp; else if (gy >= d.Ny - d.py) img_y = -d.Ny * d.Nxp; }
+            /* a shifted last tile overlaps its neighbour: only the not yet covered points are computed */
+            const bool active = (gx >= tx * Cfg::TX) && (gy >= ty * Cfg::TY);
+            double *out_row = reinterpret_cast<double *>(a.out) + (size_t)n * a.ld + (size_t)gy * Nx + gx;
+            /* byte offsets (inside a stage) of the 16-byte chunks 0,1,2 and 5,6,7 of this thread's x window */
+            int xo[6];
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                const int t = q < 3 ? q : q + 2;
+                const int gi = gx - R + 2 * t;
+                int off = ((ry + HT) * Cfg::YP + 4 * qx + 2 * t) * 8;
+                if (xper) {
+                    if (gi < 0) off = Cfg::OFF_L + (ry * SW + gi + SW) * 8;
+                    else if (gi >= Nx) off = Cfg::OFF_R + (ry * SW + gi - Nx) * 8;
+                }
+                xo[q] = off;
+            }
 #pragma unroll
             for (int u = 0; u < 7; u++)
 #pragma unroll
@@ -315,8 +350,7 @@ stream_orth_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             stage = ring + (size_t)s * Cfg::STAGE_BYTES;                                                 \
             mbar_wait(&full[s], (it / kStages) & 1);                                                     \
         }                                                                                                \
-        consume_plane<Cfg, (U)>(d, a, stage, pp, active, qx, ry, out_row, plane_elems, img_x, img_y,     \
-                                in, acc, zplane);                                                        \
+        consume_plane<Cfg, (U)>(d, a, stage, pp, active, qx, ry, xo, out_row, plane_elems, in, acc, zplane); \
         if (use_stage) {                                                                                 \
             __syncwarp();                                                                                \
             if (lane == 0) mbar_arrive(&empty[s]);                                                       \
@@ -357,13 +391,13 @@ PFN_encodeTiled get_encode()
     return fn;
 }
 
-/* 4-D view (x, y, z, column) of a block of columns in the internal layout */
+/* 4-D view (x, y, z, column) of a block of dense columns; elements outside [0,N) read as zero */
 bool make_map(CUtensorMap *map, const void *base, const Layout &L, int ncol, int box_x, int box_y, int promo)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return false;
-    cuuint64_t dims[4] = {(cuuint64_t)L.Nxp, (cuuint64_t)L.Nyp, (cuuint64_t)L.Nz, (cuuint64_t)(ncol > 0 ? ncol : 1)};
-    cuuint64_t strides[3] = {(cuuint64_t)L.Nxp * 8, (cuuint64_t)L.plane * 8, (cuuint64_t)L.ld * 8};
+    cuuint64_t dims[4] = {(cuuint64_t)L.Nx, (cuuint64_t)L.Ny, (cuuint64_t)L.Nz, (cuuint64_t)(ncol > 0 ? ncol : 1)};
+    cuuint64_t strides[3] = {(cuuint64_t)L.Nx * 8, (cuuint64_t)L.plane * 8, (cuuint64_t)L.ld * 8};
     cuuint32_t box[4] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, es,
@@ -377,9 +411,8 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
     using Cfg = TileCfg<WX, WY>;
     const chefsi_grid_t &g = ctx->grid;
     const Layout &L = ctx->lay;
-    StreamDesc d;
+    DenseDesc d;
     d.Nx = g.Nx; d.Ny = g.Ny; d.Nz = g.Nz;
-    d.Nxp = L.Nxp; d.Nyp = L.Nyp; d.px = L.px; d.py = L.py;
     d.bc[0] = g.BCx; d.bc[1] = g.BCy; d.bc[2] = g.BCz;
     d.ntx = (g.Nx + Cfg::TX - 1) / Cfg::TX;
     d.nty = (g.Ny + Cfg::TY - 1) / Cfg::TY;
@@ -388,15 +421,17 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
     const long long nitems = (long long)a.ncol * d.ntx * d.nty;
     if (nitems > 0x7fffffffLL) { chefsi_fail(ctx, "stream kernel: too many work items"); return -1; }
 
-    CUtensorMap mx, mp, mv;
+    DenseMaps m;
     const void *xp = a.xprev ? a.xprev : a.x; /* never dereferenced when s2 == 0 */
     const int promo = ctx->tma_l2promo;
-    if (!make_map(&mx, a.x, L, a.ncol, Cfg::YP, Cfg::YROWS, promo) || !make_map(&mp, xp, L, a.ncol, Cfg::XP, Cfg::TY, promo) ||
-        !make_map(&mv, ctx->d_veff, L, 1, Cfg::XP, Cfg::TY, promo)) {
+    if (!make_map(&m.y_full, a.x, L, a.ncol, Cfg::YP, Cfg::YROWS, promo) || !make_map(&m.y_top, a.x, L, a.ncol, Cfg::YP, HT, promo) ||
+        !make_map(&m.y_body, a.x, L, a.ncol, Cfg::YP, Cfg::TY, promo) || !make_map(&m.y_bot, a.x, L, a.ncol, Cfg::YP, R, promo) ||
+        !make_map(&m.y_strip, a.x, L, a.ncol, SW, Cfg::TY, promo) || !make_map(&m.xprev, xp, L, a.ncol, Cfg::XP, Cfg::TY, promo) ||
+        !make_map(&m.veff, ctx->d_veff, L, 1, Cfg::XP, Cfg::TY, promo)) {
         chefsi_fail(ctx, "cuTensorMapEncodeTiled failed");
         return -1;
     }
-    auto kern = stream_orth_kernel<WX, WY>;
+    auto kern = stream_dense_kernel<WX, WY>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(stream): %s", cudaGetErrorString(e)); return -1; }
     const int grid = (int)((nitems < ctx->num_sms) ? nitems : ctx->num_sms);
@@ -415,11 +450,11 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
     }
     int nit = (int)nitems;
     if (counter) { /* the barrier needs all CTAs co-resident: cooperative launch refuses otherwise */
-        void *args[] = {(void *)&mx, (void *)&mp, (void *)&mv, (void *)&d, (void *)&a, (void *)&nit, (void *)&counter, (void *)&base};
+        void *args[] = {(void *)&m, (void *)&d, (void *)&a, (void *)&nit, (void *)&counter, (void *)&base};
         e = cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Cfg::THREADS), args, Cfg::SMEM, ctx->stream);
         if (e != cudaSuccess) { chefsi_fail(ctx, "stream kernel cooperative launch: %s", cudaGetErrorString(e)); return -1; }
     } else {
-        kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(mx, mp, mv, d, a, nit, counter, base);
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(m, d, a, nit, counter, base);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) { chefsi_fail(ctx, "stream kernel launch: %s", cudaGetErrorString(e)); return -1; }
@@ -428,28 +463,22 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
 
 }  // namespace
 
-/* The streaming kernel needs: orthogonal cell, FD radius 6, real data, Nx a multiple of 4 (each
- * thread owns an aligned quad; TMA strides must be 16-byte multiples), the halo-padded layout, and a
- * grid big enough that tiles are not mostly halo.  Everything else goes through the general kernel. */
-bool stream_layout_wanted(const chefsi_grid_t &g)
+/* The dense streaming kernel needs: orthogonal cell, FD radius 6, real data, Nx a multiple of 4 (each
+ * thread owns an aligned quad; TMA strides must be 16-byte multiples), at least one full 32 x 32 tile
+ * per plane, and -- for a periodic y face -- a tile row count such that no 6-row halo box straddles
+ * the face (Ny mod 32 is 0 or >= 6).  Everything else goes through the general kernel. */
+bool stream_dense_wanted(const chefsi_grid_t &g)
 {
+    using Cfg = TileCfg<2, 4>;
     if (g.cell_typ != 0 || g.FDn != R) return false;
     if (g.Nx % 4 != 0) return false;
-    if (g.Nx < 32 || g.Ny < 16 || g.Nz < 2 * R) return false;
+    if (g.Nx < Cfg::TX || g.Ny < Cfg::TY || g.Nz < 2 * R) return false;
+    if (g.BCy == 0 && g.Ny % Cfg::TY != 0 && g.Ny % Cfg::TY < R) return false;
     return true;
 }
 
-bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex)
+int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a)
 {
-    if (ctx->force_general || is_complex) return false;
-    if (ctx->dense_stream) return ctx->lay.px == 0 && ctx->lay.py == 0 && stream_dense_wanted(ctx->grid);
-    return ctx->lay.px == 8 && ctx->lay.py == R && stream_layout_wanted(ctx->grid);
-}
-
-int launch_stencil_stream_orth(chefsi_ctx *ctx, const StepArgs &a, bool is_complex)
-{
-    (void)is_complex;
     if (a.ncol <= 0) return 0;
-    if (ctx->dense_stream) return launch_stencil_stream_dense(ctx, a);
     return launch_cfg<2, 4>(ctx, a);
 }

@@ -139,6 +139,60 @@ def test_stream_kernel_vs_oracle(ctx, port, N, BC):
     assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
 
 
+@pytest.fixture(scope="module")
+def ctx_dense():
+    """Context on the dense (reference) column layout: stencil_stream_dense.cu."""
+    import os
+    from sparc_b200.chefsi import ChefsiContext
+    os.environ["CHEFSI_B200_DENSE"] = "1"
+    try:
+        c = ChefsiContext(0)
+    finally:
+        del os.environ["CHEFSI_B200_DENSE"]
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("N,BC", [((32, 32, 24), (0, 0, 0)), ((48, 40, 20), (0, 0, 0)), ((36, 38, 16), (0, 0, 0)),
+                                   ((96, 96, 13), (0, 0, 0)), ((32, 32, 16), (1, 0, 1)), ((64, 32, 16), (0, 1, 0)),
+                                   ((32, 64, 12), (1, 1, 1)), ((40, 70, 12), (0, 0, 1)), ((68, 36, 12), (0, 1, 0))])
+def test_dense_stream_kernel_vs_oracle(ctx_dense, port, N, BC):
+    """Dense-layout streaming kernel: single tiles that wrap on both sides, shifted (overlapping) last
+    tiles, interior tiles (one TMA box), periodic-x strips, split periodic-y boxes, Dirichlet faces
+    (TMA zero fill)."""
+    ctx = ctx_dense
+    g = P.make_grid(N, tuple(0.45 * n for n in N), BC=BC)
+    veff = P.synthetic_veff(g)
+    proj = P.make_projectors(g, np.array([[0.02, 0.5, 0.97], [0.5, 0.5, 0.5]]), rc=[2.4, 2.0], nproj=[18, 7])
+    x = P.random_columns(g.Nd, 3, seed=11)
+    _setup(ctx, g, veff, proj)
+    a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+    Hx = np.empty_like(x)
+    ctx.Hamiltonian_vectors_mult(-0.3, x, Hx)
+    assert ctx.stats()["last_path"] == 1
+    assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, -0.3, x)) < TOL
+    X = x.copy()
+    Y = np.empty_like(X)
+    ctx.ChebyshevFiltering(X, Y, 8, a, b, a0)
+    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 8, a, b, a0)
+    assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+
+
+def test_dense_stream_many_columns_round_barrier(ctx_dense, port):
+    """More work items than SMs: the persistent CTAs loop over items and the producers' round barrier runs."""
+    ctx = ctx_dense
+    g = P.make_grid((64, 64, 12), (28.8, 28.8, 5.4))
+    veff = P.synthetic_veff(g)
+    x = P.random_columns(g.Nd, 80, seed=5)
+    _setup(ctx, g, veff, None)
+    a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+    X, Y = x.copy(), np.empty_like(x)
+    ctx.ChebyshevFiltering(X, Y, 4, a, b, a0)
+    assert ctx.stats()["last_path"] == 1
+    Xw, Yw = port.chebyshev_filter(g, None, veff, x, 4, a, b, a0)
+    assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+
+
 def test_stream_and_general_kernels_agree(ctx):
     import os
     from sparc_b200.chefsi import ChefsiContext
