@@ -80,6 +80,7 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
     ctx->force_general = getenv("CHEFSI_B200_FORCE_GENERAL") ? atoi(getenv("CHEFSI_B200_FORCE_GENERAL")) : 0;
     if (getenv("CHEFSI_B200_GRIDSYNC")) ctx->stream_gridsync = atoi(getenv("CHEFSI_B200_GRIDSYNC"));
     if (getenv("CHEFSI_B200_DENSE")) ctx->dense_stream = atoi(getenv("CHEFSI_B200_DENSE"));
+    if (getenv("CHEFSI_B200_STREAM_VARIANT")) ctx->stream_variant = atoi(getenv("CHEFSI_B200_STREAM_VARIANT"));
     if (getenv("CHEFSI_B200_NLOC_SHAPE")) ctx->nloc_shape = atoi(getenv("CHEFSI_B200_NLOC_SHAPE"));
     if (getenv("CHEFSI_B200_TMA_L2PROMO")) ctx->tma_l2promo = atoi(getenv("CHEFSI_B200_TMA_L2PROMO")) & 3;
     *out = ctx;

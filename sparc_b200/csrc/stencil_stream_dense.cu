@@ -54,7 +54,12 @@ template <int WX, int WY> struct TileCfg {
     static constexpr int OFF_X = OFF_V + X_BYTES;
     static constexpr int STAGE_BYTES = OFF_X + X_BYTES;
     static constexpr int CONSUMER_WARPS = WX * WY;
-    static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+    /* consumers + one producer WARPGROUP: setmaxnreg moves registers per warpgroup (4 warps), and the register
+       file is per scheduler (16 K registers): with a 9th warp one scheduler hosts 3 warps and ptxas has to cap
+       every thread at 168 registers; with 2 consumer warps + 1 producer warp per scheduler the producers give
+       their registers back (168 -> 40) and the consumers grow to 232 */
+    static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
+    static constexpr int PRODUCER_REGS = 40, CONSUMER_REGS = 232;
     static constexpr size_t SMEM = (size_t)kStages * STAGE_BYTES + 2 * kStages * sizeof(unsigned long long);
     static_assert((YP / 2) % 2 == 1 && (XP / 2) % 2 == 1, "row pitches must be an odd number of 16-byte chunks");
     static_assert((YP * HT * 8) % 128 == 0 && (YP * TY * 8) % 128 == 0, "box starts must be 128-byte aligned");
@@ -224,7 +229,271 @@ __device__ __forceinline__ void consume_plane(const DenseDesc &d, const StepArgs
     }
 }
 
-template <int WX, int WY>
+__device__ __forceinline__ void stg128(double *p, double v0, double v1)
+{
+    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v0), "d"(v1) : "memory");
+}
+
+/* ---- 2 x 2 thread tile (VAR 1) ---------------------------------------------------------------
+ * A thread owns the x pair (2 xp, 2 xp + 1) of rows r0 and r0 + 1 (point index 2*row + j).  Per plane it
+ * reads 2 x 7 chunks for the two x windows, 12 chunks for the rows r0-6 .. r0-1 and r0+2 .. r0+7 (each
+ * halo row serves both output rows) and 2 + 2 chunks of Veff / xprev: 30 LDS.128 per 4 points instead of
+ * the 36 of the 1 x 4 mapping.  A quarter warp reads 8 consecutive chunks of one row: conflict free for
+ * any pitch.  xmask bit q set: chunk q of the x window lies in a periodic-x strip (row pitch SW).      */
+template <class Cfg, int U>
+__device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepArgs &a, const unsigned char *stage, int p,
+                                                bool active, bool act0, bool act1, int xp, int r0, const int (&xo)[6],
+                                                unsigned xmask, double *__restrict__ out_row, size_t plane_elems,
+                                                double (&in)[7][4], double (&acc)[7][4], bool plane_is_zero)
+{
+    const int Nz = d.Nz;
+    const bool interior = (p >= 0) && (p < Nz);
+    const int o = p - R;
+    const bool emit = o >= 0 && o < Nz;
+    const double *ytile = reinterpret_cast<const double *>(stage);
+    const double *vtile = reinterpret_cast<const double *>(stage + Cfg::OFF_V);
+    const double *xtile = reinterpret_cast<const double *>(stage + Cfg::OFF_X);
+
+    double v[4] = {0, 0, 0, 0};
+    if (active && !plane_is_zero) {
+        const double *cp = ytile + (r0 + HT) * Cfg::YP + 2 * xp + R; /* centre chunk of row r0 */
+        if (interior) {
+            double xr[2][14];
+#pragma unroll
+            for (int t = 0; t < 7; t++) {
+                double2 w0, w1;
+                if (t == 3) {
+                    w0 = *reinterpret_cast<const double2 *>(cp);
+                    w1 = *reinterpret_cast<const double2 *>(cp + Cfg::YP);
+                } else {
+                    const int q = t < 3 ? t : t - 1;
+                    const int off0 = xo[q];
+                    const int off1 = off0 + (((xmask >> q) & 1u) ? SW * 8 : Cfg::YP * 8);
+                    w0 = *reinterpret_cast<const double2 *>(stage + off0);
+                    w1 = *reinterpret_cast<const double2 *>(stage + off1);
+                }
+                xr[0][2 * t] = w0.x; xr[0][2 * t + 1] = w0.y;
+                xr[1][2 * t] = w1.x; xr[1][2 * t + 1] = w1.y;
+            }
+            double ve[4] = {0, 0, 0, 0};
+            if (a.veff) {
+                const double2 w0 = *reinterpret_cast<const double2 *>(vtile + r0 * Cfg::XP + 2 * xp);
+                const double2 w1 = *reinterpret_cast<const double2 *>(vtile + (r0 + 1) * Cfg::XP + 2 * xp);
+                ve[0] = w0.x; ve[1] = w0.y; ve[2] = w1.x; ve[3] = w1.y;
+            }
+            double t4[4], sx[4], sy[4], sz[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int row = i >> 1, j = i & 1;
+                v[i] = xr[row][R + j];
+                t4[i] = (d.coef0 + a.c + ve[i]) * v[i];
+                sx[i] = d.wx[1] * (xr[row][R + j - 1] + xr[row][R + j + 1]);
+                sz[i] = d.wz[1] * in[(U - 1 + 7) % 7][i];
+            }
+#pragma unroll
+            for (int r = 2; r <= R; r++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int row = i >> 1, j = i & 1;
+                    sx[i] = fma(d.wx[r], xr[row][R + j - r] + xr[row][R + j + r], sx[i]);
+                    sz[i] = fma(d.wz[r], in[(U - r + 7) % 7][i], sz[i]);
+                }
+            /* y: up[k] = row r0-k, dn[k] = row r0+1+k (k = 1..6); row r0 pairs up[k] with (k == 1 ? own row 1 : dn[k-1]),
+               row r0+1 pairs (k == 1 ? own row 0 : up[k-1]) with dn[k] */
+            double2 up[R + 1], dn[R + 1];
+            up[0] = make_double2(v[0], v[1]); /* row r0   */
+            dn[0] = make_double2(v[2], v[3]); /* row r0+1 */
+#pragma unroll
+            for (int k = 1; k <= R; k++) {
+                up[k] = *reinterpret_cast<const double2 *>(cp - k * Cfg::YP);
+                dn[k] = *reinterpret_cast<const double2 *>(cp + (1 + k) * Cfg::YP);
+            }
+#pragma unroll
+            for (int k = 1; k <= R; k++) {
+                const double a0 = up[k].x + dn[k - 1].x, a1 = up[k].y + dn[k - 1].y;
+                const double b0 = up[k - 1].x + dn[k].x, b1 = up[k - 1].y + dn[k].y;
+                if (k == 1) {
+                    sy[0] = d.wy[1] * a0; sy[1] = d.wy[1] * a1; sy[2] = d.wy[1] * b0; sy[3] = d.wy[1] * b1;
+                } else {
+                    sy[0] = fma(d.wy[k], a0, sy[0]); sy[1] = fma(d.wy[k], a1, sy[1]);
+                    sy[2] = fma(d.wy[k], b0, sy[2]); sy[3] = fma(d.wy[k], b1, sy[3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[U][i] = (t4[i] + sx[i]) + (sy[i] + sz[i]);
+        } else {
+            const double2 w0 = *reinterpret_cast<const double2 *>(cp);
+            const double2 w1 = *reinterpret_cast<const double2 *>(cp + Cfg::YP);
+            v[0] = w0.x; v[1] = w0.y; v[2] = w1.x; v[3] = w1.y;
+        }
+    }
+    if (p >= 0) { /* scatter the z terms into the 6 accumulators behind this plane */
+#pragma unroll
+        for (int r = 1; r <= R; r++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[(U - r + 7) % 7][i] = fma(d.wz[r], v[i], acc[(U - r + 7) % 7][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) in[U][i] = v[i];
+
+    if (emit && active) {
+        double res[4];
+        if (a.s2 != 0.0) {
+            const double2 w0 = *reinterpret_cast<const double2 *>(xtile + r0 * Cfg::XP + 2 * xp);
+            const double2 w1 = *reinterpret_cast<const double2 *>(xtile + (r0 + 1) * Cfg::XP + 2 * xp);
+            res[0] = fma(-a.s2, w0.x, a.s1 * acc[(U + 1) % 7][0]);
+            res[1] = fma(-a.s2, w0.y, a.s1 * acc[(U + 1) % 7][1]);
+            res[2] = fma(-a.s2, w1.x, a.s1 * acc[(U + 1) % 7][2]);
+            res[3] = fma(-a.s2, w1.y, a.s1 * acc[(U + 1) % 7][3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) res[i] = a.s1 * acc[(U + 1) % 7][i];
+        }
+        double *dst = out_row + (size_t)o * plane_elems;
+        if (act0) stg128(dst, res[0], res[1]);
+        if (act1) stg128(dst + d.Nx, res[2], res[3]);
+    }
+}
+
+/* ---- 2 x 2 thread tile with explicitly batched shared-memory loads (VAR 2) --------------------
+ * Same arithmetic as consume_plane22.  ncu's source view of VAR 0/1 (profiles/r1_ncu_dense_v{0,1}.txt)
+ * shows each LDS.128 issued right before the DADD that consumes it (short_scoreboard = 36 % of the
+ * consumer warps' time at 2 warps per scheduler).  Here the loads of a plane are volatile and issued
+ * in three batches ahead of the arithmetic that hides them:
+ *   both x windows + Veff | z gather | x terms of row 0 | y halo rows + xprev | x terms of row 1 | y terms. */
+__device__ __forceinline__ double2 lds128(uint32_t addr)
+{
+    double2 w;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w.x), "=d"(w.y) : "r"(addr));
+    return w;
+}
+
+template <class Cfg, int U>
+__device__ __forceinline__ void consume_plane22b(const DenseDesc &d, const StepArgs &a, const uint32_t stage, int p,
+                                                 bool active, bool act0, bool act1, int xp, int r0, const int (&xo)[6],
+                                                 unsigned xmask, double *__restrict__ out_row, size_t plane_elems,
+                                                 double (&in)[7][4], double (&acc)[7][4], bool plane_is_zero)
+{
+    const int Nz = d.Nz;
+    const bool interior = (p >= 0) && (p < Nz);
+    const int o = p - R;
+    const bool emit = o >= 0 && o < Nz && active;
+    const uint32_t cp = stage + ((r0 + HT) * Cfg::YP + 2 * xp + R) * 8; /* centre chunk of row r0 */
+    const uint32_t vp = stage + Cfg::OFF_V + (r0 * Cfg::XP + 2 * xp) * 8;
+    const uint32_t pp = stage + Cfg::OFF_X + (r0 * Cfg::XP + 2 * xp) * 8;
+
+    double v[4] = {0, 0, 0, 0};
+    if (active && !plane_is_zero) {
+        if (interior) {
+            /* batch 1: x windows of both rows, Veff */
+            double2 w0[7], w1[7];
+            w0[3] = lds128(cp);
+            w1[3] = lds128(cp + Cfg::YP * 8);
+#pragma unroll
+            for (int t = 0; t < 7; t++) {
+                if (t == 3) continue;
+                const int q = t < 3 ? t : t - 1;
+                w0[t] = lds128(stage + xo[q]);
+            }
+#pragma unroll
+            for (int t = 0; t < 7; t++) {
+                if (t == 3) continue;
+                const int q = t < 3 ? t : t - 1;
+                w1[t] = lds128(stage + xo[q] + (((xmask >> q) & 1u) ? SW * 8 : Cfg::YP * 8));
+            }
+            double2 ve0 = make_double2(0, 0), ve1 = make_double2(0, 0);
+            if (a.veff) { ve0 = lds128(vp); ve1 = lds128(vp + Cfg::XP * 8); }
+            /* z gather (registers only) */
+            double sz[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) sz[i] = d.wz[1] * in[(U - 1 + 7) % 7][i];
+#pragma unroll
+            for (int r = 2; r <= R; r++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) sz[i] = fma(d.wz[r], in[(U - r + 7) % 7][i], sz[i]);
+            /* x terms of row 0 */
+            double xr[14], sx[4], t4[4];
+#pragma unroll
+            for (int t = 0; t < 7; t++) { xr[2 * t] = w0[t].x; xr[2 * t + 1] = w0[t].y; }
+            v[0] = xr[R]; v[1] = xr[R + 1];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                sx[j] = d.wx[1] * (xr[R + j - 1] + xr[R + j + 1]);
+#pragma unroll
+                for (int r = 2; r <= R; r++) sx[j] = fma(d.wx[r], xr[R + j - r] + xr[R + j + r], sx[j]);
+            }
+            t4[0] = (d.coef0 + a.c + ve0.x) * v[0];
+            t4[1] = (d.coef0 + a.c + ve0.y) * v[1];
+            /* batch 2: y halo rows (up[k] = row r0-k, dn[k] = row r0+1+k), xprev */
+            double2 up[R + 1], dn[R + 1];
+#pragma unroll
+            for (int k = 1; k <= R; k++) {
+                up[k] = lds128(cp - k * Cfg::YP * 8);
+                dn[k] = lds128(cp + (1 + k) * Cfg::YP * 8);
+            }
+            /* x terms of row 1 */
+#pragma unroll
+            for (int t = 0; t < 7; t++) { xr[2 * t] = w1[t].x; xr[2 * t + 1] = w1[t].y; }
+            v[2] = xr[R]; v[3] = xr[R + 1];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                sx[2 + j] = d.wx[1] * (xr[R + j - 1] + xr[R + j + 1]);
+#pragma unroll
+                for (int r = 2; r <= R; r++) sx[2 + j] = fma(d.wx[r], xr[R + j - r] + xr[R + j + r], sx[2 + j]);
+            }
+            t4[2] = (d.coef0 + a.c + ve1.x) * v[2];
+            t4[3] = (d.coef0 + a.c + ve1.y) * v[3];
+            /* y terms */
+            up[0] = make_double2(v[0], v[1]);
+            dn[0] = make_double2(v[2], v[3]);
+            double sy[4];
+#pragma unroll
+            for (int k = 1; k <= R; k++) {
+                const double a0 = up[k].x + dn[k - 1].x, a1 = up[k].y + dn[k - 1].y;
+                const double b0 = up[k - 1].x + dn[k].x, b1 = up[k - 1].y + dn[k].y;
+                if (k == 1) {
+                    sy[0] = d.wy[1] * a0; sy[1] = d.wy[1] * a1; sy[2] = d.wy[1] * b0; sy[3] = d.wy[1] * b1;
+                } else {
+                    sy[0] = fma(d.wy[k], a0, sy[0]); sy[1] = fma(d.wy[k], a1, sy[1]);
+                    sy[2] = fma(d.wy[k], b0, sy[2]); sy[3] = fma(d.wy[k], b1, sy[3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[U][i] = (t4[i] + sx[i]) + (sy[i] + sz[i]);
+        } else {
+            const double2 c0 = lds128(cp), c1 = lds128(cp + Cfg::YP * 8);
+            v[0] = c0.x; v[1] = c0.y; v[2] = c1.x; v[3] = c1.y;
+        }
+    }
+    double2 xp0 = make_double2(0, 0), xp1 = make_double2(0, 0);
+    if (emit && a.s2 != 0.0) { xp0 = lds128(pp); xp1 = lds128(pp + Cfg::XP * 8); }
+    if (p >= 0) { /* scatter the z terms into the 6 accumulators behind this plane */
+#pragma unroll
+        for (int r = 1; r <= R; r++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[(U - r + 7) % 7][i] = fma(d.wz[r], v[i], acc[(U - r + 7) % 7][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) in[U][i] = v[i];
+
+    if (emit) {
+        double res[4];
+        if (a.s2 != 0.0) {
+            res[0] = fma(-a.s2, xp0.x, a.s1 * acc[(U + 1) % 7][0]);
+            res[1] = fma(-a.s2, xp0.y, a.s1 * acc[(U + 1) % 7][1]);
+            res[2] = fma(-a.s2, xp1.x, a.s1 * acc[(U + 1) % 7][2]);
+            res[3] = fma(-a.s2, xp1.y, a.s1 * acc[(U + 1) % 7][3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) res[i] = a.s1 * acc[(U + 1) % 7][i];
+        }
+        double *dst = out_row + (size_t)o * plane_elems;
+        if (act0) stg128(dst, res[0], res[1]);
+        if (act1) stg128(dst + d.Nx, res[2], res[3]);
+    }
+}
+
+template <int WX, int WY, int VAR>
 __global__ void __launch_bounds__(TileCfg<WX, WY>::THREADS, 1)
 stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constant__ DenseDesc d, const StepArgs a,
                     const int nitems, unsigned int *__restrict__ sync_counter, const unsigned int sync_base)
@@ -250,9 +519,10 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
     const size_t plane_elems = (size_t)Nx * Ny;
     uint32_t it = 0; /* ring position, continues across work items */
 
-    if (warp == Cfg::CONSUMER_WARPS) {
-        /* ================= producer warp (one elected lane issues the TMA boxes) ================= */
-        if (lane == 0) {
+    if (warp >= Cfg::CONSUMER_WARPS) {
+        /* ================= producer warpgroup (one elected lane issues the TMA boxes) ================= */
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::PRODUCER_REGS));
+        if (warp == Cfg::CONSUMER_WARPS && lane == 0) {
             unsigned int round = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, round++) {
                 const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
@@ -308,28 +578,41 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
         }
     } else {
         /* ================= consumer warps ================= */
-        const int wx = warp % WX, wy = warp / WX;
-        const int qx = wx * 4 + (lane & 3); /* quad index along x inside the tile */
-        const int ry = wy * 8 + (lane >> 2); /* row inside the tile                */
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
+        /* VAR 0: a thread owns 4 consecutive x of one row (qx: quad index, ry: row).
+           VAR 1: a thread owns a 2 x 2 patch (qx: x-pair index, ry: first of its two rows). */
+        int qx, ry;
+        if (VAR == 0) {
+            const int wx = warp % WX, wy = warp / WX;
+            qx = wx * 4 + (lane & 3);
+            ry = wy * 8 + (lane >> 2);
+        } else {
+            qx = lane & 15;
+            ry = warp * 4 + 2 * (lane >> 4);
+        }
         double in[7][4], acc[7][4];
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
             const int tx = tile % d.ntx, ty = tile / d.ntx;
             const int x0 = tile_origin(tx, Cfg::TX, Nx), y0 = tile_origin(ty, Cfg::TY, Ny);
-            const int gx = x0 + 4 * qx, gy = y0 + ry;
+            const int gx = x0 + (VAR == 0 ? 4 : 2) * qx, gy = y0 + ry;
             /* a shifted last tile overlaps its neighbour: only the not yet covered points are computed */
-            const bool active = (gx >= tx * Cfg::TX) && (gy >= ty * Cfg::TY);
+            const bool act0 = (gx >= tx * Cfg::TX) && (gy >= ty * Cfg::TY);
+            const bool act1 = (gx >= tx * Cfg::TX) && (gy + 1 >= ty * Cfg::TY); /* second row of a 2 x 2 patch */
+            const bool active = (VAR == 0) ? act0 : act1;
             double *out_row = reinterpret_cast<double *>(a.out) + (size_t)n * a.ld + (size_t)gy * Nx + gx;
-            /* byte offsets (inside a stage) of the 16-byte chunks 0,1,2 and 5,6,7 of this thread's x window */
+            /* byte offsets (inside a stage) of the 16-byte chunks of this thread's x window that may lie across a
+               periodic x face (VAR 0: chunks 0,1,2,5,6,7 of 8; VAR 1: chunks 0,1,2,4,5,6 of 7, first row) */
             int xo[6];
+            unsigned xmask = 0;
 #pragma unroll
             for (int q = 0; q < 6; q++) {
-                const int t = q < 3 ? q : q + 2;
+                const int t = (VAR == 0) ? (q < 3 ? q : q + 2) : (q < 3 ? q : q + 1);
                 const int gi = gx - R + 2 * t;
-                int off = ((ry + HT) * Cfg::YP + 4 * qx + 2 * t) * 8;
+                int off = ((ry + HT) * Cfg::YP + (VAR == 0 ? 4 : 2) * qx + 2 * t) * 8;
                 if (xper) {
-                    if (gi < 0) off = Cfg::OFF_L + (ry * SW + gi + SW) * 8;
-                    else if (gi >= Nx) off = Cfg::OFF_R + (ry * SW + gi - Nx) * 8;
+                    if (gi < 0) { off = Cfg::OFF_L + (ry * SW + gi + SW) * 8; xmask |= 1u << q; }
+                    else if (gi >= Nx) { off = Cfg::OFF_R + (ry * SW + gi - Nx) * 8; xmask |= 1u << q; }
                 }
                 xo[q] = off;
             }
@@ -350,7 +633,14 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
             stage = ring + (size_t)s * Cfg::STAGE_BYTES;                                                 \
             mbar_wait(&full[s], (it / kStages) & 1);                                                     \
         }                                                                                                \
-        consume_plane<Cfg, (U)>(d, a, stage, pp, active, qx, ry, xo, out_row, plane_elems, in, acc, zplane); \
+        if (VAR == 0)                                                                                    \
+            consume_plane<Cfg, (U)>(d, a, stage, pp, active, qx, ry, xo, out_row, plane_elems, in, acc, zplane); \
+        else if (VAR == 1)                                                                               \
+            consume_plane22<Cfg, (U)>(d, a, stage, pp, active, act0, act1, qx, ry, xo, xmask, out_row,    \
+                                      plane_elems, in, acc, zplane);                                     \
+        else                                                                                             \
+            consume_plane22b<Cfg, (U)>(d, a, smem_u32(stage), pp, active, act0, act1, qx, ry, xo, xmask,  \
+                                       out_row, plane_elems, in, acc, zplane);                           \
         if (use_stage) {                                                                                 \
             __syncwarp();                                                                                \
             if (lane == 0) mbar_arrive(&empty[s]);                                                       \
@@ -405,7 +695,7 @@ bool make_map(CUtensorMap *map, const void *base, const Layout &L, int ncol, int
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int WX, int WY>
+template <int WX, int WY, int VAR>
 int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
 {
     using Cfg = TileCfg<WX, WY>;
@@ -431,7 +721,8 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
         chefsi_fail(ctx, "cuTensorMapEncodeTiled failed");
         return -1;
     }
-    auto kern = stream_dense_kernel<WX, WY>;
+    static_assert(VAR == 0 || (Cfg::TX == 32 && Cfg::TY == 4 * Cfg::CONSUMER_WARPS && Cfg::CONSUMER_WARPS % 4 == 0), "2 x 2 mapping: 16 pairs x 4 rows per warp");
+    auto kern = stream_dense_kernel<WX, WY, VAR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(stream): %s", cudaGetErrorString(e)); return -1; }
     const int grid = (int)((nitems < ctx->num_sms) ? nitems : ctx->num_sms);
@@ -480,5 +771,7 @@ bool stream_dense_wanted(const chefsi_grid_t &g)
 int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a)
 {
     if (a.ncol <= 0) return 0;
-    return launch_cfg<2, 4>(ctx, a);
+    if (ctx->stream_variant == 0) return launch_cfg<2, 4, 0>(ctx, a);
+    if (ctx->stream_variant == 1) return launch_cfg<2, 4, 1>(ctx, a);
+    return launch_cfg<2, 4, 2>(ctx, a);
 }

@@ -23,6 +23,21 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(scope="module")
+def ctx_padded():
+    """Context on the halo-padded column layout (stencil_stream_orth.cu; CHEFSI_B200_DENSE=0), the
+    first streaming kernel of round 1, kept selectable."""
+    import os
+    from sparc_b200.chefsi import ChefsiContext
+    os.environ["CHEFSI_B200_DENSE"] = "0"
+    try:
+        c = ChefsiContext(0)
+    finally:
+        del os.environ["CHEFSI_B200_DENSE"]
+    yield c
+    c.close()
+
+
 def _setup(ctx, g, veff, proj, kvec=None):
     ctx.set_grid(g)
     ctx.set_veff(veff)
@@ -120,8 +135,9 @@ def test_fd_radius_four(ctx, port):
 # ---------------------------------------------------------------- streaming orthogonal kernel
 @pytest.mark.parametrize("N,BC", [((32, 32, 24), (0, 0, 0)), ((48, 40, 20), (0, 0, 0)), ((36, 24, 16), (0, 0, 0)),
                                    ((32, 32, 16), (1, 0, 1)), ((64, 32, 16), (0, 1, 0)), ((32, 16, 12), (1, 1, 1))])
-def test_stream_kernel_vs_oracle(ctx, port, N, BC):
-    """Shapes that take the streaming path (incl. ragged tiles, Dirichlet faces)."""
+def test_stream_kernel_vs_oracle(ctx_padded, port, N, BC):
+    """Shapes that take the padded-layout streaming path (incl. ragged tiles, Dirichlet faces)."""
+    ctx = ctx_padded
     g = P.make_grid(N, tuple(0.45 * n for n in N), BC=BC)
     veff = P.synthetic_veff(g)
     proj = P.make_projectors(g, np.array([[0.02, 0.5, 0.97], [0.5, 0.5, 0.5]]), rc=[2.4, 2.0], nproj=[18, 7])
@@ -139,23 +155,27 @@ def test_stream_kernel_vs_oracle(ctx, port, N, BC):
     assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
 
 
-@pytest.fixture(scope="module")
-def ctx_dense():
-    """Context on the dense (reference) column layout: stencil_stream_dense.cu."""
+@pytest.fixture(scope="module", params=[2, 1, 0], ids=["map2x2batched", "map2x2", "map1x4"])
+def ctx_dense(request):
+    """Context on the dense (reference) column layout: stencil_stream_dense.cu, both thread mappings
+    (2 x 2 points per thread = the default, 1 x 4 = the first version)."""
     import os
     from sparc_b200.chefsi import ChefsiContext
     os.environ["CHEFSI_B200_DENSE"] = "1"
+    os.environ["CHEFSI_B200_STREAM_VARIANT"] = str(request.param)
     try:
         c = ChefsiContext(0)
     finally:
         del os.environ["CHEFSI_B200_DENSE"]
+        del os.environ["CHEFSI_B200_STREAM_VARIANT"]
     yield c
     c.close()
 
 
 @pytest.mark.parametrize("N,BC", [((32, 32, 24), (0, 0, 0)), ((48, 40, 20), (0, 0, 0)), ((36, 38, 16), (0, 0, 0)),
                                    ((96, 96, 13), (0, 0, 0)), ((32, 32, 16), (1, 0, 1)), ((64, 32, 16), (0, 1, 0)),
-                                   ((32, 64, 12), (1, 1, 1)), ((40, 70, 12), (0, 0, 1)), ((68, 36, 12), (0, 1, 0))])
+                                   ((32, 64, 12), (1, 1, 1)), ((40, 70, 12), (0, 0, 1)), ((68, 36, 12), (0, 1, 0)),
+                                   ((40, 39, 12), (0, 0, 0)), ((44, 37, 14), (0, 1, 0))])
 def test_dense_stream_kernel_vs_oracle(ctx_dense, port, N, BC):
     """Dense-layout streaming kernel: single tiles that wrap on both sides, shifted (overlapping) last
     tiles, interior tiles (one TMA box), periodic-x strips, split periodic-y boxes, Dirichlet faces
