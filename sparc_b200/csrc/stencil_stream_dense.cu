@@ -98,17 +98,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+/* try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires)
+   instead of re-issuing try_wait + branch every few hundred cycles.  Without it the producer lane's spinning on
+   the `empty` barriers was 18 % of all instructions the kernel executed (ncu source view, profiles/) and competed
+   with the two consumer warps of its scheduler for issue slots. */
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra.uni WAIT_DONE;\n"
         "bra.uni WAIT_LOOP;\n"
         "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
 }
 /* TMA tiled load of one 4-D box (x, y, z, column), completion counted in bytes on an mbarrier */
@@ -281,13 +285,15 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
                 const double2 w1 = *reinterpret_cast<const double2 *>(vtile + (r0 + 1) * Cfg::XP + 2 * xp);
                 ve[0] = w0.x; ve[1] = w0.y; ve[2] = w1.x; ve[3] = w1.y;
             }
-            double t4[4], sx[4], sy[4], sz[4];
+            /* d.w*, d.coef0 carry the recurrence scale s1 (and the shift c) in this mapping, see launch_cfg:
+               40 FP64 instructions per point instead of 43 */
+            double sx[4], sy[4], sz[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int row = i >> 1, j = i & 1;
                 v[i] = xr[row][R + j];
-                t4[i] = (d.coef0 + a.c + ve[i]) * v[i];
-                sx[i] = d.wx[1] * (xr[row][R + j - 1] + xr[row][R + j + 1]);
+                const double diag = a.veff ? fma(a.s1, ve[i], d.coef0) : d.coef0;
+                sx[i] = fma(d.wx[1], xr[row][R + j - 1] + xr[row][R + j + 1], diag * v[i]);
                 sz[i] = d.wz[1] * in[(U - 1 + 7) % 7][i];
             }
 #pragma unroll
@@ -299,7 +305,7 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
                     sz[i] = fma(d.wz[r], in[(U - r + 7) % 7][i], sz[i]);
                 }
             /* y: up[k] = row r0-k, dn[k] = row r0+1+k (k = 1..6); row r0 pairs up[k] with (k == 1 ? own row 1 : dn[k-1]),
-               row r0+1 pairs (k == 1 ? own row 0 : up[k-1]) with dn[k] */
+               row r0+1 pairs (k == 1 ? own row 0 : up[k-1]) with dn[k]; the y chains start from the z sums */
             double2 up[R + 1], dn[R + 1];
             up[0] = make_double2(v[0], v[1]); /* row r0   */
             dn[0] = make_double2(v[2], v[3]); /* row r0+1 */
@@ -309,18 +315,16 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
                 dn[k] = *reinterpret_cast<const double2 *>(cp + (1 + k) * Cfg::YP);
             }
 #pragma unroll
+            for (int i = 0; i < 4; i++) sy[i] = sz[i];
+#pragma unroll
             for (int k = 1; k <= R; k++) {
                 const double a0 = up[k].x + dn[k - 1].x, a1 = up[k].y + dn[k - 1].y;
                 const double b0 = up[k - 1].x + dn[k].x, b1 = up[k - 1].y + dn[k].y;
-                if (k == 1) {
-                    sy[0] = d.wy[1] * a0; sy[1] = d.wy[1] * a1; sy[2] = d.wy[1] * b0; sy[3] = d.wy[1] * b1;
-                } else {
-                    sy[0] = fma(d.wy[k], a0, sy[0]); sy[1] = fma(d.wy[k], a1, sy[1]);
-                    sy[2] = fma(d.wy[k], b0, sy[2]); sy[3] = fma(d.wy[k], b1, sy[3]);
-                }
+                sy[0] = fma(d.wy[k], a0, sy[0]); sy[1] = fma(d.wy[k], a1, sy[1]);
+                sy[2] = fma(d.wy[k], b0, sy[2]); sy[3] = fma(d.wy[k], b1, sy[3]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) acc[U][i] = (t4[i] + sx[i]) + (sy[i] + sz[i]);
+            for (int i = 0; i < 4; i++) acc[U][i] = sx[i] + sy[i];
         } else {
             const double2 w0 = *reinterpret_cast<const double2 *>(cp);
             const double2 w1 = *reinterpret_cast<const double2 *>(cp + Cfg::YP);
@@ -341,151 +345,13 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
         if (a.s2 != 0.0) {
             const double2 w0 = *reinterpret_cast<const double2 *>(xtile + r0 * Cfg::XP + 2 * xp);
             const double2 w1 = *reinterpret_cast<const double2 *>(xtile + (r0 + 1) * Cfg::XP + 2 * xp);
-            res[0] = fma(-a.s2, w0.x, a.s1 * acc[(U + 1) % 7][0]);
-            res[1] = fma(-a.s2, w0.y, a.s1 * acc[(U + 1) % 7][1]);
-            res[2] = fma(-a.s2, w1.x, a.s1 * acc[(U + 1) % 7][2]);
-            res[3] = fma(-a.s2, w1.y, a.s1 * acc[(U + 1) % 7][3]);
+            res[0] = fma(-a.s2, w0.x, acc[(U + 1) % 7][0]);
+            res[1] = fma(-a.s2, w0.y, acc[(U + 1) % 7][1]);
+            res[2] = fma(-a.s2, w1.x, acc[(U + 1) % 7][2]);
+            res[3] = fma(-a.s2, w1.y, acc[(U + 1) % 7][3]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) res[i] = a.s1 * acc[(U + 1) % 7][i];
-        }
-        double *dst = out_row + (size_t)o * plane_elems;
-        if (act0) stg128(dst, res[0], res[1]);
-        if (act1) stg128(dst + d.Nx, res[2], res[3]);
-    }
-}
-
-/* ---- 2 x 2 thread tile with explicitly batched shared-memory loads (VAR 2) --------------------
- * Same arithmetic as consume_plane22.  ncu's source view of VAR 0/1 (profiles/r1_ncu_dense_v{0,1}.txt)
- * shows each LDS.128 issued right before the DADD that consumes it (short_scoreboard = 36 % of the
- * consumer warps' time at 2 warps per scheduler).  Here the loads of a plane are volatile and issued
- * in three batches ahead of the arithmetic that hides them:
- *   both x windows + Veff | z gather | x terms of row 0 | y halo rows + xprev | x terms of row 1 | y terms. */
-__device__ __forceinline__ double2 lds128(uint32_t addr)
-{
-    double2 w;
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w.x), "=d"(w.y) : "r"(addr));
-    return w;
-}
-
-template <class Cfg, int U>
-__device__ __forceinline__ void consume_plane22b(const DenseDesc &d, const StepArgs &a, const uint32_t stage, int p,
-                                                 bool active, bool act0, bool act1, int xp, int r0, const int (&xo)[6],
-                                                 unsigned xmask, double *__restrict__ out_row, size_t plane_elems,
-                                                 double (&in)[7][4], double (&acc)[7][4], bool plane_is_zero)
-{
-    const int Nz = d.Nz;
-    const bool interior = (p >= 0) && (p < Nz);
-    const int o = p - R;
-    const bool emit = o >= 0 && o < Nz && active;
-    const uint32_t cp = stage + ((r0 + HT) * Cfg::YP + 2 * xp + R) * 8; /* centre chunk of row r0 */
-    const uint32_t vp = stage + Cfg::OFF_V + (r0 * Cfg::XP + 2 * xp) * 8;
-    const uint32_t pp = stage + Cfg::OFF_X + (r0 * Cfg::XP + 2 * xp) * 8;
-
-    double v[4] = {0, 0, 0, 0};
-    if (active && !plane_is_zero) {
-        if (interior) {
-            /* batch 1: x windows of both rows, Veff */
-            double2 w0[7], w1[7];
-            w0[3] = lds128(cp);
-            w1[3] = lds128(cp + Cfg::YP * 8);
-#pragma unroll
-            for (int t = 0; t < 7; t++) {
-                if (t == 3) continue;
-                const int q = t < 3 ? t : t - 1;
-                w0[t] = lds128(stage + xo[q]);
-            }
-#pragma unroll
-            for (int t = 0; t < 7; t++) {
-                if (t == 3) continue;
-                const int q = t < 3 ? t : t - 1;
-                w1[t] = lds128(stage + xo[q] + (((xmask >> q) & 1u) ? SW * 8 : Cfg::YP * 8));
-            }
-            double2 ve0 = make_double2(0, 0), ve1 = make_double2(0, 0);
-            if (a.veff) { ve0 = lds128(vp); ve1 = lds128(vp + Cfg::XP * 8); }
-            /* z gather (registers only) */
-            double sz[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) sz[i] = d.wz[1] * in[(U - 1 + 7) % 7][i];
-#pragma unroll
-            for (int r = 2; r <= R; r++)
-#pragma unroll
-                for (int i = 0; i < 4; i++) sz[i] = fma(d.wz[r], in[(U - r + 7) % 7][i], sz[i]);
-            /* x terms of row 0 */
-            double xr[14], sx[4], t4[4];
-#pragma unroll
-            for (int t = 0; t < 7; t++) { xr[2 * t] = w0[t].x; xr[2 * t + 1] = w0[t].y; }
-            v[0] = xr[R]; v[1] = xr[R + 1];
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                sx[j] = d.wx[1] * (xr[R + j - 1] + xr[R + j + 1]);
-#pragma unroll
-                for (int r = 2; r <= R; r++) sx[j] = fma(d.wx[r], xr[R + j - r] + xr[R + j + r], sx[j]);
-            }
-            t4[0] = (d.coef0 + a.c + ve0.x) * v[0];
-            t4[1] = (d.coef0 + a.c + ve0.y) * v[1];
-            /* batch 2: y halo rows (up[k] = row r0-k, dn[k] = row r0+1+k), xprev */
-            double2 up[R + 1], dn[R + 1];
-#pragma unroll
-            for (int k = 1; k <= R; k++) {
-                up[k] = lds128(cp - k * Cfg::YP * 8);
-                dn[k] = lds128(cp + (1 + k) * Cfg::YP * 8);
-            }
-            /* x terms of row 1 */
-#pragma unroll
-            for (int t = 0; t < 7; t++) { xr[2 * t] = w1[t].x; xr[2 * t + 1] = w1[t].y; }
-            v[2] = xr[R]; v[3] = xr[R + 1];
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                sx[2 + j] = d.wx[1] * (xr[R + j - 1] + xr[R + j + 1]);
-#pragma unroll
-                for (int r = 2; r <= R; r++) sx[2 + j] = fma(d.wx[r], xr[R + j - r] + xr[R + j + r], sx[2 + j]);
-            }
-            t4[2] = (d.coef0 + a.c + ve1.x) * v[2];
-            t4[3] = (d.coef0 + a.c + ve1.y) * v[3];
-            /* y terms */
-            up[0] = make_double2(v[0], v[1]);
-            dn[0] = make_double2(v[2], v[3]);
-            double sy[4];
-#pragma unroll
-            for (int k = 1; k <= R; k++) {
-                const double a0 = up[k].x + dn[k - 1].x, a1 = up[k].y + dn[k - 1].y;
-                const double b0 = up[k - 1].x + dn[k].x, b1 = up[k - 1].y + dn[k].y;
-                if (k == 1) {
-                    sy[0] = d.wy[1] * a0; sy[1] = d.wy[1] * a1; sy[2] = d.wy[1] * b0; sy[3] = d.wy[1] * b1;
-                } else {
-                    sy[0] = fma(d.wy[k], a0, sy[0]); sy[1] = fma(d.wy[k], a1, sy[1]);
-                    sy[2] = fma(d.wy[k], b0, sy[2]); sy[3] = fma(d.wy[k], b1, sy[3]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) acc[U][i] = (t4[i] + sx[i]) + (sy[i] + sz[i]);
-        } else {
-            const double2 c0 = lds128(cp), c1 = lds128(cp + Cfg::YP * 8);
-            v[0] = c0.x; v[1] = c0.y; v[2] = c1.x; v[3] = c1.y;
-        }
-    }
-    double2 xp0 = make_double2(0, 0), xp1 = make_double2(0, 0);
-    if (emit && a.s2 != 0.0) { xp0 = lds128(pp); xp1 = lds128(pp + Cfg::XP * 8); }
-    if (p >= 0) { /* scatter the z terms into the 6 accumulators behind this plane */
-#pragma unroll
-        for (int r = 1; r <= R; r++)
-#pragma unroll
-            for (int i = 0; i < 4; i++) acc[(U - r + 7) % 7][i] = fma(d.wz[r], v[i], acc[(U - r + 7) % 7][i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) in[U][i] = v[i];
-
-    if (emit) {
-        double res[4];
-        if (a.s2 != 0.0) {
-            res[0] = fma(-a.s2, xp0.x, a.s1 * acc[(U + 1) % 7][0]);
-            res[1] = fma(-a.s2, xp0.y, a.s1 * acc[(U + 1) % 7][1]);
-            res[2] = fma(-a.s2, xp1.x, a.s1 * acc[(U + 1) % 7][2]);
-            res[3] = fma(-a.s2, xp1.y, a.s1 * acc[(U + 1) % 7][3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++) res[i] = a.s1 * acc[(U + 1) % 7][i];
+            for (int i = 0; i < 4; i++) res[i] = acc[(U + 1) % 7][i];
         }
         double *dst = out_row + (size_t)o * plane_elems;
         if (act0) stg128(dst, res[0], res[1]);
@@ -635,12 +501,9 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
         }                                                                                                \
         if (VAR == 0)                                                                                    \
             consume_plane<Cfg, (U)>(d, a, stage, pp, active, qx, ry, xo, out_row, plane_elems, in, acc, zplane); \
-        else if (VAR == 1)                                                                               \
+        else                                                                                             \
             consume_plane22<Cfg, (U)>(d, a, stage, pp, active, act0, act1, qx, ry, xo, xmask, out_row,    \
                                       plane_elems, in, acc, zplane);                                     \
-        else                                                                                             \
-            consume_plane22b<Cfg, (U)>(d, a, smem_u32(stage), pp, active, act0, act1, qx, ry, xo, xmask,  \
-                                       out_row, plane_elems, in, acc, zplane);                           \
         if (use_stage) {                                                                                 \
             __syncwarp();                                                                                \
             if (lane == 0) mbar_arrive(&empty[s]);                                                       \
@@ -708,6 +571,10 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
     d.nty = (g.Ny + Cfg::TY - 1) / Cfg::TY;
     d.coef0 = ctx->desc.coef0;
     for (int r = 0; r <= R; r++) { d.wx[r] = ctx->desc.wx[r]; d.wy[r] = ctx->desc.wy[r]; d.wz[r] = ctx->desc.wz[r]; }
+    if (VAR == 1) { /* the 2 x 2 mapping applies s1 (and c) through the weights: out = (s1 H') x - s2 xprev */
+        d.coef0 = a.s1 * (d.coef0 + a.c);
+        for (int r = 0; r <= R; r++) { d.wx[r] *= a.s1; d.wy[r] *= a.s1; d.wz[r] *= a.s1; }
+    }
     const long long nitems = (long long)a.ncol * d.ntx * d.nty;
     if (nitems > 0x7fffffffLL) { chefsi_fail(ctx, "stream kernel: too many work items"); return -1; }
 
@@ -772,6 +639,5 @@ int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a)
 {
     if (a.ncol <= 0) return 0;
     if (ctx->stream_variant == 0) return launch_cfg<2, 4, 0>(ctx, a);
-    if (ctx->stream_variant == 1) return launch_cfg<2, 4, 1>(ctx, a);
-    return launch_cfg<2, 4, 2>(ctx, a);
+    return launch_cfg<2, 4, 1>(ctx, a);
 }
