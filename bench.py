@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--block", type=int, default=128, help="columns filtered per launch group")
     ap.add_argument("--ncell", type=int, default=6, help="fcc conventional cells per axis (4 atoms each)")
     ap.add_argument("--no-nloc", action="store_true", help="stencil + Veff only (roofline study)")
+    ap.add_argument("--no-veff", action="store_true", help="skip the local potential (experiment: cost of the Veff tile stream)")
     ap.add_argument("--e2e-cols", type=int, default=256)
     ap.add_argument("--cpu-cols-per-core", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -227,7 +228,8 @@ def run_ours(args):
 
     ctx = ChefsiContext(local_rank)
     ctx.set_grid(g)
-    ctx.set_veff(veff)
+    if not args.no_veff:
+        ctx.set_veff(veff)
     ctx.set_projectors(proj)
     ld = ctx.device_ld
     first_col, ncol_local = band_partition(args.ncol, world, rank)

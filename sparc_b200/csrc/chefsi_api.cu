@@ -10,6 +10,7 @@
  * where every "(H - c) .  scaled, minus xprev" is ONE fused stencil launch plus the nonlocal
  * projector launches, and X<-Y<-Ynew is a rotation of three device buffers (no copies).
  */
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -104,11 +105,11 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     cudaStreamSynchronize(ctx->stream);
     free_nloc(ctx->nl);
     cudaFree(ctx->d_veff);
-    for (int i = 0; i < 3; i++) cudaFree(ctx->d_buf[i]);
+    for (int i = 0; i < 3; i++) { cudaFree(ctx->d_buf[i]); cudaFree(ctx->d_buf2[i]); cudaFree(ctx->d_buf3[i]); }
     cudaFree(ctx->d_alpha[0]);
     cudaFree(ctx->d_alpha[1]);
     for (int i = 0; i < 2; i++) { cudaFree(ctx->d_stage_in[i]); cudaFree(ctx->d_stage_out[i]); }
-    for (int i = 0; i < 8; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
+    for (int i = 0; i < 12; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     cudaFree(ctx->d_sync);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -310,13 +311,29 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
             seen[p] = 1;
         }
     }
-    /* CSR atom -> images */
-    std::vector<int> off(nl->n_atom + 1, 0), lst(nl->n_img);
-    for (int J = 0; J < nl->n_img; J++) off[nl->img_atom[J] + 1]++;
+    /* Segments: the projector kernels run one CTA per (sphere image, 32 columns).  A system with few atoms
+       (the SCF test systems: 12-18 images) would occupy a tenth of the SMs, so its images are cut into
+       segments of kSeg consecutive sphere points, each of which the kernels treat as an image of its own
+       (own alpha partial; the consumer sums the partials of all segments of the atom in a fixed order).
+       With >= one image per SM the images stay whole. */
+    const int kSeg = (nl->n_img >= ctx->num_sms) ? 0x7fffffff : 256;
+    std::vector<int> seg_img, seg_atom, seg_ndc, seg_pt0;
+    for (int J = 0; J < nl->n_img; J++)
+        for (int pt0 = 0; pt0 < nl->img_ndc[J]; pt0 += kSeg) {
+            seg_img.push_back(J);
+            seg_atom.push_back(nl->img_atom[J]);
+            seg_pt0.push_back(pt0);
+            seg_ndc.push_back(std::min(kSeg, nl->img_ndc[J] - pt0));
+        }
+    const int n_seg = (int)seg_img.size();
+    d.n_img = n_seg;
+    /* CSR atom -> segments */
+    std::vector<int> off(nl->n_atom + 1, 0), lst(n_seg);
+    for (int s2 = 0; s2 < n_seg; s2++) off[seg_atom[s2] + 1]++;
     for (int a = 0; a < nl->n_atom; a++) off[a + 1] += off[a];
     {
         std::vector<int> cur(off.begin(), off.end() - 1);
-        for (int J = 0; J < nl->n_img; J++) lst[cur[nl->img_atom[J]]++] = J;
+        for (int s2 = 0; s2 < n_seg; s2++) lst[cur[seg_atom[s2]]++] = s2;
     }
     /* sphere indices in the internal layout, and the list of sphere points mirrored in halo pads */
     const Layout &L = ctx->lay;
@@ -345,20 +362,19 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
     if (upload(ctx, &d.patch_dst, pdst.data(), pdst.size())) return 1;
     if (upload(ctx, &d.IP_displ, nl->IP_displ, (size_t)nl->n_atom + 1)) return 1;
     if (upload(ctx, &d.gamma, nl->gamma, (size_t)d.ntot)) return 1;
-    if (upload(ctx, &d.img_atom, nl->img_atom, (size_t)nl->n_img)) return 1;
-    if (upload(ctx, &d.img_ndc, nl->img_ndc, (size_t)nl->n_img)) return 1;
-    if (upload(ctx, &d.pos_off, nl->pos_off, (size_t)nl->n_img + 1)) return 1;
+    if (upload(ctx, &d.img_atom, seg_atom.data(), (size_t)n_seg)) return 1;
+    if (upload(ctx, &d.img_ndc, seg_ndc.data(), (size_t)n_seg)) return 1;
+    {
+        std::vector<long long> poff((size_t)n_seg + 1, 0);
+        for (int s2 = 0; s2 < n_seg; s2++) poff[s2] = nl->pos_off[seg_img[s2]] + seg_pt0[s2];
+        poff[n_seg] = npos;
+        if (upload(ctx, &d.pos_off, poff.data(), poff.size())) return 1;
+    }
     if (upload(ctx, &d.grid_pos, ppos.data(), (size_t)npos)) return 1;
     {   /* Chi per image transposed to point-major and zero-padded to np_pad projectors (what the nloc
-           kernel streams with 16-byte cp.async); per-image offsets of the alpha partials */
+           kernel streams with 16-byte cp.async); per-segment offsets into it and of the alpha partials */
         std::vector<long long> toff((size_t)nl->n_img + 1, 0);
-        std::vector<int> aoff((size_t)nl->n_img + 1, 0);
-        for (int J = 0; J < nl->n_img; J++) {
-            const int np = nl->IP_displ[nl->img_atom[J] + 1] - nl->IP_displ[nl->img_atom[J]];
-            toff[J + 1] = toff[J] + (long long)nl->img_ndc[J] * d.np_pad;
-            aoff[J + 1] = aoff[J] + np;
-        }
-        d.img_proj_total = aoff[nl->n_img];
+        for (int J = 0; J < nl->n_img; J++) toff[J + 1] = toff[J] + (long long)nl->img_ndc[J] * d.np_pad;
         std::vector<double> chiT((size_t)toff[nl->n_img], 0.0);
         for (int J = 0; J < nl->n_img; J++) {
             const int np = nl->IP_displ[nl->img_atom[J] + 1] - nl->IP_displ[nl->img_atom[J]];
@@ -368,15 +384,24 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
             for (int p = 0; p < np; p++)
                 for (int i = 0; i < ndc; i++) dst[(size_t)i * d.np_pad + p] = src[(size_t)p * ndc + i];
         }
-        if (upload(ctx, &d.chiT_off, toff.data(), toff.size())) return 1;
+        std::vector<long long> soff((size_t)n_seg + 1, 0);
+        std::vector<int> aoff((size_t)n_seg + 1, 0);
+        for (int s2 = 0; s2 < n_seg; s2++) {
+            const int np = nl->IP_displ[seg_atom[s2] + 1] - nl->IP_displ[seg_atom[s2]];
+            soff[s2] = toff[seg_img[s2]] + (long long)seg_pt0[s2] * d.np_pad;
+            aoff[s2 + 1] = aoff[s2] + np;
+        }
+        soff[n_seg] = toff[nl->n_img];
+        d.img_proj_total = aoff[n_seg];
+        if (upload(ctx, &d.chiT_off, soff.data(), soff.size())) return 1;
         if (upload(ctx, &d.img_aoff, aoff.data(), aoff.size())) return 1;
         if (upload(ctx, &d.chiT, chiT.data(), chiT.size())) return 1;
     }
     if (upload(ctx, &d.atom_img_off, off.data(), off.size())) return 1;
     if (upload(ctx, &d.atom_img, lst.data(), lst.size())) return 1;
-    CHEFSI_CUDA(ctx, cudaMalloc((void **)&d.img_phase, sizeof(double2) * nl->n_img));
-    d.h_img_coords = (double *)malloc(sizeof(double) * 3 * nl->n_img);
-    memcpy(d.h_img_coords, nl->img_coords, sizeof(double) * 3 * nl->n_img);
+    CHEFSI_CUDA(ctx, cudaMalloc((void **)&d.img_phase, sizeof(double2) * n_seg));
+    d.h_img_coords = (double *)malloc(sizeof(double) * 3 * n_seg);
+    for (int s2 = 0; s2 < n_seg; s2++) memcpy(d.h_img_coords + 3 * s2, nl->img_coords + 3 * seg_img[s2], sizeof(double) * 3);
     return update_nloc_phases(ctx);
 }
 
@@ -596,14 +621,32 @@ static int ensure_bufs(chefsi_ctx *ctx, size_t bytes_each)
     return 0;
 }
 
+static int ensure_bufs2(chefsi_ctx *ctx, size_t bytes_each)
+{
+    if (bytes_each <= ctx->buf2_bytes) return 0;
+    for (int i = 0; i < 3; i++) {
+        cudaFree(ctx->d_buf2[i]); ctx->d_buf2[i] = nullptr;
+        cudaFree(ctx->d_buf3[i]); ctx->d_buf3[i] = nullptr;
+    }
+    ctx->buf2_bytes = 0;
+    for (int i = 0; i < 3; i++) {
+        CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_buf2[i], bytes_each));
+        CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_buf3[i], bytes_each));
+    }
+    ctx->buf2_bytes = bytes_each;
+    return 0;
+}
+
 /* columns per chunk: small enough that the pipeline has ~8 chunks to overlap and that three blocks,
  * four staging blocks and alpha fit in the free device memory; large enough to fill the GPU */
 static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
 {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
-    free_b += 3 * ctx->buf_bytes + 2 * ctx->alpha_bytes + 4 * ctx->stage_bytes; /* what we already hold can be reused */
-    const size_t per_col = 3 * ctx->ld * esz + 4 * ctx->Nd * esz + 2 * (size_t)ctx->nl.img_proj_total * esz;
+    free_b += 3 * ctx->buf_bytes + 6 * ctx->buf2_bytes + 2 * ctx->alpha_bytes + 4 * ctx->stage_bytes; /* what we already hold can be reused */
+    /* padded layout: 3 blocks + 4 dense staging blocks; dense layout: three trios, no staging */
+    const size_t per_col = ((ctx->lay.px || ctx->lay.py) ? 3 * ctx->ld * esz + 4 * ctx->Nd * esz : 9 * ctx->ld * esz) +
+                           2 * (size_t)ctx->nl.img_proj_total * esz;
     size_t budget = (size_t)(0.85 * (double)free_b);
     const char *env = getenv("CHEFSI_B200_MAX_CHUNK_BYTES");
     if (env) { size_t v = strtoull(env, nullptr, 10); if (v && v < budget) budget = v; }
@@ -613,7 +656,7 @@ static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
     /* pipeline granularity: only worth it when the block is big enough for the copies to matter */
     const size_t block_bytes = (size_t)ncol * ctx->Nd * esz;
     if (block_bytes > ((size_t)64 << 20)) {
-        size_t want = ((size_t)ncol + 7) / 8;
+        size_t want = ((size_t)ncol + 3) / 4;
         if (want < 32) want = 32;
         if (want > 128) want = 128;
         const char *e2 = getenv("CHEFSI_B200_HOST_CHUNK");
@@ -626,7 +669,7 @@ static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
 static int ensure_pipe_events(chefsi_ctx *ctx)
 {
     if (ctx->pipe_ev[0]) return 0;
-    for (int i = 0; i < 8; i++) CHEFSI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 12; i++) CHEFSI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
     return 0;
 }
 
@@ -639,16 +682,47 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
     const int chunk = chunk_columns(ctx, ncol, esz);
+    /* dense layout: the device block IS the reference's layout (columns ld apart), so the copies go straight
+       into / out of the recurrence buffers; chunks rotate through three buffer trios (with two, the chain
+       D2H(k) -> H2D(k+2) -> filter(k+2) would expose a copy per chunk).  No staging, no pack / unpack passes
+       (6 of ~65 block passes per degree-20 call). */
+    const bool direct = (ctx->lay.px == 0 && ctx->lay.py == 0);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
-    if (ensure_stage(ctx, (size_t)chunk * ctx->Nd * esz)) return 1;
+    if (direct) {
+        if (chunk < ncol && ensure_bufs2(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
+    } else if (ensure_stage(ctx, (size_t)chunk * ctx->Nd * esz)) return 1;
     if (ensure_pipe_events(ctx)) return 1;
-    cudaEvent_t *ev_h2d = ctx->pipe_ev, *ev_in_free = ctx->pipe_ev + 2, *ev_out = ctx->pipe_ev + 4, *ev_d2h = ctx->pipe_ev + 6;
+    cudaEvent_t *ev_h2d = ctx->pipe_ev, *ev_in_free = ctx->pipe_ev + 3, *ev_out = ctx->pipe_ev + 6, *ev_d2h = ctx->pipe_ev + 9;
     const bool copy_x = !(flags & CHEFSI_FLAG_NO_X_COPYBACK);
     const size_t row = ctx->Nd * esz;
     cudaEvent_t t0 = ctx->ev[2], t1 = ctx->ev[3];
     CHEFSI_CUDA(ctx, cudaEventRecord(t0, ctx->stream));
     CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, t0, 0)); /* order after earlier work of this context */
     int k = 0;
+    if (direct) {
+        const size_t pitch = ctx->ld * esz;
+        for (int c0 = 0; c0 < ncol; c0 += chunk, k++) {
+            const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
+            const int s = k % 3;
+            void **trio = s == 0 ? ctx->d_buf : (s == 1 ? ctx->d_buf2 : ctx->d_buf3);
+            /* trio s is free again when the copies of chunk k-3 out of it have finished */
+            if (k >= 3) CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, ev_d2h[s], 0));
+            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(trio[0], pitch, (const char *)X + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
+                                               cudaMemcpyHostToDevice, ctx->h2d_stream));
+            CHEFSI_CUDA(ctx, cudaEventRecord(ev_h2d[s], ctx->h2d_stream));
+            CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[s], 0));
+            int ys = 1, xs = 0;
+            if (filter_device(ctx, trio, nc, m, a, b, a0, is_complex, &ys, &xs)) return 1;
+            CHEFSI_CUDA(ctx, cudaEventRecord(ev_out[s], ctx->stream));
+            CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev_out[s], 0));
+            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Y + (size_t)c0 * ldo * esz, ldo * esz, trio[ys], pitch, row, nc,
+                                               cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            if (copy_x)
+                CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)X + (size_t)c0 * ldi * esz, ldi * esz, trio[xs], pitch, row, nc,
+                                                   cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            CHEFSI_CUDA(ctx, cudaEventRecord(ev_d2h[s], ctx->d2h_stream));
+        }
+    } else
     for (int c0 = 0; c0 < ncol; c0 += chunk, k++) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
         const int s = k & 1;
@@ -685,7 +759,7 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
         CHEFSI_CUDA(ctx, cudaEventRecord(ev_d2h[s], ctx->d2h_stream));
     }
     /* join: the compute stream waits for the last copies, then the host waits for it */
-    for (int s = 0; s < 2 && s < k; s++) CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[s], 0));
+    for (int s = 0; s < (direct ? 3 : 2) && s < k; s++) CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[s], 0));
     CHEFSI_CUDA(ctx, cudaEventRecord(t1, ctx->stream));
     CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -712,11 +786,21 @@ static int hmult_host(chefsi_ctx *ctx, int ncol, double c, const void *x, size_t
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
     const int chunk = chunk_columns(ctx, ncol, esz);
+    const bool direct = (ctx->lay.px == 0 && ctx->lay.py == 0); /* dense layout: no staging (see filter_host) */
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
-    if (ensure_stage(ctx, (size_t)chunk * ctx->Nd * esz)) return 1;
-    const size_t row = ctx->Nd * esz;
+    if (!direct && ensure_stage(ctx, (size_t)chunk * ctx->Nd * esz)) return 1;
+    const size_t row = ctx->Nd * esz, pitch = ctx->ld * esz;
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
+        if (direct) {
+            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_buf[0], pitch, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
+                                               cudaMemcpyHostToDevice, ctx->stream));
+            if (hmult_device(ctx, nc, c, ctx->d_buf[0], ctx->d_buf[1], is_complex)) return 1;
+            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Hx + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_buf[1], pitch, row, nc,
+                                               cudaMemcpyDeviceToHost, ctx->stream));
+            CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            continue;
+        }
         CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_stage_in[0], row, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
                                            cudaMemcpyHostToDevice, ctx->stream));
         int n = launch_pack(ctx, ctx->d_stage_in[0], ctx->Nd, ctx->d_buf[0], nc, is_complex);

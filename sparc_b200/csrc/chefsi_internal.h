@@ -102,13 +102,16 @@ struct chefsi_ctx {
     double *d_zero = nullptr;    /* unused spare */
     void *d_stage_in[2] = {nullptr, nullptr};  /* dense staging blocks of the host entry points' pipeline */
     void *d_stage_out[2] = {nullptr, nullptr};
-    cudaEvent_t pipe_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes = 0;
     bool have_veff = false;
     NlocDev nl;
     double kvec[3] = {0, 0, 0};
     /* scratch owned by the host entry points */
     void *d_buf[3] = {nullptr, nullptr, nullptr};
+    void *d_buf2[3] = {nullptr, nullptr, nullptr}; /* second and third trio: dense-layout host pipeline (chunks rotate) */
+    void *d_buf3[3] = {nullptr, nullptr, nullptr};
+    size_t buf2_bytes = 0;
     size_t buf_bytes = 0;
     void *d_alpha[2] = {nullptr, nullptr}; /* per-image alpha partials: [cur] belongs to the current input */
     int alpha_cur = 0;

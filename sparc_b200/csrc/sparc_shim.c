@@ -64,6 +64,8 @@ static struct {
     int npinned;
     unsigned long long n_filter, n_hmult, n_forward;
     double t_filter;
+    unsigned long long n_filter_fwd; /* ChebyshevFiltering calls forwarded to the reference, and their seconds */
+    double t_filter_fwd;
 } G;
 
 static void shim_fatal(const char *what)
@@ -83,8 +85,19 @@ static void shim_report(void)
 {
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] %llu ChebyshevFiltering calls (%.3f s), %llu Hamiltonian_vectors_mult calls, "
-                        "%llu calls forwarded to the reference\n", G.n_filter, G.t_filter, G.n_hmult, G.n_forward);
+                        "%llu calls forwarded to the reference (of which %llu ChebyshevFiltering calls, %.3f s)\n",
+                G.n_filter, G.t_filter, G.n_hmult, G.n_forward, G.n_filter_fwd, G.t_filter_fwd);
     if (G.ctx) { chefsi_destroy(G.ctx); G.ctx = NULL; }
+}
+
+/* the exit report is also wanted when every call is forwarded (CHEFSI_B200_DISABLE=1: the CPU arm of scripts/scf_table.sh) */
+static void shim_register_report(void)
+{
+    static int done = 0;
+    if (done) return;
+    done = 1;
+    G.verbose = getenv("CHEFSI_B200_SHIM_VERBOSE") ? atoi(getenv("CHEFSI_B200_SHIM_VERBOSE")) : 0;
+    atexit(shim_report);
 }
 
 static void shim_init(void)
@@ -97,12 +110,11 @@ static void shim_init(void)
     if (!lr) lr = getenv("MV2_COMM_WORLD_LOCAL_RANK");
     if (!lr) lr = getenv("SLURM_LOCALID");
     if (!dev && lr) device = atoi(lr);
-    G.verbose = getenv("CHEFSI_B200_SHIM_VERBOSE") ? atoi(getenv("CHEFSI_B200_SHIM_VERBOSE")) : 0;
+    shim_register_report();
     if (chefsi_create(&G.ctx, device) != 0) {
         fprintf(stderr, "[chefsi_b200 shim] cannot create the CUDA context: %s\n", chefsi_last_error(NULL));
         exit(EXIT_FAILURE);
     }
-    atexit(shim_report);
     if (G.verbose) fprintf(stderr, "[chefsi_b200 shim] %s on device %d\n", chefsi_version(), device);
 }
 
@@ -279,7 +291,11 @@ void ChebyshevFiltering(SPARC_OBJ *pSPARC, int *DMVertices, double *X, int ldi, 
                      (1 - DMVertices[4] + DMVertices[5]);
     if (!shim_supported(pSPARC, DMnd, DMVertices, comm, pSPARC->nlocProj)) {
         G.n_forward++;
+        shim_register_report();
+        const double t0 = MPI_Wtime();
         ChebyshevFiltering_ref(pSPARC, DMVertices, X, ldi, Y, ldo, ncol, m, a, b, a0, k, spn_i, comm, time_info);
+        G.n_filter_fwd++;
+        G.t_filter_fwd += MPI_Wtime() - t0;
         return;
     }
     const double t1 = MPI_Wtime();
@@ -311,7 +327,11 @@ void ChebyshevFiltering_kpt(SPARC_OBJ *pSPARC, int *DMVertices, double _Complex 
                      (1 - DMVertices[4] + DMVertices[5]);
     if (!shim_supported(pSPARC, DMnd, DMVertices, comm, pSPARC->nlocProj)) {
         G.n_forward++;
+        shim_register_report();
+        const double t0 = MPI_Wtime();
         ChebyshevFiltering_kpt_ref(pSPARC, DMVertices, X, ldi, Y, ldo, ncol, m, a, b, a0, kpt, spn_i, comm, time_info);
+        G.n_filter_fwd++;
+        G.t_filter_fwd += MPI_Wtime() - t0;
         return;
     }
     const double t1 = MPI_Wtime();
