@@ -147,7 +147,7 @@ int launch_stencil_general(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
 bool stream_layout_wanted(const chefsi_grid_t &g);
 bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex);
 int launch_stencil_stream_orth(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
-bool stream_dense_wanted(const chefsi_grid_t &g);
+bool stream_dense_wanted(const chefsi_grid_t &g, int variant);
 int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a);
 
 /* nloc.cu: see launch_nloc for the three modes */

@@ -610,7 +610,15 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
     if (counter) { /* the barrier needs all CTAs co-resident: cooperative launch refuses otherwise */
         void *args[] = {(void *)&m, (void *)&d, (void *)&a, (void *)&nit, (void *)&counter, (void *)&base};
         e = cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Cfg::THREADS), args, Cfg::SMEM, ctx->stream);
-        if (e != cudaSuccess) { chefsi_fail(ctx, "stream kernel cooperative launch: %s", cudaGetErrorString(e)); return -1; }
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+            /* the SMs are shared (MPS, another context, a smaller MIG slice): run without the round barrier -- the
+               result is the same, only the xy-halos of neighbouring tiles hit L2 less often */
+            cudaGetLastError();
+            ctx->sync_arrivals = base; /* nothing will arrive for this launch */
+            ctx->stream_gridsync = 0;
+            counter = nullptr;
+            kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(m, d, a, nit, counter, base);
+        } else if (e != cudaSuccess) { chefsi_fail(ctx, "stream kernel cooperative launch: %s", cudaGetErrorString(e)); return -1; }
     } else {
         kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(m, d, a, nit, counter, base);
     }
@@ -621,15 +629,15 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
 
 }  // namespace
 
-/* The dense streaming kernel needs: orthogonal cell, FD radius 6, real data, Nx a multiple of 4 (each
- * thread owns an aligned quad; TMA strides must be 16-byte multiples), at least one full 32 x 32 tile
+/* The dense streaming kernel needs: orthogonal cell, FD radius 6, real data, Nx even (a thread owns aligned x
+ * pairs and TMA strides must be 16-byte multiples; the 1 x 4 mapping owns quads: Nx a multiple of 4), at least one full 32 x 32 tile
  * per plane, and -- for a periodic y face -- a tile row count such that no 6-row halo box straddles
  * the face (Ny mod 32 is 0 or >= 6).  Everything else goes through the general kernel. */
-bool stream_dense_wanted(const chefsi_grid_t &g)
+bool stream_dense_wanted(const chefsi_grid_t &g, int variant)
 {
     using Cfg = TileCfg<2, 4>;
     if (g.cell_typ != 0 || g.FDn != R) return false;
-    if (g.Nx % 4 != 0) return false;
+    if (g.Nx % (variant == 0 ? 4 : 2) != 0) return false;
     if (g.Nx < Cfg::TX || g.Ny < Cfg::TY || g.Nz < 2 * R) return false;
     if (g.BCy == 0 && g.Ny % Cfg::TY != 0 && g.Ny % Cfg::TY < R) return false;
     return true;

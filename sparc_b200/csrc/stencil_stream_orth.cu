@@ -442,7 +442,7 @@ bool stream_layout_wanted(const chefsi_grid_t &g)
 bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex)
 {
     if (ctx->force_general || is_complex) return false;
-    if (ctx->dense_stream) return ctx->lay.px == 0 && ctx->lay.py == 0 && stream_dense_wanted(ctx->grid);
+    if (ctx->dense_stream) return ctx->lay.px == 0 && ctx->lay.py == 0 && stream_dense_wanted(ctx->grid, ctx->stream_variant);
     return ctx->lay.px == 8 && ctx->lay.py == R && stream_layout_wanted(ctx->grid);
 }
 
