@@ -82,6 +82,7 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
     if (getenv("CHEFSI_B200_GRIDSYNC")) ctx->stream_gridsync = atoi(getenv("CHEFSI_B200_GRIDSYNC"));
     if (getenv("CHEFSI_B200_DENSE")) ctx->dense_stream = atoi(getenv("CHEFSI_B200_DENSE"));
     if (getenv("CHEFSI_B200_STREAM_VARIANT")) ctx->stream_variant = atoi(getenv("CHEFSI_B200_STREAM_VARIANT"));
+    if (getenv("CHEFSI_B200_ALPHA_REDUCE_MIN")) ctx->alpha_reduce_min = atoi(getenv("CHEFSI_B200_ALPHA_REDUCE_MIN"));
     if (getenv("CHEFSI_B200_NLOC_SHAPE")) ctx->nloc_shape = atoi(getenv("CHEFSI_B200_NLOC_SHAPE"));
     if (getenv("CHEFSI_B200_TMA_L2PROMO")) ctx->tma_l2promo = atoi(getenv("CHEFSI_B200_TMA_L2PROMO")) & 3;
     *out = ctx;
@@ -108,6 +109,7 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     for (int i = 0; i < 3; i++) { cudaFree(ctx->d_buf[i]); cudaFree(ctx->d_buf2[i]); cudaFree(ctx->d_buf3[i]); }
     cudaFree(ctx->d_alpha[0]);
     cudaFree(ctx->d_alpha[1]);
+    cudaFree(ctx->d_alpha_sum);
     for (int i = 0; i < 2; i++) { cudaFree(ctx->d_stage_in[i]); cudaFree(ctx->d_stage_out[i]); }
     for (int i = 0; i < 12; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     cudaFree(ctx->d_sync);
@@ -330,6 +332,8 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
     /* CSR atom -> segments */
     std::vector<int> off(nl->n_atom + 1, 0), lst(n_seg);
     for (int s2 = 0; s2 < n_seg; s2++) off[seg_atom[s2] + 1]++;
+    d.max_parts = 0;
+    for (int a = 0; a < nl->n_atom; a++) d.max_parts = std::max(d.max_parts, off[a + 1]);
     for (int a = 0; a < nl->n_atom; a++) off[a + 1] += off[a];
     {
         std::vector<int> cur(off.begin(), off.end() - 1);

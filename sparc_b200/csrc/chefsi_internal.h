@@ -78,6 +78,7 @@ struct NlocDev {
     int *img_aoff = nullptr;      /* [n_img+1] prefix sum of nproj over images: per-image alpha partials */
     int np_pad = 0;               /* projector padding the nloc kernels are instantiated for */
     long long img_proj_total = 0; /* img_aoff[n_img] */
+    int max_parts = 0;            /* largest number of images/segments (= alpha partials) of any atom */
     double2 *img_phase = nullptr; /* [n_img] (cos theta, sin theta) for the current k-point */
     int *atom_img_off = nullptr;  /* CSR atom -> images */
     int *atom_img = nullptr;
@@ -114,6 +115,9 @@ struct chefsi_ctx {
     size_t buf2_bytes = 0;
     size_t buf_bytes = 0;
     void *d_alpha[2] = {nullptr, nullptr}; /* per-image alpha partials: [cur] belongs to the current input */
+    int alpha_reduce_min = 8;              /* atoms with more alpha partials than this get them summed by alpha_reduce_kernel */
+    size_t alpha_sum_bytes = 0;
+    void *d_alpha_sum = nullptr;           /* per-atom sums of the partials (only when nl.max_parts is large) */
     int alpha_cur = 0;
     size_t alpha_bytes = 0;
     /* stats */

@@ -33,6 +33,8 @@
  * columns (re, im); the Bloch factors (nlocVecRoutines.c:911-921, :982-989) are applied where beta is
  * formed and where alpha is written.
  */
+#include <algorithm>
+
 #include "chefsi_internal.h"
 
 namespace {
@@ -63,6 +65,7 @@ struct NlocView {
     const double *chiT;
     const double2 *img_phase;
     const int *atom_img_off, *atom_img;
+    const double *alpha_sum; /* != NULL: per-atom sums of the partials (alpha_reduce_kernel), atom a at IP_displ[a] * ncol * WORDS */
     int Nxp, Nyp, px, py, Nx, Ny, mirx, miry; /* halo-pad geometry (mirx/miry: periodic pads present) */
 };
 
@@ -88,7 +91,7 @@ template <int NP, class SH> struct Smem {
 
 /* vec: MODE_PROJECT -> the input block x (read only); otherwise the output block (read-modify-write).
  * Word column wc of the block lives at vec + (wc / WORDS) * ld * WORDS + (wc % WORDS), element stride WORDS. */
-template <int NP, int WORDS, int MODE, class SH>
+template <int NP, int WORDS, int MODE, class SH, bool SUMMED>
 __global__ void __launch_bounds__(SH::T, ((NP <= 20) ? 2 : 1) * (256 / SH::T))
 nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__restrict__ alpha_next,
             double *__restrict__ vec, const size_t ld, const int ncol, const int ngroups, const double scale,
@@ -118,20 +121,31 @@ nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__
     for (int p = 0; p < NP; p++) { beta[p] = 0.0; acc[p] = 0.0; }
     const int mywc = wc0 + lane;
     const bool colvalid = mywc < nwc;
+    /* alpha partials are stored [image/segment][data column][projector] */
     if (MODE != MODE_PROJECT && colvalid) {
         const int dc = mywc / WORDS, w = mywc % WORDS;
         double sre[NP], sim[NP];
 #pragma unroll
         for (int p = 0; p < NP; p++) { sre[p] = 0.0; sim[p] = 0.0; }
-        for (int jj = nl.atom_img_off[atom]; jj < nl.atom_img_off[atom + 1]; jj++) {
-            const int J2 = nl.atom_img[jj];
-            const double *ap = alpha_prev + ((size_t)nl.img_aoff[J2] * ncol + (size_t)dc * nproj) * WORDS;
+        if (SUMMED) { /* per-atom sums prepared by alpha_reduce_kernel (same [column][projector] layout per atom) */
+            const double *ap = nl.alpha_sum + ((size_t)ip0 * ncol + (size_t)dc * nproj) * WORDS;
 #pragma unroll
             for (int p = 0; p < NP; p++)
                 if (p < nproj) {
-                    sre[p] += ap[p * WORDS];
-                    if (WORDS == 2) sim[p] += ap[p * WORDS + 1];
+                    sre[p] = ap[p * WORDS];
+                    if (WORDS == 2) sim[p] = ap[p * WORDS + 1];
                 }
+        } else {
+            for (int jj = nl.atom_img_off[atom]; jj < nl.atom_img_off[atom + 1]; jj++) {
+                const int J2 = nl.atom_img[jj];
+                const double *ap = alpha_prev + ((size_t)nl.img_aoff[J2] * ncol + (size_t)dc * nproj) * WORDS;
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    if (p < nproj) {
+                        sre[p] += ap[p * WORDS];
+                        if (WORDS == 2) sim[p] += ap[p * WORDS + 1];
+                    }
+            }
         }
         double2 ph = make_double2(1.0, 0.0);
         if (WORDS == 2) ph = nl.img_phase[J];
@@ -301,6 +315,24 @@ nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__
     }
 }
 
+/* Per-atom sums of the alpha partials (layout per atom as in a partial: [column][projector]), summed over the atom's images/segments in list
+ * order (deterministic).  Launched only when some atom has many partials (segmented spheres of small systems,
+ * atoms with many periodic images): every consumer CTA then reads one row set instead of looping over them. */
+__global__ void alpha_reduce_kernel(const NlocView nl, const double *__restrict__ alpha, double *__restrict__ asum,
+                                    const size_t rowlen)
+{
+    const int atom = blockIdx.y;
+    const int ip0 = nl.IP_displ[atom];
+    const int nproj = nl.IP_displ[atom + 1] - ip0;
+    const size_t n = (size_t)nproj * rowlen;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int jj = nl.atom_img_off[atom]; jj < nl.atom_img_off[atom + 1]; jj++)
+            acc += alpha[(size_t)nl.img_aoff[nl.atom_img[jj]] * rowlen + t];
+        asum[(size_t)ip0 * rowlen + t] = acc;
+    }
+}
+
 template <int WORDS>
 __global__ void nloc_patch_kernel(double *__restrict__ out, const size_t ld, const int *__restrict__ src,
                                   const int *__restrict__ dst, const int n)
@@ -319,7 +351,7 @@ int launch_shape(chefsi_ctx *ctx, const NlocView &v, const double *aprev, double
     constexpr int kThreads = SH::T;
     constexpr size_t red_bytes = (size_t)SH::kWarps * NP * (kCols + 1) * sizeof(double);
     constexpr size_t smem = sizeof(Smem<NP, SH>) > red_bytes ? sizeof(Smem<NP, SH>) : red_bytes;
-    auto kern = nloc_kernel<NP, WORDS, MODE, SH>;
+    auto kern = v.alpha_sum ? nloc_kernel<NP, WORDS, MODE, SH, true> : nloc_kernel<NP, WORDS, MODE, SH, false>;
     {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(nloc): %s", cudaGetErrorString(e)); return -1; }
@@ -380,14 +412,23 @@ int nloc_padded_nproj(int max_nproj)
 static int ensure_alpha(chefsi_ctx *ctx, int ncol, int words)
 {
     const size_t need = (size_t)ctx->nl.img_proj_total * ncol * sizeof(double) * words;
-    if (need <= ctx->alpha_bytes) return 0;
-    for (int i = 0; i < 2; i++) { cudaFree(ctx->d_alpha[i]); ctx->d_alpha[i] = nullptr; }
-    ctx->alpha_bytes = 0;
-    for (int i = 0; i < 2; i++) {
-        cudaError_t e = cudaMalloc(&ctx->d_alpha[i], need);
-        if (e != cudaSuccess) { chefsi_fail(ctx, "cudaMalloc(alpha, %zu): %s", need, cudaGetErrorString(e)); return -1; }
+    if (need > ctx->alpha_bytes) {
+        for (int i = 0; i < 2; i++) { cudaFree(ctx->d_alpha[i]); ctx->d_alpha[i] = nullptr; }
+        ctx->alpha_bytes = 0;
+        for (int i = 0; i < 2; i++) {
+            cudaError_t e = cudaMalloc(&ctx->d_alpha[i], need);
+            if (e != cudaSuccess) { chefsi_fail(ctx, "cudaMalloc(alpha, %zu): %s", need, cudaGetErrorString(e)); return -1; }
+        }
+        ctx->alpha_bytes = need;
     }
-    ctx->alpha_bytes = need;
+    const size_t ns = (ctx->nl.max_parts > ctx->alpha_reduce_min) ? (size_t)ctx->nl.ntot * ncol * sizeof(double) * words : 0;
+    if (ns > ctx->alpha_sum_bytes) {
+        cudaFree(ctx->d_alpha_sum); ctx->d_alpha_sum = nullptr;
+        ctx->alpha_sum_bytes = 0;
+        cudaError_t e = cudaMalloc(&ctx->d_alpha_sum, ns);
+        if (e != cudaSuccess) { chefsi_fail(ctx, "cudaMalloc(alpha sums, %zu): %s", ns, cudaGetErrorString(e)); return -1; }
+        ctx->alpha_sum_bytes = ns;
+    }
     return 0;
 }
 
@@ -402,13 +443,23 @@ int launch_nloc(chefsi_ctx *ctx, int mode, void *vec, size_t ld, int ncol, doubl
     if (ensure_alpha(ctx, ncol, words)) return -1;
     const Layout &L = ctx->lay;
     NlocView v{d.IP_displ, d.gamma, d.img_atom, d.img_ndc, d.img_aoff, d.pos_off, d.chiT_off, d.grid_pos, d.chiT,
-               d.img_phase, d.atom_img_off, d.atom_img,
+               d.img_phase, d.atom_img_off, d.atom_img, nullptr,
                L.Nxp, L.Nyp, L.px, L.py, L.Nx, L.Ny,
                (L.px && !ctx->grid.BCx) ? 1 : 0, (L.py && !ctx->grid.BCy) ? 1 : 0};
     int kmode = mode;
     if (mode == NLOC_FUSED && d.overlap) { chefsi_fail(ctx, "nloc: fused mode needs disjoint spheres"); return -1; }
     if (mode == NLOC_EXPAND && d.overlap) kmode = MODE_EXPAND_ATOMIC;
     const double *aprev = reinterpret_cast<const double *>(ctx->d_alpha[ctx->alpha_cur]);
+    int n_extra = 0;
+    if (mode != NLOC_PROJECT && d.max_parts > ctx->alpha_reduce_min) { /* consumers read per-atom sums instead of looping over many partials */
+        const size_t rowlen = (size_t)ncol * words;
+        const unsigned gx = (unsigned)std::min<size_t>(64, ((size_t)d.max_nproj * rowlen + 255) / 256);
+        alpha_reduce_kernel<<<dim3(gx ? gx : 1, (unsigned)d.n_atom), 256, 0, ctx->stream>>>(v, aprev, (double *)ctx->d_alpha_sum, rowlen);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { chefsi_fail(ctx, "alpha reduce launch: %s", cudaGetErrorString(e)); return -1; }
+        v.alpha_sum = (const double *)ctx->d_alpha_sum;
+        n_extra = 1;
+    }
     double *anext = reinterpret_cast<double *>(ctx->d_alpha[mode == NLOC_FUSED ? ctx->alpha_cur ^ 1 : ctx->alpha_cur]);
     double *p = reinterpret_cast<double *>(vec);
     int n = -1;
@@ -428,7 +479,7 @@ int launch_nloc(chefsi_ctx *ctx, int mode, void *vec, size_t ld, int ncol, doubl
 #undef CHEFSI_NLOC_CASE
     if (n < 0) return -1;
     if (mode == NLOC_FUSED) ctx->alpha_cur ^= 1;
-    return n;
+    return n + n_extra;
 }
 
 int launch_nloc_halo_patch(chefsi_ctx *ctx, void *out, size_t ld, int ncol, bool is_complex)

@@ -64,6 +64,7 @@ static struct {
     int npinned;
     unsigned long long n_filter, n_hmult, n_forward;
     double t_filter;
+    double t_init, t_sync, t_hmult;  /* seconds in context creation, table/Veff synchronisation, H-apply calls */
     unsigned long long n_filter_fwd; /* ChebyshevFiltering calls forwarded to the reference, and their seconds */
     double t_filter_fwd;
 } G;
@@ -87,6 +88,9 @@ static void shim_report(void)
         fprintf(stderr, "[chefsi_b200 shim] %llu ChebyshevFiltering calls (%.3f s), %llu Hamiltonian_vectors_mult calls, "
                         "%llu calls forwarded to the reference (of which %llu ChebyshevFiltering calls, %.3f s)\n",
                 G.n_filter, G.t_filter, G.n_hmult, G.n_forward, G.n_filter_fwd, G.t_filter_fwd);
+    if (G.verbose)
+        fprintf(stderr, "[chefsi_b200 shim] context creation %.3f s, Hamiltonian_vectors_mult calls %.3f s, grid/projector/Veff "
+                        "synchronisation %.3f s (included in the call times)\n", G.t_init, G.t_hmult, G.t_sync);
     if (G.ctx) { chefsi_destroy(G.ctx); G.ctx = NULL; }
 }
 
@@ -111,10 +115,12 @@ static void shim_init(void)
     if (!lr) lr = getenv("SLURM_LOCALID");
     if (!dev && lr) device = atoi(lr);
     shim_register_report();
+    const double t_init0 = MPI_Wtime();
     if (chefsi_create(&G.ctx, device) != 0) {
         fprintf(stderr, "[chefsi_b200 shim] cannot create the CUDA context: %s\n", chefsi_last_error(NULL));
         exit(EXIT_FAILURE);
     }
+    G.t_init += MPI_Wtime() - t_init0;
     if (G.verbose) fprintf(stderr, "[chefsi_b200 shim] %s on device %d\n", chefsi_version(), device);
 }
 
@@ -298,12 +304,13 @@ void ChebyshevFiltering(SPARC_OBJ *pSPARC, int *DMVertices, double *X, int ldi, 
         G.t_filter_fwd += MPI_Wtime() - t0;
         return;
     }
-    const double t1 = MPI_Wtime();
     shim_init();
+    const double t1 = MPI_Wtime();
     shim_sync_grid(pSPARC);
     shim_sync_projectors(pSPARC, pSPARC->Atom_Influence_nloc, pSPARC->nlocProj, 0);
     const int sg = pSPARC->spin_start_indx + spn_i; /* eigenSolver.c:756 */
     if (chefsi_set_veff(G.ctx, pSPARC->Veff_loc_dmcomm + (size_t)sg * pSPARC->Nd_d_dmcomm) != 0) shim_fatal("chefsi_set_veff");
+    G.t_sync += MPI_Wtime() - t1;
     if (ncol > 0) {
         shim_pin(X, sizeof(double) * (size_t)ldi * ncol);
         shim_pin(Y, sizeof(double) * (size_t)ldo * ncol);
@@ -334,13 +341,14 @@ void ChebyshevFiltering_kpt(SPARC_OBJ *pSPARC, int *DMVertices, double _Complex 
         G.t_filter_fwd += MPI_Wtime() - t0;
         return;
     }
-    const double t1 = MPI_Wtime();
     shim_init();
+    const double t1 = MPI_Wtime();
     shim_sync_grid(pSPARC);
     shim_sync_projectors(pSPARC, pSPARC->Atom_Influence_nloc, pSPARC->nlocProj, 1);
     const int sg = pSPARC->spin_start_indx + spn_i;
     if (chefsi_set_veff(G.ctx, pSPARC->Veff_loc_dmcomm + (size_t)sg * pSPARC->Nd_d_dmcomm) != 0) shim_fatal("chefsi_set_veff");
     if (chefsi_set_kpoint(G.ctx, pSPARC->k1_loc[kpt], pSPARC->k2_loc[kpt], pSPARC->k3_loc[kpt]) != 0) shim_fatal("chefsi_set_kpoint");
+    G.t_sync += MPI_Wtime() - t1;
     if (ncol > 0) {
         shim_pin(X, sizeof(double _Complex) * (size_t)ldi * ncol);
         shim_pin(Y, sizeof(double _Complex) * (size_t)ldo * ncol);
@@ -364,11 +372,14 @@ void Hamiltonian_vectors_mult(const SPARC_OBJ *pSPARC, int DMnd, int *DMVertices
         return;
     }
     shim_init();
+    const double t1 = MPI_Wtime();
     shim_sync_grid(pSPARC);
     shim_sync_projectors(pSPARC, Atom_Influence_nloc, nlocProj, 0);
     if (chefsi_set_veff(G.ctx, Veff_loc) != 0) shim_fatal("chefsi_set_veff");
+    G.t_sync += MPI_Wtime() - t1;
     if (chefsi_hamiltonian_mult(G.ctx, ncol, c, x, (size_t)ldi, Hx, (size_t)ldo) != 0) shim_fatal("chefsi_hamiltonian_mult");
     G.n_hmult++;
+    G.t_hmult += MPI_Wtime() - t1;
 }
 
 void Hamiltonian_vectors_mult_kpt(const SPARC_OBJ *pSPARC, int DMnd, int *DMVertices, double *Veff_loc,
@@ -383,10 +394,13 @@ void Hamiltonian_vectors_mult_kpt(const SPARC_OBJ *pSPARC, int DMnd, int *DMVert
         return;
     }
     shim_init();
+    const double t1 = MPI_Wtime();
     shim_sync_grid(pSPARC);
     shim_sync_projectors(pSPARC, Atom_Influence_nloc, nlocProj, 1);
     if (chefsi_set_veff(G.ctx, Veff_loc) != 0) shim_fatal("chefsi_set_veff");
     if (chefsi_set_kpoint(G.ctx, pSPARC->k1_loc[kpt], pSPARC->k2_loc[kpt], pSPARC->k3_loc[kpt]) != 0) shim_fatal("chefsi_set_kpoint");
+    G.t_sync += MPI_Wtime() - t1;
     if (chefsi_hamiltonian_mult_kpt(G.ctx, ncol, c, x, (size_t)ldi, Hx, (size_t)ldo) != 0) shim_fatal("chefsi_hamiltonian_mult_kpt");
     G.n_hmult++;
+    G.t_hmult += MPI_Wtime() - t1;
 }
