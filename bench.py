@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--block", type=int, default=128, help="columns filtered per launch group")
     ap.add_argument("--ncell", type=int, default=6, help="fcc conventional cells per axis (4 atoms each)")
     ap.add_argument("--no-nloc", action="store_true", help="stencil + Veff only (roofline study)")
+    # SURVEY.md 8d "secondary synthetic" configurations (not the headline line): the same workload on the k-point
+    # (complex, Bloch-phase halo) path and on a non-orthogonal lattice
+    ap.add_argument("--kpt", action="store_true", help="complex orbitals at k = (0.25, 0.25, 0.25) * 2 pi / L")
+    ap.add_argument("--cell-typ", type=int, default=0, help="lattice flavour (0 orthogonal; 11..17: problem.LATVEC_BY_CELL_TYP)")
     ap.add_argument("--no-veff", action="store_true", help="skip the local potential (experiment: cost of the Veff tile stream)")
     ap.add_argument("--e2e-cols", type=int, default=256)
     ap.add_argument("--cpu-cols-per-core", type=int, default=1)
@@ -57,7 +61,7 @@ def build_problem(args):
     from sparc_b200 import problem as P
     n = args.grid
     L = 45.9 * n / 160.0  # keep h = 0.286875 Bohr when the grid is shrunk for debugging
-    g = P.make_grid((n, n, n), (L, L, L))
+    g = P.make_grid((n, n, n), (L, L, L), latvec=P.LATVEC_BY_CELL_TYP[args.cell_typ] if args.cell_typ else None)
     veff = P.synthetic_veff(g)
     proj = None
     if not args.no_nloc:
@@ -69,8 +73,10 @@ def build_problem(args):
 
 def workload_name(args, proj):
     nat = proj.n_atom if proj is not None else 0
+    kind = "complex FP64 (k-point)" if args.kpt else "real FP64"
+    lat = f", cell_typ {args.cell_typ} lattice" if args.cell_typ else ""
     return (f"synthetic Al fcc supercell {args.grid}^3 grid x {args.ncol} states, Chebyshev degree {args.degree}, "
-            f"FD order 12, {nat} atoms x 18 KB projectors, real FP64")
+            f"FD order 12, {nat} atoms x 18 KB projectors{lat}, {kind}")
 
 
 class ClockSampler:
@@ -231,6 +237,10 @@ def run_ours(args):
     if not args.no_veff:
         ctx.set_veff(veff)
     ctx.set_projectors(proj)
+    cplx = bool(args.kpt)
+    words = 2 if cplx else 1
+    if cplx:
+        ctx.set_kpoint(tuple(0.25 * 2 * np.pi / Lk for Lk in g.L))
     ld = ctx.device_ld
     first_col, ncol_local = band_partition(args.ncol, world, rank)
     block = min(args.block, max(ncol_local, 1))
@@ -238,19 +248,19 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
     # all local columns resident in HBM: nblocks slots + 2 spare slots that rotate through the recurrence
-    slots = [torch.empty(block * ld, dtype=torch.float64, device="cuda") for _ in range(nblocks + 2)]
+    slots = [torch.empty(block * ld * words, dtype=torch.float64, device="cuda") for _ in range(nblocks + 2)]
     where = list(range(nblocks))           # slot holding block i
     spare = [nblocks, nblocks + 1]
     for i in range(nblocks):
         nc = min(block, ncol_local - i * block)
-        ctx.fill_random_device(slots[where[i]], nc, first_col=first_col + i * block, seed=1)
+        ctx.fill_random_device(slots[where[i]], nc, first_col=first_col + i * block, seed=1, is_complex=cplx)
     ctx.synchronize()
 
     def one_step():
         for i in range(nblocks):
             nc = min(block, ncol_local - i * block)
             trio = [where[i], spare[0], spare[1]]
-            ys, xs = ctx.filter_device(slots[trio[0]], slots[trio[1]], slots[trio[2]], nc, m, a, b, a0)
+            ys, xs = ctx.filter_device(slots[trio[0]], slots[trio[1]], slots[trio[2]], nc, m, a, b, a0, is_complex=cplx)
             new_where = trio[ys]
             rest = [t for t in trio if t != new_where]
             where[i], spare[0], spare[1] = new_where, rest[0], rest[1]
@@ -293,7 +303,7 @@ def run_ours(args):
     for i in range(nblocks):
         nc = min(block, ncol_local - i * block)
         trio = [where[i], spare[0], spare[1]]
-        ys, xs = ctx.filter_device(slots[trio[0]], slots[trio[1]], slots[trio[2]], nc, m, a, b, a0)
+        ys, xs = ctx.filter_device(slots[trio[0]], slots[trio[1]], slots[trio[2]], nc, m, a, b, a0, is_complex=cplx)
         new_where = trio[ys]
         rest = [t for t in trio if t != new_where]
         where[i], spare[0], spare[1] = new_where, rest[0], rest[1]
@@ -301,7 +311,7 @@ def run_ours(args):
         st_ms += s["last_stencil_ms"]
         st_n += s["last_stencil_launches"]
         nl_ms += s["last_nloc_ms"]
-        alg_bytes += 8.0 * (3 * m - 1) * g.Nd * nc   # 16 B first step, 24 B the others
+        alg_bytes += 8.0 * words * (3 * m - 1) * g.Nd * nc   # 16 B first step, 24 B the others (x2 complex)
     ctx.set_profiling(False)
     peaks = {}
     try:
@@ -312,11 +322,11 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     achieved = alg_bytes / (st_ms * 1e-3) / 1e9 if st_ms > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": ("stream_dense_kernel" if os.environ.get("CHEFSI_B200_DENSE", "1") != "0" else "stream_orth_kernel") + " (fused stencil + Veff + recurrence)" if ctx.stats()["last_path"] == 1 else "stencil_general_kernel",
+        "bound": "hbm", "kernel": ("stream_dense_kernel" if os.environ.get("CHEFSI_B200_DENSE", "1") != "0" else "stream_orth_kernel") + " (fused stencil + Veff + recurrence)" if ctx.stats()["last_path"] == 1 else ("stencil_zmarch_kernel" if ctx.stats()["last_path"] == 2 else "stencil_general_kernel"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if (args.grid == 160 and block == 128 and ctx.stats()["last_path"] == 1 and os.environ.get("CHEFSI_B200_DENSE", "1") != "0") else None,
         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 128-column launch (profiles/r1_ncu_dense_map2x2.txt)",
         "peak_source": peak_src, "avg_launch_ms": st_ms / st_n if st_n else None,
-        "algorithmic_bytes_per_launch": 8.0 * (3 * m - 1) * g.Nd * block / m,
+        "algorithmic_bytes_per_launch": 8.0 * words * (3 * m - 1) * g.Nd * block / m,
         "timing": "per-launch CUDA events over one full step run back to back with the timed steps (sustained clocks)",
         "stencil_share_of_filter": st_ms / (st_ms + nl_ms) if st_ms + nl_ms > 0 else None,
         "nloc_ms_per_degree": nl_ms / st_n if st_n else None,
@@ -324,8 +334,9 @@ def run_ours(args):
 
     # ---- e2e: the same metric through the host-buffer C-ABI call (H2D + D2H inside the timed region) ----
     e2e_cols = max(1, min(args.e2e_cols // world, ncol_local))
-    xh = torch.empty((e2e_cols, g.Nd), dtype=torch.float64).pin_memory()
-    yh = torch.empty((e2e_cols, g.Nd), dtype=torch.float64).pin_memory()
+    hdt = torch.complex128 if cplx else torch.float64
+    xh = torch.empty((e2e_cols, g.Nd), dtype=hdt).pin_memory()
+    yh = torch.empty((e2e_cols, g.Nd), dtype=hdt).pin_memory()
     from sparc_b200 import problem as P
     xh.numpy()[:] = P.random_columns(g.Nd, 1, first_col=first_col, seed=1)[0]  # same column replicated: content is irrelevant to timing
     del slots  # free HBM for the host entry point's own buffers
@@ -334,7 +345,7 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     ctx.ChebyshevFiltering(xh, yh, m, a, b, a0, copy_back_x=False)
-    checksum = float(yh[0, :8].sum())  # device->host result is read on the host
+    checksum = float(yh[0, :8].sum().real)  # device->host result is read on the host
     t_e2e = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
@@ -342,7 +353,7 @@ def run_ours(args):
         t_e2e = float(t.item())
     e2e_total_cols = e2e_cols * world
     e2e = {"value": g.Nd * e2e_total_cols / t_e2e, "unit": UNIT,
-           "h2d_bytes_per_step": int(e2e_cols * g.Nd * 8), "d2h_bytes_per_step": int(e2e_cols * g.Nd * 8),
+           "h2d_bytes_per_step": int(e2e_cols * g.Nd * 8 * words), "d2h_bytes_per_step": int(e2e_cols * g.Nd * 8 * words),
            "columns": e2e_total_cols, "seconds": t_e2e, "checksum": checksum,
            "api": "chefsi_chebyshev_filter (host buffers, pinned), X copy-back off as in the SPARC shim"}
 

@@ -164,7 +164,7 @@ typedef struct chefsi_stats {
     double last_stencil_ms;             /* summed device time of its stencil-step kernels  */
     double last_nloc_ms;                /* summed device time of its projector kernels     */
     int last_stencil_launches;
-    int last_path;                      /* 0 = general kernel, 1 = streaming orth kernel   */
+    int last_path;                      /* 0 = 3-D brick kernel, 1 = TMA streaming kernel, 2 = z-march kernel */
 } chefsi_stats_t;
 int chefsi_get_stats(const chefsi_ctx_t *ctx, chefsi_stats_t *out);
 /* when on, every kernel of a filter call is bracketed by CUDA events (adds host

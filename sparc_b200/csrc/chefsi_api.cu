@@ -476,8 +476,15 @@ static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void
         n = launch_stencil_stream_orth(ctx, a, is_complex);
         ctx->stats.last_path = 1;
     } else {
-        n = launch_stencil_general(ctx, a, is_complex);
-        ctx->stats.last_path = 0;
+        n = -2;
+        if (stencil_zmarch_supported(ctx)) {
+            n = launch_stencil_zmarch(ctx, a, is_complex); /* -2: this case does not fit (shared memory) */
+            ctx->stats.last_path = 2;
+        }
+        if (n == -2) {
+            n = launch_stencil_general(ctx, a, is_complex);
+            ctx->stats.last_path = 0;
+        }
     }
     prof.end();
     if (n < 0) return 1;

@@ -126,7 +126,7 @@ struct chefsi_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int num_sms = 148;
     size_t max_smem_optin = 0;
-    int force_general = 0;
+    int force_general = 0;         /* 1: no TMA streaming kernel; 2: neither streaming nor z-march (3-D brick kernel only) */
     int stream_gridsync = 1;       /* round barrier between the streaming kernel's producers */
     int tma_l2promo = 3;           /* CUtensorMapL2promotion of the streaming kernel's tensor maps */
     int dense_stream = 1;          /* 1: dense column layout + stencil_stream_dense.cu (default); 0: halo-padded layout */
@@ -148,6 +148,8 @@ int chefsi_fail(chefsi_ctx *ctx, const char *fmt, ...);
 
 /* ---- kernel launchers (each returns the number of kernels it launched, <0 on error) --- */
 int launch_stencil_general(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
+bool stencil_zmarch_supported(const chefsi_ctx *ctx);
+int launch_stencil_zmarch(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
 bool stream_layout_wanted(const chefsi_grid_t &g);
 bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex);
 int launch_stencil_stream_orth(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);

@@ -192,7 +192,7 @@ def test_dense_stream_kernel_vs_oracle(ctx_dense, port, N, BC):
     Hx = np.empty_like(x)
     ctx.Hamiltonian_vectors_mult(-0.3, x, Hx)
     # Nx = 38, 70 (even, not a multiple of 4) stream only with the 2 x 2 mapping; the 1 x 4 mapping owns quads
-    expect_stream = 1 if (N[0] % 4 == 0 or ctx_dense.variant != 0) else 0
+    expect_stream = 1 if (N[0] % 4 == 0 or ctx_dense.variant != 0) else 2   # 2: the z-march kernel takes it
     assert ctx.stats()["last_path"] == expect_stream
     assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, -0.3, x)) < TOL
     X = x.copy()
@@ -217,7 +217,8 @@ def test_dense_stream_many_columns_round_barrier(ctx_dense, port):
     assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
 
 
-def test_stream_and_general_kernels_agree(ctx):
+def test_stream_zmarch_and_brick_kernels_agree(ctx):
+    """The three stencil kernels (TMA streaming, z-march, 3-D brick) on the same orthogonal problem."""
     import os
     from sparc_b200.chefsi import ChefsiContext
     g = P.make_grid((64, 48, 40), (20.0, 15.0, 12.5))
@@ -228,17 +229,59 @@ def test_stream_and_general_kernels_agree(ctx):
     X1, Y1 = x.copy(), np.empty_like(x)
     ctx.ChebyshevFiltering(X1, Y1, 10, a, b, a0)
     assert ctx.stats()["last_path"] == 1
-    os.environ["CHEFSI_B200_FORCE_GENERAL"] = "1"
+    for level, path, tol in ((1, 2, 1e-12), (2, 0, 1e-12)):
+        os.environ["CHEFSI_B200_FORCE_GENERAL"] = str(level)
+        try:
+            c2 = ChefsiContext(0)
+        finally:
+            del os.environ["CHEFSI_B200_FORCE_GENERAL"]
+        _setup(c2, g, veff, None)
+        X2, Y2 = x.copy(), np.empty_like(x)
+        c2.ChebyshevFiltering(X2, Y2, 10, a, b, a0)
+        assert c2.stats()["last_path"] == path
+        c2.close()
+        assert rel_fro(Y1, Y2) < tol and rel_fro(X1, X2) < tol
+
+
+@pytest.fixture(scope="module")
+def ctx_brick():
+    """Context restricted to the 3-D brick kernel (CHEFSI_B200_FORCE_GENERAL=2), the first general kernel."""
+    import os
+    from sparc_b200.chefsi import ChefsiContext
+    os.environ["CHEFSI_B200_FORCE_GENERAL"] = "2"
     try:
-        c2 = ChefsiContext(0)
+        c = ChefsiContext(0)
     finally:
         del os.environ["CHEFSI_B200_FORCE_GENERAL"]
-    _setup(c2, g, veff, None)
-    X2, Y2 = x.copy(), np.empty_like(x)
-    c2.ChebyshevFiltering(X2, Y2, 10, a, b, a0)
-    assert c2.stats()["last_path"] == 0
-    c2.close()
-    assert rel_fro(Y1, Y2) < 1e-12 and rel_fro(X1, X2) < 1e-12
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("cell_typ", [0, 11, 12, 13, 14, 15, 16, 17])
+@pytest.mark.parametrize("complex_", [False, True])
+def test_brick_kernel_all_cell_types(ctx_brick, port, cell_typ, complex_):
+    """The brick kernel stays the fallback (FD radius != 6, complex cell_typ 15): keep it pinned to the oracle."""
+    g, veff, proj, x = small_case(cell_typ, (0, 0, 0), complex_=complex_)
+    _setup(ctx_brick, g, veff, proj, KVEC)
+    Hx = np.empty_like(x)
+    ctx_brick.Hamiltonian_vectors_mult(0.25, x, Hx)
+    assert ctx_brick.stats()["last_path"] == 0
+    assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, 0.25, x, kvec=KVEC)) < TOL
+
+
+@pytest.mark.parametrize("cell_typ", [0, 12, 15, 17])
+@pytest.mark.parametrize("complex_", [False, True])
+@pytest.mark.parametrize("N", [(45, 21, 19), (70, 35, 14)])
+def test_zmarch_kernel_multi_tile(ctx, port, cell_typ, complex_, N):
+    """z-march kernel on grids with several (ragged) tiles per plane, all three kinds of mixed-derivative
+    components (x-, y- and z-extended), real and complex."""
+    g, veff, proj, x = small_case(cell_typ, (0, 0, 0), N=N, L=tuple(0.5 * n for n in N), complex_=complex_)
+    _setup(ctx, g, veff, proj, KVEC)
+    Hx = np.empty_like(x)
+    ctx.Hamiltonian_vectors_mult(0.25, x, Hx)
+    # complex cell_typ 15 does not fit the z-march kernel's shared memory and takes the brick kernel
+    assert ctx.stats()["last_path"] == (0 if (cell_typ == 15 and complex_) else 2)
+    assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, 0.25, x, kvec=KVEC)) < TOL
 
 
 # ---------------------------------------------------------------- full-size properties (160^3)
