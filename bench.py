@@ -322,7 +322,7 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     achieved = alg_bytes / (st_ms * 1e-3) / 1e9 if st_ms > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": ("stream_dense_kernel" if os.environ.get("CHEFSI_B200_DENSE", "1") != "0" else "stream_orth_kernel") + " (fused stencil + Veff + recurrence)" if ctx.stats()["last_path"] == 1 else ("stencil_zmarch_kernel" if ctx.stats()["last_path"] == 2 else "stencil_general_kernel"),
+        "bound": "hbm", "kernel": ("stream_kpt_kernel" if cplx else "stream_dense_kernel" if os.environ.get("CHEFSI_B200_DENSE", "1") != "0" else "stream_orth_kernel") + " (fused stencil + Veff + recurrence)" if ctx.stats()["last_path"] == 1 else ("stencil_zmarch_kernel" if ctx.stats()["last_path"] == 2 else "stencil_general_kernel"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if (args.grid == 160 and block == 128 and ctx.stats()["last_path"] == 1 and os.environ.get("CHEFSI_B200_DENSE", "1") != "0") else None,
         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 128-column launch (profiles/r1_ncu_dense_map2x2.txt)",
         "peak_source": peak_src, "avg_launch_ms": st_ms / st_n if st_n else None,

@@ -475,6 +475,9 @@ static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void
     if (stream_orth_supported(ctx, is_complex)) {
         n = launch_stencil_stream_orth(ctx, a, is_complex);
         ctx->stats.last_path = 1;
+    } else if (is_complex && stream_kpt_supported(ctx)) {
+        n = launch_stencil_stream_kpt(ctx, a);
+        ctx->stats.last_path = 1;
     } else {
         n = -2;
         if (stencil_zmarch_supported(ctx)) {

@@ -148,6 +148,8 @@ int chefsi_fail(chefsi_ctx *ctx, const char *fmt, ...);
 
 /* ---- kernel launchers (each returns the number of kernels it launched, <0 on error) --- */
 int launch_stencil_general(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
+bool stream_kpt_supported(const chefsi_ctx *ctx);
+int launch_stencil_stream_kpt(chefsi_ctx *ctx, const StepArgs &a);
 bool stencil_zmarch_supported(const chefsi_ctx *ctx);
 int launch_stencil_zmarch(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
 bool stream_layout_wanted(const chefsi_grid_t &g);

@@ -202,6 +202,46 @@ def test_dense_stream_kernel_vs_oracle(ctx_dense, port, N, BC):
     assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
 
 
+@pytest.mark.parametrize("N,BC", [((16, 32, 12), (0, 0, 0)), ((32, 32, 16), (0, 0, 0)), ((40, 38, 14), (0, 0, 0)),
+                                   ((48, 64, 12), (0, 0, 0)), ((18, 39, 13), (0, 0, 0)), ((34, 70, 12), (0, 0, 0)),
+                                   ((32, 32, 16), (1, 0, 1)), ((36, 32, 12), (0, 1, 0)), ((32, 40, 12), (1, 1, 1)),
+                                   ((38, 33, 12), (0, 1, 1))])
+def test_kpt_stream_kernel_vs_oracle(ctx, port, N, BC):
+    """k-point (complex) streaming kernel: Bloch phases on periodic-x strips, wrapped y boxes and z wrap planes,
+    shifted last tiles, Dirichlet faces, with projectors; H apply and a degree-8 filter against the oracle."""
+    g = P.make_grid(N, tuple(0.45 * n for n in N), BC=BC)
+    veff = P.synthetic_veff(g)
+    proj = P.make_projectors(g, np.array([[0.02, 0.5, 0.97], [0.5, 0.5, 0.5]]), rc=[2.4, 2.0], nproj=[18, 7])
+    x = P.random_columns(g.Nd, 3, seed=21) + 1j * P.random_columns(g.Nd, 3, first_col=500, seed=21)
+    x = np.ascontiguousarray(x)
+    kvec = tuple(kk if bc == 0 else 0.0 for kk, bc in zip(KVEC, BC))  # SPARC has no k component along Dirichlet axes
+    _setup(ctx, g, veff, proj, kvec)
+    Hx = np.empty_like(x)
+    ctx.Hamiltonian_vectors_mult(-0.3, x, Hx)
+    assert ctx.stats()["last_path"] == 1
+    assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, -0.3, x, kvec=kvec)) < TOL
+    a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+    X = x.copy()
+    Y = np.empty_like(X)
+    ctx.ChebyshevFiltering(X, Y, 8, a, b, a0)
+    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 8, a, b, a0, kvec=kvec)
+    assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+
+
+def test_kpt_stream_many_columns(ctx, port):
+    """More k-point work items than SMs (round barrier, ring wrap-around across items)."""
+    g = P.make_grid((32, 64, 12), (14.4, 28.8, 5.4))
+    veff = P.synthetic_veff(g)
+    x = np.ascontiguousarray(P.random_columns(g.Nd, 50, seed=6) + 1j * P.random_columns(g.Nd, 50, first_col=900, seed=6))
+    _setup(ctx, g, veff, None, KVEC)
+    a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+    X, Y = x.copy(), np.empty_like(x)
+    ctx.ChebyshevFiltering(X, Y, 4, a, b, a0)
+    assert ctx.stats()["last_path"] == 1
+    Xw, Yw = port.chebyshev_filter(g, None, veff, x, 4, a, b, a0, kvec=KVEC)
+    assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+
+
 def test_dense_stream_many_columns_round_barrier(ctx_dense, port):
     """More work items than SMs: the persistent CTAs loop over items and the producers' round barrier runs."""
     ctx = ctx_dense
