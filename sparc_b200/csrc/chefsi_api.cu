@@ -670,7 +670,7 @@ static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
     /* pipeline granularity: only worth it when the block is big enough for the copies to matter */
     const size_t block_bytes = (size_t)ncol * ctx->Nd * esz;
     if (block_bytes > ((size_t)64 << 20)) {
-        size_t want = ((size_t)ncol + 3) / 4;
+        size_t want = ((size_t)ncol + 7) / 8;
         if (want < 32) want = 32;
         if (want > 128) want = 128;
         const char *e2 = getenv("CHEFSI_B200_HOST_CHUNK");
@@ -715,8 +715,23 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     int k = 0;
     if (direct) {
         const size_t pitch = ctx->ld * esz;
-        for (int c0 = 0; c0 < ncol; c0 += chunk, k++) {
-            const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
+        /* Chunk schedule: the first H2D and the last D2H are the only copies nothing overlaps with, so the
+           pipeline ramps up and down through quarter- and half-size chunks (c/4, c/2, c, ..., c, c/2, c/4). */
+        std::vector<int> sched;
+        {
+            const int q = chunk / 4, h = chunk / 2;
+            if (ncol >= 3 * chunk && q >= 8 && getenv("CHEFSI_B200_FLAT_CHUNKS") == nullptr) {
+                int rest = ncol - 2 * (q + h);
+                sched.push_back(q); sched.push_back(h);
+                while (rest > 0) { const int c1 = rest < chunk ? rest : chunk; sched.push_back(c1); rest -= c1; }
+                sched.push_back(h); sched.push_back(q);
+            } else {
+                for (int c0 = 0; c0 < ncol; c0 += chunk) sched.push_back((ncol - c0 < chunk) ? ncol - c0 : chunk);
+            }
+        }
+        int c0 = 0;
+        for (size_t kk = 0; kk < sched.size(); c0 += sched[kk], kk++, k++) {
+            const int nc = sched[kk];
             const int s = k % 3;
             void **trio = s == 0 ? ctx->d_buf : (s == 1 ? ctx->d_buf2 : ctx->d_buf3);
             /* trio s is free again when the copies of chunk k-3 out of it have finished */

@@ -324,6 +324,28 @@ def test_zmarch_kernel_multi_tile(ctx, port, cell_typ, complex_, N):
     assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, 0.25, x, kvec=KVEC)) < TOL
 
 
+def test_host_pipeline_ramped_chunks(port):
+    """Host-buffer entry point on a block big enough for the chunk pipeline (three buffer trios, chunk schedule
+    8, 16, 32, .., 16, 8), X copy-back on: every column must come back filtered exactly once."""
+    import os
+    from sparc_b200.chefsi import ChefsiContext
+    os.environ["CHEFSI_B200_HOST_CHUNK"] = "32"
+    try:
+        c = ChefsiContext(0)
+        g = P.make_grid((64, 64, 64), (28.8, 28.8, 28.8))
+        veff = P.synthetic_veff(g)
+        x = P.random_columns(g.Nd, 100, seed=9)
+        _setup(c, g, veff, None)
+        a, b, a0 = P.chebyshev_bounds(g)
+        X, Y = x.copy(), np.empty_like(x)
+        c.ChebyshevFiltering(X, Y, 3, a, b, a0)
+        Xw, Yw = port.chebyshev_filter(g, None, veff, x, 3, a, b, a0)
+        assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+        c.close()
+    finally:
+        del os.environ["CHEFSI_B200_HOST_CHUNK"]
+
+
 # ---------------------------------------------------------------- full-size properties (160^3)
 def test_full_size_plane_wave_and_linearity(ctx):
     """BASELINE.json's grid (160^3, FD order 12): a plane wave is an eigenvector of H when Veff is
