@@ -139,6 +139,22 @@ int chefsi_hamiltonian_mult_device(chefsi_ctx_t *ctx, int ncol, double c, const 
                                    double *Hx);
 int chefsi_hamiltonian_mult_kpt_device(chefsi_ctx_t *ctx, int ncol, double c, const void *x,
                                        void *Hx);
+/* Building blocks of the optional DOMAIN SPLIT (z slabs over ranks, sparc_b200/domain_split.py), real data:
+ * the reference exchanges FDn halo planes per face before every stencil application
+ * (Lap_plus_diag_vec_mult_orth, src/lapVecRoutines.c:387-442,494-534) and all-reduces the projector
+ * inner products alpha over the domain communicator (Vnl_vec_mult, src/nlocVecRoutines.c:834-838).
+ * The caller owns the exchange (NCCL send/recv, all-reduce); these calls are the local pieces in between,
+ * on device-resident blocks in the internal layout of the rank's slab (grid set with its halo planes and a
+ * Dirichlet z face):
+ *   stencil_step   out = s1 * ((-1/2 Lap + Veff + c) x) - s2 * xprev        (no projector part; xprev may be NULL)
+ *   nloc_project   alpha[IP_displ[atom] * ncol + col * nproj(atom) + p] = dV * sum over the LOCAL sphere points
+ *                  of Chi x, written to the caller's device buffer alpha_out (n_proj_total * ncol doubles),
+ *                  which the caller all-reduces over the ranks of the split
+ *   nloc_expand    out += scale * Chi Gamma alpha_in    (alpha_in: the reduced buffer, device)             */
+int chefsi_stencil_step_device(chefsi_ctx_t *ctx, const double *x, const double *xprev, double *out, int ncol,
+                               double c, double s1, double s2);
+int chefsi_nloc_project_device(chefsi_ctx_t *ctx, const double *x, int ncol, double *alpha_out);
+int chefsi_nloc_expand_device(chefsi_ctx_t *ctx, double *out, int ncol, double scale, const double *alpha_in);
 int chefsi_synchronize(chefsi_ctx_t *ctx);
 /* Page-lock / unlock a caller-owned host range so the host entry points' chunk pipeline copies at
  * full PCIe rate and overlaps with the kernels (cudaHostRegister; the caller's malloc'd orbital

@@ -23,6 +23,7 @@ EXPORTS = (
     "chefsi_hamiltonian_mult_device", "chefsi_hamiltonian_mult_kpt_device",
     "chefsi_synchronize", "chefsi_fill_random_device", "chefsi_pack_device", "chefsi_unpack_device",
     "chefsi_get_stats", "chefsi_set_profiling", "chefsi_stream", "chefsi_host_register", "chefsi_host_unregister",
+    "chefsi_stencil_step_device", "chefsi_nloc_project_device", "chefsi_nloc_expand_device",
 )
 
 
@@ -84,6 +85,9 @@ def load_library() -> C.CDLL:
     lib.chefsi_set_profiling.argtypes = [vp, i]
     lib.chefsi_host_register.argtypes = [vp, vp, sz]
     lib.chefsi_host_unregister.argtypes = [vp, vp]
+    lib.chefsi_stencil_step_device.argtypes = [vp, dp, dp, dp, i, d, d, d]
+    lib.chefsi_nloc_project_device.argtypes = [vp, dp, i, dp]
+    lib.chefsi_nloc_expand_device.argtypes = [vp, dp, i, d, dp]
     lib.chefsi_stream.argtypes = [vp]
     lib.chefsi_stream.restype = vp
     _lib = lib

@@ -134,6 +134,21 @@ class ChefsiContext:
         fn = self._lib.chefsi_hamiltonian_mult_kpt_device if is_complex else self._lib.chefsi_hamiltonian_mult_device
         self._check(fn(self._h, int(ncol), float(c), _addr(x), _addr(Hx)))
 
+    # -- domain-split building blocks (real data; see domain_split.py) -----------------------------
+    def stencil_step_device(self, x, xprev, out, ncol, c, s1, s2):
+        """out = s1 ((-1/2 Lap + Veff + c) x) - s2 xprev on device blocks, without the projector part."""
+        self._check(self._lib.chefsi_stencil_step_device(self._h, _addr(x), _addr(xprev), _addr(out), int(ncol),
+                                                         float(c), float(s1), float(s2)))
+
+    def nloc_project_device(self, x, ncol, alpha_out):
+        """Local projector inner products of x into the caller's device buffer (n_proj_total * ncol doubles,
+        atom a at IP_displ[a] * ncol, [column][projector])."""
+        self._check(self._lib.chefsi_nloc_project_device(self._h, _addr(x), int(ncol), _addr(alpha_out)))
+
+    def nloc_expand_device(self, out, ncol, scale, alpha_in):
+        """out += scale * Chi Gamma alpha_in (the all-reduced buffer)."""
+        self._check(self._lib.chefsi_nloc_expand_device(self._h, _addr(out), int(ncol), float(scale), _addr(alpha_in)))
+
     def fill_random_device(self, buf, ncol, first_col=0, seed=1, is_complex=False):
         self._check(self._lib.chefsi_fill_random_device(self._h, _addr(buf), int(ncol), int(first_col), int(seed),
                                                         int(bool(is_complex))))

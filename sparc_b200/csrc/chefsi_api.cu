@@ -456,14 +456,14 @@ struct Profiler {
  *         fused projector kernel); otherwise they are computed here from x.
  * nl_out: after adding Vnl x, also project `out` for the next step (only legal when spheres are disjoint). */
 static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void *xprev, void *out, int ncol, double c,
-                      double s1, double s2, bool is_complex, bool nl_in, bool nl_out)
+                      double s1, double s2, bool is_complex, bool nl_in, bool nl_out, bool with_nl = true)
 {
     StepArgs a;
     a.x = x; a.xprev = xprev; a.out = out;
     a.veff = ctx->have_veff ? ctx->d_veff : nullptr;
     a.ld = ctx->ld; a.ncol = ncol; a.c = c; a.s1 = s1; a.s2 = s2;
     int n;
-    const bool have_nl = ctx->nl.n_img > 0 && ctx->nl.ntot > 0;
+    const bool have_nl = with_nl && ctx->nl.n_img > 0 && ctx->nl.ntot > 0;
     if (have_nl && !nl_in) {
         prof.begin(1);
         n = launch_nloc(ctx, NLOC_PROJECT, const_cast<void *>(x), ctx->ld, ncol, 0.0, is_complex);
@@ -916,6 +916,60 @@ extern "C" int chefsi_get_stats(const chefsi_ctx_t *ctx, chefsi_stats_t *out)
     *out = ctx->stats;
     return 0;
 }
+/* ---- domain-split building blocks (see include/chefsi_b200.h) ---------------------------------------- */
+extern "C" int chefsi_stencil_step_device(chefsi_ctx_t *ctx, const double *x, const double *xprev, double *out, int ncol,
+                                          double c, double s1, double s2)
+{
+    if (!ctx) return 1;
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    Profiler prof(ctx);
+    if (stream_orth_supported(ctx, false)) {
+        int n = launch_halo_prepare(ctx, const_cast<double *>(x), ncol, false, 0);
+        if (n < 0) return 1;
+        ctx->stats.kernel_launches += n;
+    }
+    const int rc = apply_step(ctx, prof, x, xprev, out, ncol, c, s1, s2, false, false, false, /*with_nl=*/false);
+    prof.finish();
+    return rc;
+}
+
+extern "C" int chefsi_nloc_project_device(chefsi_ctx_t *ctx, const double *x, int ncol, double *alpha_out)
+{
+    if (!ctx || !alpha_out) return 1;
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ctx->nl.n_img == 0 || ctx->nl.ntot == 0) return chefsi_fail(ctx, "nloc_project: no projectors on this context");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->alpha_reduce_min = -1; /* this context always keeps per-atom sums */
+    int n = launch_nloc(ctx, NLOC_PROJECT, const_cast<double *>(x), ctx->ld, ncol, 0.0, false);
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    n = launch_alpha_reduce(ctx, ncol, false);
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    CHEFSI_CUDA(ctx, cudaMemcpyAsync(alpha_out, ctx->d_alpha_sum, sizeof(double) * (size_t)ctx->nl.ntot * ncol,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" int chefsi_nloc_expand_device(chefsi_ctx_t *ctx, double *out, int ncol, double scale, const double *alpha_in)
+{
+    if (!ctx || !alpha_in) return 1;
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ctx->nl.n_img == 0 || ctx->nl.ntot == 0) return chefsi_fail(ctx, "nloc_expand: no projectors on this context");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->alpha_reduce_min = -1;
+    if (nloc_ensure_alpha(ctx, ncol, false)) return 1;
+    CHEFSI_CUDA(ctx, cudaMemcpyAsync(ctx->d_alpha_sum, alpha_in, sizeof(double) * (size_t)ctx->nl.ntot * ncol,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->alpha_sum_external = 1; /* expand reads the buffer as it is */
+    const int n = launch_nloc(ctx, NLOC_EXPAND, out, ctx->ld, ncol, scale, false);
+    ctx->alpha_sum_external = 0;
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    return 0;
+}
+
 extern "C" int chefsi_set_profiling(chefsi_ctx_t *ctx, int on)
 {
     if (!ctx) return 1;

@@ -115,6 +115,7 @@ struct chefsi_ctx {
     size_t buf2_bytes = 0;
     size_t buf_bytes = 0;
     void *d_alpha[2] = {nullptr, nullptr}; /* per-image alpha partials: [cur] belongs to the current input */
+    int alpha_sum_external = 0;            /* 1: d_alpha_sum was produced by chefsi_nloc_project_device: expand must not rebuild it */
     int alpha_reduce_min = 8;              /* atoms with more alpha partials than this get them summed by alpha_reduce_kernel */
     size_t alpha_sum_bytes = 0;
     void *d_alpha_sum = nullptr;           /* per-atom sums of the partials (only when nl.max_parts is large) */
@@ -162,6 +163,8 @@ int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a);
 enum { NLOC_PROJECT = 0, NLOC_FUSED = 1, NLOC_EXPAND = 2 };
 int launch_nloc(chefsi_ctx *ctx, int mode, void *vec, size_t ld, int ncol, double scale, bool is_complex);
 int nloc_padded_nproj(int max_nproj);
+int launch_alpha_reduce(chefsi_ctx *ctx, int ncol, bool is_complex);
+int nloc_ensure_alpha(chefsi_ctx *ctx, int ncol, bool is_complex); /* (re)allocate the alpha buffers for ncol columns */
 
 int launch_nloc_halo_patch(chefsi_ctx *ctx, void *out, size_t ld, int ncol, bool is_complex);
 

@@ -432,6 +432,26 @@ static int ensure_alpha(chefsi_ctx *ctx, int ncol, int words)
     return 0;
 }
 
+int nloc_ensure_alpha(chefsi_ctx *ctx, int ncol, bool is_complex) { return ensure_alpha(ctx, ncol, is_complex ? 2 : 1); }
+
+/* per-atom sums of the current alpha partials into ctx->d_alpha_sum (see alpha_reduce_kernel) */
+int launch_alpha_reduce(chefsi_ctx *ctx, int ncol, bool is_complex)
+{
+    NlocDev &d = ctx->nl;
+    const int words = is_complex ? 2 : 1;
+    if (ensure_alpha(ctx, ncol, words)) return -1;
+    if (!ctx->d_alpha_sum) { chefsi_fail(ctx, "alpha reduce: no sum buffer"); return -1; }
+    NlocView v{};
+    v.IP_displ = d.IP_displ; v.img_aoff = d.img_aoff; v.atom_img_off = d.atom_img_off; v.atom_img = d.atom_img;
+    const size_t rowlen = (size_t)ncol * words;
+    const unsigned gx = (unsigned)std::min<size_t>(64, ((size_t)d.max_nproj * rowlen + 255) / 256);
+    alpha_reduce_kernel<<<dim3(gx ? gx : 1, (unsigned)d.n_atom), 256, 0, ctx->stream>>>(
+        v, reinterpret_cast<const double *>(ctx->d_alpha[ctx->alpha_cur]), (double *)ctx->d_alpha_sum, rowlen);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { chefsi_fail(ctx, "alpha reduce launch: %s", cudaGetErrorString(e)); return -1; }
+    return 1;
+}
+
 /* mode: NLOC_PROJECT  alpha(cur) = dV * phase * Chi^T vec                       (vec is read only)
  *       NLOC_FUSED    vec += scale * Chi Gamma alpha(cur); alpha(next) = proj(vec); cur <-> next
  *       NLOC_EXPAND   vec += scale * Chi Gamma alpha(cur)   (atomics when spheres overlap)            */
@@ -452,13 +472,11 @@ int launch_nloc(chefsi_ctx *ctx, int mode, void *vec, size_t ld, int ncol, doubl
     const double *aprev = reinterpret_cast<const double *>(ctx->d_alpha[ctx->alpha_cur]);
     int n_extra = 0;
     if (mode != NLOC_PROJECT && d.max_parts > ctx->alpha_reduce_min) { /* consumers read per-atom sums instead of looping over many partials */
-        const size_t rowlen = (size_t)ncol * words;
-        const unsigned gx = (unsigned)std::min<size_t>(64, ((size_t)d.max_nproj * rowlen + 255) / 256);
-        alpha_reduce_kernel<<<dim3(gx ? gx : 1, (unsigned)d.n_atom), 256, 0, ctx->stream>>>(v, aprev, (double *)ctx->d_alpha_sum, rowlen);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { chefsi_fail(ctx, "alpha reduce launch: %s", cudaGetErrorString(e)); return -1; }
+        if (!ctx->alpha_sum_external) {
+            n_extra = launch_alpha_reduce(ctx, ncol, is_complex);
+            if (n_extra < 0) return -1;
+        }
         v.alpha_sum = (const double *)ctx->d_alpha_sum;
-        n_extra = 1;
     }
     double *anext = reinterpret_cast<double *>(ctx->d_alpha[mode == NLOC_FUSED ? ctx->alpha_cur ^ 1 : ctx->alpha_cur]);
     double *p = reinterpret_cast<double *>(vec);
