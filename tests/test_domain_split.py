@@ -183,3 +183,34 @@ def test_gpu_building_blocks_two_slabs_one_device(case):
     for e in eng:
         e.close()
     assert _rel(Yg, Yw) < 1e-10
+
+
+def _nccl_worker(rank, world, port_no, out_dir, case):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from sparc_b200 import domain_split as DS
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    Y, X = _run_slab(lambda gl, vl, pl: DS.GpuSlabEngine(rank, gl, vl, pl), case, rank, world, None)
+    np.save(os.path.join(out_dir, f"y{rank}.npy"), Y)
+    np.save(os.path.join(out_dir, f"x{rank}.npy"), X)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(CASES))
+def test_gpu_two_ranks_nccl(tmp_path, case):
+    """One process per GPU, NCCL send/recv halo exchange + all-reduce of alpha (needs two visible GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port_no = 29700 + (os.getpid() % 200)
+    mp.spawn(_nccl_worker, args=(2, port_no, str(tmp_path), case), nprocs=2, join=True)
+    Yw, Xw = _want(case)
+    Y = np.concatenate([np.load(tmp_path / f"y{r}.npy") for r in range(2)], axis=1)
+    X = np.concatenate([np.load(tmp_path / f"x{r}.npy") for r in range(2)], axis=1)
+    assert _rel(Y, Yw) < 1e-10 and _rel(X, Xw) < 1e-10
