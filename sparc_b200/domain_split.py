@@ -152,7 +152,13 @@ class GpuSlabEngine:
             self.ctx.nloc_expand_device(out, out.shape[0], scale, alpha)
 
     def sync(self):
+        """Wait for the library's stream (its kernels) -- before torch / NCCL touch the blocks."""
         self.ctx.synchronize()
+
+    def fence(self):
+        """Wait for torch's streams (copies, NCCL) -- before the library's stream touches the blocks: the library
+        runs on its own non-blocking stream, which torch's stream semantics know nothing about."""
+        self.torch.cuda.synchronize(self.device)
 
     def close(self):
         self.ctx.close()
@@ -185,14 +191,15 @@ class DomainSplitFilter:
         prev, nxt = (self.rank - 1) % self.world, (self.rank + 1) % self.world
         has_prev = periodic or self.rank > 0
         has_next = periodic or self.rank < self.world - 1
+        self.e.sync()
         if self.world == 1:
             if periodic:
                 lo_halo.copy_(hi_own.clone())
                 hi_halo.copy_(lo_own.clone())
             else:
                 lo_halo.zero_(); hi_halo.zero_()
+            self.e.fence()
             return
-        self.e.sync()
         send_dn, send_up = lo_own.contiguous(), hi_own.contiguous()
         recv_hi, recv_lo = torch.empty_like(send_dn), torch.empty_like(send_up)
         ops = []
@@ -207,6 +214,7 @@ class DomainSplitFilter:
         else: hi_halo.zero_()
         if has_prev: lo_halo.copy_(recv_lo)
         else: lo_halo.zero_()
+        self.e.fence()
 
     def _alpha(self, x, alpha):
         import torch.distributed as dist
@@ -214,6 +222,7 @@ class DomainSplitFilter:
         if self.world > 1 and self.ntot:
             self.e.sync()
             dist.all_reduce(alpha, group=self.group)
+        self.e.fence()
 
     def ChebyshevFiltering(self, X, Y, W, m, a, b, a0):
         """Blocks X (input, destroyed), Y, W of the engine; returns (result block, block holding p_{m-1}(H)X0)."""
@@ -222,6 +231,7 @@ class DomainSplitFilter:
         sigma = sigma1 = e_ / (a0 - c)
         gamma = 2.0 / sigma1
         alpha = self.e.alpha_buffer(self.ntot, X.shape[0])
+        self.e.fence()
         self.exchange(X)
         self._alpha(X, alpha)
         self.e.stencil_step(X, None, Y, -c, sigma1 / e_, 0.0)

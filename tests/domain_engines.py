@@ -67,5 +67,8 @@ class OracleSlabEngine:
     def sync(self):
         pass
 
+    def fence(self):
+        pass
+
     def close(self):
         pass

@@ -150,6 +150,7 @@ def test_gpu_building_blocks_two_slabs_one_device(case):
             else: views[r][:, F + nzl:] = 0
             if per or r > 0: views[r][:, :F] = views[dn][:, nzd:nzd + F]
             else: views[r][:, :F] = 0
+        torch.cuda.synchronize()
 
     a, b, a0 = BOUNDS
     e_, c = 0.5 * (b - a), 0.5 * (b + a)
@@ -164,8 +165,10 @@ def test_gpu_building_blocks_two_slabs_one_device(case):
         tot = al[0] + al[1]
         for r in range(world):
             al[r].copy_(tot)
+        torch.cuda.synchronize()
 
     X, Y, W = 0, 1, 2
+    torch.cuda.synchronize()
     exchange(X); reduce_alpha(X)
     for r in range(world):
         eng[r].stencil_step(blk[r][X], None, blk[r][Y], -c, sigma1 / e_, 0.0)
