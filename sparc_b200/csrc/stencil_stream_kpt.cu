@@ -25,8 +25,11 @@
 #include <cuda.h>
 
 #include "chefsi_internal.h"
+#include "tma_ring.cuh"
 
 namespace {
+
+using namespace tma_ring;
 
 constexpr int R = 6;        /* FD radius (complex points) */
 constexpr int HT = 8;       /* top halo rows held in the tile (6 used) */
@@ -72,46 +75,6 @@ struct KptMaps {
     CUtensorMap y_full, y_top, y_body, y_bot, y_strip, xprev, veff;
 };
 
-/* ---- PTX helpers (see stencil_stream_dense.cu) -------------------------------------------------- */
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@p bra.uni WAIT_DONE;\n"
-        "bra.uni WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void stg128(double *p, double v0, double v1)
-{
-    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v0), "d"(v1) : "memory");
-}
-__device__ __forceinline__ int tile_origin(int t, int T, int N) { return min(t * T, N - T); }
 /* (re, im) * (pr + i pi) */
 __device__ __forceinline__ double2 cmul(double2 a, double pr, double pi)
 {
@@ -423,23 +386,6 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
 }
 
 /* ---- host side ---------------------------------------------------------------------------- */
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled get_encode()
-{
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-    }
-    return fn;
-}
-
 /* 4-D view (x in doubles, y, z, column) of a block of dense columns of `words` doubles per point (2: complex
  * orbitals, 1: the real Veff); elements outside the grid read as zero */
 bool make_map(CUtensorMap *map, const void *base, const Layout &L, int words, int ncol, int box_x, int box_y, int promo)
