@@ -6,6 +6,6 @@ for l in sys.stdin:
     elif 'rror' in l or 'Trace' in l: print(l.rstrip())
 "; }
 for rep in 1 2; do
-run gridsync1 CHEFSI_B200_GRIDSYNC=1
-run gridsync0 CHEFSI_B200_GRIDSYNC=0
+run barrier_on CHEFSI_B200_GRIDSYNC=2
+run barrier_off CHEFSI_B200_GRIDSYNC=1
 done

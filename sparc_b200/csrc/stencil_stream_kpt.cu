@@ -17,9 +17,9 @@
  *   - the haloed tile is 16 + 2*6 complex wide (58 doubles pitch); the x window of a point is 13 chunks per row;
  *   - periodic-x strips are 7 complex wide; Veff is a real tile (one double per point);
  *   - phases: the x strips and the wrapped y rows of a stage are multiplied by their face's phase in shared
- *     memory by the consumer threads (<= 4 chunks each + one named barrier per plane, tiles at a periodic face
- *     only); the planes beyond a periodic z face are multiplied when their centre values are read.  Interior tiles
- *     run the same instruction stream as the real kernel (with a 13-chunk x window).
+ *     memory by the three spare warps of the producer warpgroup, between the TMA completion and the hand-over to
+ *     the consumers; the planes beyond a periodic z face are multiplied when their centre values are read.  All
+ *     consumers run the same instruction stream as the real kernel (with a 13-chunk x window).
  * Because complex rows are always 16-byte aligned there is no parity restriction on Nx.
  */
 #include <cuda.h>
@@ -56,7 +56,7 @@ struct Cfg {
     static constexpr int CONSUMER_WARPS = 8;
     static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32; /* + producer warpgroup, see stencil_stream_dense.cu */
     static constexpr int PRODUCER_REGS = 40, CONSUMER_REGS = 232;
-    static constexpr size_t SMEM = (size_t)kStages * STAGE_BYTES + 2 * kStages * sizeof(unsigned long long);
+    static constexpr size_t SMEM = (size_t)kStages * STAGE_BYTES + 3 * kStages * sizeof(unsigned long long);
     static_assert((YP * HT * 8) % 128 == 0 && (YP * TY * 8) % 128 == 0, "box starts must be 128-byte aligned");
     static_assert(TY == 4 * CONSUMER_WARPS, "16 points x 4 rows per warp");
 };
@@ -83,26 +83,31 @@ __device__ __forceinline__ double2 cmul(double2 a, double pr, double pi)
 
 /* ---- Bloch phases of a freshly loaded stage -----------------------------------------------------
  * Every chunk of an x strip and of the 6 wrapped top / bottom rows was fetched from the other side of the cell:
- * the 256 consumer threads multiply them in place by the face's phase (<= 4 chunks per thread), then meet at a
- * named barrier.  Only stages of tiles at a periodic face do this; interior tiles skip it. */
+ * the three spare warps of the producer warpgroup multiply them in place by the face's phase between the TMA
+ * completion (`landed` barrier) and the hand-over to the consumers (`full` barrier), a few planes ahead of them;
+ * the consumers of boundary and interior tiles run the same instruction stream. */
 __device__ __forceinline__ void fix_chunk(unsigned char *p, double pr, double pi)
 {
     double2 *q = reinterpret_cast<double2 *>(p);
     *q = cmul(*q, pr, pi);
 }
-__device__ __forceinline__ void fix_phases(const KptDesc &d, unsigned char *stage, int ct, bool need_l, bool need_r,
-                                           bool wrap_top, bool wrap_bot)
+__device__ __forceinline__ void fix_phases(const KptDesc &d, unsigned char *stage, int ft, int nthreads, bool need_l,
+                                           bool need_r, bool wrap_top, bool wrap_bot)
 {
-    if (ct < SWC * TY) {
-        const int row = ct / SWC, col = ct % SWC;
-        if (need_l) fix_chunk(stage + Cfg::OFF_L + (row * Cfg::SP + 2 * col) * 8, d.phm_re[0], d.phm_im[0]);
-        if (need_r) fix_chunk(stage + Cfg::OFF_R + (row * Cfg::SP + 2 * col) * 8, d.php_re[0], d.php_im[0]);
+    if (need_l || need_r) {
+        for (int c = ft; c < SWC * TY; c += nthreads) {
+            const int row = c / SWC, col = c % SWC;
+            if (need_l) fix_chunk(stage + Cfg::OFF_L + (row * Cfg::SP + 2 * col) * 8, d.phm_re[0], d.phm_im[0]);
+            if (need_r) fix_chunk(stage + Cfg::OFF_R + (row * Cfg::SP + 2 * col) * 8, d.php_re[0], d.php_im[0]);
+        }
     }
     constexpr int CPR = Cfg::YP / 2; /* chunks per tile row */
-    if (ct < R * CPR) {
-        const int row = ct / CPR, col = ct % CPR;
-        if (wrap_top) fix_chunk(stage + ((HT - R + row) * Cfg::YP + 2 * col) * 8, d.phm_re[1], d.phm_im[1]);
-        if (wrap_bot) fix_chunk(stage + ((HT + TY + row) * Cfg::YP + 2 * col) * 8, d.php_re[1], d.php_im[1]);
+    if (wrap_top || wrap_bot) {
+        for (int c = ft; c < R * CPR; c += nthreads) {
+            const int row = c / CPR, col = c % CPR;
+            if (wrap_top) fix_chunk(stage + ((HT - R + row) * Cfg::YP + 2 * col) * 8, d.phm_re[1], d.phm_im[1]);
+            if (wrap_bot) fix_chunk(stage + ((HT + TY + row) * Cfg::YP + 2 * col) * 8, d.php_re[1], d.php_im[1]);
+        }
     }
 }
 
@@ -236,11 +241,13 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
     unsigned char *ring = smem_raw;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kStages * Cfg::STAGE_BYTES);
     uint64_t *empty = full + kStages;
+    uint64_t *landed = empty + kStages; /* TMA completion; the fix-up warps turn it into `full` */
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full[s], 1);
+            mbar_init(&landed[s], 1);
             mbar_init(&empty[s], Cfg::CONSUMER_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -288,23 +295,48 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
                     const int s = it % kStages;
                     unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
                     mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
-                    mbar_expect_tx(&full[s], (need_y ? ybytes : 0u) + (uint32_t)((need_v ? Cfg::VP * TY * 8 : 0) +
+                    mbar_expect_tx(&landed[s], (need_y ? ybytes : 0u) + (uint32_t)((need_v ? Cfg::VP * TY * 8 : 0) +
                                                                                 (need_x ? Cfg::XP * TY * 8 : 0)));
                     const int xd = 2 * (x0 - R); /* x coordinates of the complex maps are in doubles */
                     if (need_y) {
                         if (!split_y) {
-                            tma_load_4d(stage, &maps.y_full, xd, y0 - HT, kz, n, &full[s]);
+                            tma_load_4d(stage, &maps.y_full, xd, y0 - HT, kz, n, &landed[s]);
                         } else {
-                            tma_load_4d(stage, &maps.y_top, xd, ytop, kz, n, &full[s]);
-                            tma_load_4d(stage + Cfg::YP * HT * 8, &maps.y_body, xd, y0, kz, n, &full[s]);
-                            tma_load_4d(stage + Cfg::YP * (HT + TY) * 8, &maps.y_bot, xd, ybot, kz, n, &full[s]);
+                            tma_load_4d(stage, &maps.y_top, xd, ytop, kz, n, &landed[s]);
+                            tma_load_4d(stage + Cfg::YP * HT * 8, &maps.y_body, xd, y0, kz, n, &landed[s]);
+                            tma_load_4d(stage + Cfg::YP * (HT + TY) * 8, &maps.y_bot, xd, ybot, kz, n, &landed[s]);
                         }
-                        if (need_l) tma_load_4d(stage + Cfg::OFF_L, &maps.y_strip, 2 * (Nx - SWC), y0, kz, n, &full[s]);
-                        if (need_r) tma_load_4d(stage + Cfg::OFF_R, &maps.y_strip, 0, y0, kz, n, &full[s]);
+                        if (need_l) tma_load_4d(stage + Cfg::OFF_L, &maps.y_strip, 2 * (Nx - SWC), y0, kz, n, &landed[s]);
+                        if (need_r) tma_load_4d(stage + Cfg::OFF_R, &maps.y_strip, 0, y0, kz, n, &landed[s]);
                     }
-                    if (need_v) tma_load_4d(stage + Cfg::OFF_V, &maps.veff, x0, y0, p, 0, &full[s]);
-                    if (need_x) tma_load_4d(stage + Cfg::OFF_X, &maps.xprev, 2 * x0, y0, o, n, &full[s]);
+                    if (need_v) tma_load_4d(stage + Cfg::OFF_V, &maps.veff, x0, y0, p, 0, &landed[s]);
+                    if (need_x) tma_load_4d(stage + Cfg::OFF_X, &maps.xprev, 2 * x0, y0, o, n, &landed[s]);
                     it++;
+                }
+            }
+        } else if (warp > Cfg::CONSUMER_WARPS) {
+            /* ---- fix-up warps: same (item, plane) sequence as the producer lane ---- */
+            const int ft = (int)threadIdx.x - (Cfg::CONSUMER_WARPS + 1) * 32; /* 0 .. 95 */
+            uint32_t itf = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int tile = item % (d.ntx * d.nty);
+                const int x0 = tile_origin(tile % d.ntx, TXC, Nx), y0 = tile_origin(tile / d.ntx, TY, Ny);
+                const bool wrap_top = yper && (y0 - R < 0), wrap_bot = yper && (y0 + TY + R > Ny);
+                const bool need_l = xper && (x0 - R < 0), need_r = xper && (x0 + TXC + R > Nx);
+                const bool fix_any = wrap_top || wrap_bot || need_l || need_r;
+                for (int p = -R; p < Nz + R; p++) {
+                    const bool interior = (p >= 0 && p < Nz);
+                    const int o = p - R;
+                    const bool need_y = interior || zper;
+                    const bool need_x = (o >= 0 && o < Nz) && a.s2 != 0.0;
+                    if (!need_y && !need_x) continue;
+                    const int s = itf % kStages;
+                    unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
+                    mbar_wait(&landed[s], (itf / kStages) & 1);
+                    if (fix_any && need_y) fix_phases(d, stage, ft, 96, need_l, need_r, wrap_top, wrap_bot);
+                    asm volatile("bar.sync 2, 96;" ::: "memory");
+                    if (ft == 0) mbar_arrive(&full[s]);
+                    itf++;
                 }
             }
         }
@@ -325,10 +357,6 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
             const bool active = act1;
             double *out_row = reinterpret_cast<double *>(a.out) + 2 * ((size_t)n * a.ld + (size_t)gy * Nx + gx);
             /* byte offsets (inside a stage) of the chunks x-6..x-1, x+1..x+6 of the first row */
-            /* which pieces of this tile's planes come from across a periodic face (as in the producer) */
-            const bool wrap_top = yper && (y0 - R < 0), wrap_bot = yper && (y0 + TY + R > Ny);
-            const bool need_l = xper && (x0 - R < 0), need_r = xper && (x0 + TXC + R > Nx);
-            const bool fix_any = wrap_top || wrap_bot || need_l || need_r;
             int xo[12];
             unsigned xmask = 0;
 #pragma unroll
@@ -358,10 +386,6 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
             s = it % kStages;                                                                            \
             stage = ring + (size_t)s * Cfg::STAGE_BYTES;                                                 \
             mbar_wait(&full[s], (it / kStages) & 1);                                                     \
-        }                                                                                                \
-        if (fix_any && !zplane) {                                                                        \
-            fix_phases(d, const_cast<unsigned char *>(stage), (int)threadIdx.x, need_l, need_r, wrap_top, wrap_bot); \
-            asm volatile("bar.sync 1, 256;" ::: "memory");                                               \
         }                                                                                                \
         consume_plane<(U)>(d, a, stage, pp, active, act0, act1, xp, r0, xo, xmask, out_row,               \
                            plane_doubles, in, acc, zplane);                                              \
@@ -456,10 +480,7 @@ int launch_stencil_stream_kpt(chefsi_ctx *ctx, const StepArgs &a)
     const int grid = (int)((nitems < ctx->num_sms) ? nitems : ctx->num_sms);
     unsigned int *counter = nullptr;
     unsigned int base = 0;
-    /* The round barrier is off by default here (CHEFSI_B200_GRIDSYNC=2 turns it on): tiles at a periodic face do
-       extra work (phase fix-up), so waiting for the slowest CTA of every round costs more than the L2 hits of the
-       xy-halos bring (measured 4.65 -> 4.1-4.4 ms per 64-column launch, profiles/r1_exp_kpt_stream.log) */
-    if (ctx->stream_gridsync >= 2 && nitems > grid) {
+    if (ctx->stream_gridsync && nitems > grid) { /* round barrier between the producers, as in the real kernel */
         if (!ctx->d_sync) {
             if (cudaMalloc((void **)&ctx->d_sync, 256) != cudaSuccess || cudaMemset(ctx->d_sync, 0, 256) != cudaSuccess) {
                 chefsi_fail(ctx, "k-point stream kernel: cannot allocate the round-barrier counter");
