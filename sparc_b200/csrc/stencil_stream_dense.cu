@@ -63,7 +63,7 @@ template <int WX, int WY> struct TileCfg {
        their registers back (168 -> 40) and the consumers grow to 232 */
     static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
     static constexpr int PRODUCER_REGS = 40, CONSUMER_REGS = 232;
-    static constexpr size_t SMEM = (size_t)kStages * STAGE_BYTES + 2 * kStages * sizeof(unsigned long long);
+    static constexpr size_t SMEM = (size_t)kStages * STAGE_BYTES + 3 * kStages * sizeof(unsigned long long);
     static_assert((YP / 2) % 2 == 1 && (XP / 2) % 2 == 1, "row pitches must be an odd number of 16-byte chunks");
     static_assert((YP * HT * 8) % 128 == 0 && (YP * TY * 8) % 128 == 0, "box starts must be 128-byte aligned");
 };
@@ -193,7 +193,7 @@ __device__ __forceinline__ void consume_plane(const DenseDesc &d, const StepArgs
  * halo row serves both output rows) and 2 + 2 chunks of Veff / xprev: 30 LDS.128 per 4 points instead of
  * the 36 of the 1 x 4 mapping.  A quarter warp reads 8 consecutive chunks of one row: conflict free for
  * any pitch.  xmask bit q set: chunk q of the x window lies in a periodic-x strip (row pitch SW).      */
-template <class Cfg, int U>
+template <class Cfg, int U, bool MERGED>
 __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepArgs &a, const unsigned char *stage, int p,
                                                 bool active, bool act0, bool act1, int xp, int r0, const int (&xo)[6],
                                                 unsigned xmask, double *__restrict__ out_row, size_t plane_elems,
@@ -215,9 +215,9 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
 #pragma unroll
             for (int t = 0; t < 7; t++) {
                 double2 w0, w1;
-                if (t == 3) {
-                    w0 = *reinterpret_cast<const double2 *>(cp);
-                    w1 = *reinterpret_cast<const double2 *>(cp + Cfg::YP);
+                if (t == 3 || MERGED) { /* MERGED: the strips were copied into the tile's halo columns */
+                    w0 = *reinterpret_cast<const double2 *>(cp + 2 * (t - 3));
+                    w1 = *reinterpret_cast<const double2 *>(cp + 2 * (t - 3) + Cfg::YP);
                 } else {
                     const int q = t < 3 ? t : t - 1;
                     const int off0 = xo[q];
@@ -318,11 +318,13 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
     unsigned char *ring = smem_raw;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kStages * Cfg::STAGE_BYTES);
     uint64_t *empty = full + kStages;
+    uint64_t *landed = empty + kStages; /* VAR 3: TMA completion; the merge warps turn it into `full` */
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full[s], 1);
+            mbar_init(&landed[s], 1);
             mbar_init(&empty[s], Cfg::CONSUMER_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -337,6 +339,7 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
     if (warp >= Cfg::CONSUMER_WARPS) {
         /* ================= producer warpgroup (one elected lane issues the TMA boxes) ================= */
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::PRODUCER_REGS));
+        uint64_t *tb = (VAR == 3) ? landed : full; /* barrier the TMA boxes of a stage complete on */
         if (warp == Cfg::CONSUMER_WARPS && lane == 0) {
             unsigned int round = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, round++) {
@@ -372,22 +375,65 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
                     const int s = it % kStages;
                     unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
                     mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
-                    mbar_expect_tx(&full[s], (need_y ? ybytes : 0u) + (uint32_t)((need_v ? Cfg::XP * Cfg::TY * 8 : 0) +
+                    mbar_expect_tx(&tb[s], (need_y ? ybytes : 0u) + (uint32_t)((need_v ? Cfg::XP * Cfg::TY * 8 : 0) +
                                                                                 (need_x ? Cfg::XP * Cfg::TY * 8 : 0)));
                     if (need_y) {
                         if (!split_y) {
-                            tma_load_4d(stage, &maps.y_full, x0 - R, y0 - HT, kz, n, &full[s]);
+                            tma_load_4d(stage, &maps.y_full, x0 - R, y0 - HT, kz, n, &tb[s]);
                         } else {
-                            tma_load_4d(stage, &maps.y_top, x0 - R, ytop, kz, n, &full[s]);
-                            tma_load_4d(stage + Cfg::YP * HT * 8, &maps.y_body, x0 - R, y0, kz, n, &full[s]);
-                            tma_load_4d(stage + Cfg::YP * (HT + Cfg::TY) * 8, &maps.y_bot, x0 - R, ybot, kz, n, &full[s]);
+                            tma_load_4d(stage, &maps.y_top, x0 - R, ytop, kz, n, &tb[s]);
+                            tma_load_4d(stage + Cfg::YP * HT * 8, &maps.y_body, x0 - R, y0, kz, n, &tb[s]);
+                            tma_load_4d(stage + Cfg::YP * (HT + Cfg::TY) * 8, &maps.y_bot, x0 - R, ybot, kz, n, &tb[s]);
                         }
-                        if (need_l) tma_load_4d(stage + Cfg::OFF_L, &maps.y_strip, Nx - SW, y0, kz, n, &full[s]);
-                        if (need_r) tma_load_4d(stage + Cfg::OFF_R, &maps.y_strip, 0, y0, kz, n, &full[s]);
+                        if (need_l) tma_load_4d(stage + Cfg::OFF_L, &maps.y_strip, Nx - SW, y0, kz, n, &tb[s]);
+                        if (need_r) tma_load_4d(stage + Cfg::OFF_R, &maps.y_strip, 0, y0, kz, n, &tb[s]);
                     }
-                    if (need_v) tma_load_4d(stage + Cfg::OFF_V, &maps.veff, x0, y0, p, 0, &full[s]);
-                    if (need_x) tma_load_4d(stage + Cfg::OFF_X, &maps.xprev, x0, y0, o, n, &full[s]);
+                    if (need_v) tma_load_4d(stage + Cfg::OFF_V, &maps.veff, x0, y0, p, 0, &tb[s]);
+                    if (need_x) tma_load_4d(stage + Cfg::OFF_X, &maps.xprev, x0, y0, o, n, &tb[s]);
                     it++;
+                }
+            }
+        } else if (VAR == 3 && warp > Cfg::CONSUMER_WARPS) {
+            /* ---- merge warps (the three spare warps of the producer warpgroup): same (item, plane) sequence as the
+               producer lane; they copy the periodic-x strips of a landed stage into the zero-filled halo columns of
+               its tile, so that the consumers read every x window with constant offsets ---- */
+            const int ft = (int)threadIdx.x - (Cfg::CONSUMER_WARPS + 1) * 32; /* 0 .. 95 */
+            uint32_t itf = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int tile = item % (d.ntx * d.nty);
+                const int x0 = tile_origin(tile % d.ntx, Cfg::TX, Nx);
+                const bool need_l = xper && (x0 - R < 0), need_r = xper && (x0 + Cfg::TX + R > Nx);
+                for (int p = -R; p < Nz + R; p++) {
+                    const bool interior = (p >= 0 && p < Nz);
+                    const int o = p - R;
+                    const bool need_y = interior || zper;
+                    const bool need_x = (o >= 0 && o < Nz) && a.s2 != 0.0;
+                    if (!need_y && !need_x) continue;
+                    const int s = itf % kStages;
+                    unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
+                    mbar_wait(&landed[s], (itf / kStages) & 1);
+                    if (need_y && (need_l || need_r)) {
+                        double *tile_d = reinterpret_cast<double *>(stage);
+                        const double *sl = reinterpret_cast<const double *>(stage + Cfg::OFF_L);
+                        const double *sr = reinterpret_cast<const double *>(stage + Cfg::OFF_R);
+                        if (need_l)
+                            for (int c = ft; c < 3 * Cfg::TY; c += 96) {
+                                const int row = c / 3, j = c % 3, gi = x0 - R + 2 * j;
+                                if (gi < 0)
+                                    *reinterpret_cast<double2 *>(tile_d + (HT + row) * Cfg::YP + 2 * j) =
+                                        *reinterpret_cast<const double2 *>(sl + row * SW + gi + SW);
+                            }
+                        if (need_r)
+                            for (int c = ft; c < 4 * Cfg::TY; c += 96) {
+                                const int row = c / 4, j = c % 4, col = Nx + 2 * j - (x0 - R);
+                                if (col + 1 < Cfg::YP)
+                                    *reinterpret_cast<double2 *>(tile_d + (HT + row) * Cfg::YP + col) =
+                                        *reinterpret_cast<const double2 *>(sr + row * SW + 2 * j);
+                            }
+                    }
+                    asm volatile("bar.sync 2, 96;" ::: "memory");
+                    if (ft == 0) mbar_arrive(&full[s]);
+                    itf++;
                 }
             }
         }
@@ -451,8 +497,8 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
         if (VAR == 0)                                                                                    \
             consume_plane<Cfg, (U)>(d, a, stage, pp, active, qx, ry, xo, out_row, plane_elems, in, acc, zplane); \
         else                                                                                             \
-            consume_plane22<Cfg, (U)>(d, a, stage, pp, active, act0, act1, qx, ry, xo, xmask, out_row,    \
-                                      plane_elems, in, acc, zplane);                                     \
+            consume_plane22<Cfg, (U), VAR == 3>(d, a, stage, pp, active, act0, act1, qx, ry, xo, xmask, out_row, \
+                                                plane_elems, in, acc, zplane);                           \
         if (use_stage) {                                                                                 \
             __syncwarp();                                                                                \
             if (lane == 0) mbar_arrive(&empty[s]);                                                       \
@@ -503,7 +549,7 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
     d.nty = (g.Ny + Cfg::TY - 1) / Cfg::TY;
     d.coef0 = ctx->desc.coef0;
     for (int r = 0; r <= R; r++) { d.wx[r] = ctx->desc.wx[r]; d.wy[r] = ctx->desc.wy[r]; d.wz[r] = ctx->desc.wz[r]; }
-    if (VAR == 1) { /* the 2 x 2 mapping applies s1 (and c) through the weights: out = (s1 H') x - s2 xprev */
+    if (VAR >= 1) { /* the 2 x 2 mapping applies s1 (and c) through the weights: out = (s1 H') x - s2 xprev */
         d.coef0 = a.s1 * (d.coef0 + a.c);
         for (int r = 0; r <= R; r++) { d.wx[r] *= a.s1; d.wy[r] *= a.s1; d.wz[r] *= a.s1; }
     }
@@ -579,5 +625,6 @@ int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a)
 {
     if (a.ncol <= 0) return 0;
     if (ctx->stream_variant == 0) return launch_cfg<2, 4, 0>(ctx, a);
-    return launch_cfg<2, 4, 1>(ctx, a);
+    if (ctx->stream_variant == 1) return launch_cfg<2, 4, 1>(ctx, a);
+    return launch_cfg<2, 4, 3>(ctx, a);
 }

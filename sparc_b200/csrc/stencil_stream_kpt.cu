@@ -91,14 +91,28 @@ __device__ __forceinline__ void fix_chunk(unsigned char *p, double pr, double pi
     double2 *q = reinterpret_cast<double2 *>(p);
     *q = cmul(*q, pr, pi);
 }
-__device__ __forceinline__ void fix_phases(const KptDesc &d, unsigned char *stage, int ft, int nthreads, bool need_l,
-                                           bool need_r, bool wrap_top, bool wrap_bot)
+__device__ __forceinline__ void fix_phases(const KptDesc &d, unsigned char *stage, int ft, int nthreads, int x0,
+                                           bool need_l, bool need_r, bool wrap_top, bool wrap_bot)
 {
-    if (need_l || need_r) {
-        for (int c = ft; c < SWC * TY; c += nthreads) {
-            const int row = c / SWC, col = c % SWC;
-            if (need_l) fix_chunk(stage + Cfg::OFF_L + (row * Cfg::SP + 2 * col) * 8, d.phm_re[0], d.phm_im[0]);
-            if (need_r) fix_chunk(stage + Cfg::OFF_R + (row * Cfg::SP + 2 * col) * 8, d.php_re[0], d.php_im[0]);
+    /* x strips: multiplied by the face's phase and written into the (zero-filled) halo columns of the tile, so that
+       the consumers read every x window with constant offsets */
+    double *tile = reinterpret_cast<double *>(stage);
+    if (need_l) {
+        const double *sl = reinterpret_cast<const double *>(stage + Cfg::OFF_L);
+        for (int c = ft; c < R * TY; c += nthreads) {
+            const int row = c / R, j = c % R, gi = x0 - R + j; /* tile chunk j <-> complex point gi */
+            if (gi < 0)
+                *reinterpret_cast<double2 *>(tile + (HT + row) * Cfg::YP + 2 * j) =
+                    cmul(*reinterpret_cast<const double2 *>(sl + row * Cfg::SP + 2 * (gi + SWC)), d.phm_re[0], d.phm_im[0]);
+        }
+    }
+    if (need_r) {
+        const double *sr = reinterpret_cast<const double *>(stage + Cfg::OFF_R);
+        for (int c = ft; c < R * TY; c += nthreads) {
+            const int row = c / R, j = c % R, col = d.Nx + j - (x0 - R); /* tile chunk of complex point Nx + j */
+            if (col < Cfg::YP / 2)
+                *reinterpret_cast<double2 *>(tile + (HT + row) * Cfg::YP + 2 * col) =
+                    cmul(*reinterpret_cast<const double2 *>(sr + row * Cfg::SP + 2 * j), d.php_re[0], d.php_im[0]);
         }
     }
     constexpr int CPR = Cfg::YP / 2; /* chunks per tile row */
@@ -114,12 +128,12 @@ __device__ __forceinline__ void fix_phases(const KptDesc &d, unsigned char *stag
 /* ---- one plane step of a consumer thread -------------------------------------------------------
  * The thread owns the complex point xp of rows r0 and r0 + 1; value index = 2 * row + (0: re, 1: im).
  * U = (p + 7) mod 7 (compile time): register-queue rotation by renaming.
- * xmask bit q: chunk q of the x window (0..5 left of the point, 6..11 right) comes from a periodic-x strip.
- * The Bloch phases of strips and wrapped y rows have been applied in shared memory (fix_phases) by now. */
+ * The periodic-x strips (phase applied) have been merged into the tile and the wrapped y rows multiplied by their
+ * phase in shared memory (fix_phases) by now: every window is read with constant offsets. */
 template <int U>
 __device__ __forceinline__ void consume_plane(const KptDesc &d, const StepArgs &a, const unsigned char *stage, int p,
-                                              bool active, bool act0, bool act1, int xp, int r0, const int (&xo)[12],
-                                              unsigned xmask, double *__restrict__ out_row,
+                                              bool active, bool act0, bool act1, int xp, int r0,
+                                              double *__restrict__ out_row,
                                               size_t plane_doubles, double (&in)[7][4], double (&acc)[7][4],
                                               bool plane_is_zero)
 {
@@ -154,13 +168,7 @@ __device__ __forceinline__ void consume_plane(const KptDesc &d, const StepArgs &
                 double2 w[13];
 #pragma unroll
                 for (int t = 0; t < 13; t++) {
-                    if (t == 6) {
-                        w[t] = *reinterpret_cast<const double2 *>(cp + row * Cfg::YP);
-                    } else {
-                        const int q = t < 6 ? t : t - 1;
-                        const int off = xo[q] + (row ? (((xmask >> q) & 1u) ? Cfg::SP * 8 : Cfg::YP * 8) : 0);
-                        w[t] = *reinterpret_cast<const double2 *>(stage + off);
-                    }
+                    w[t] = *reinterpret_cast<const double2 *>(cp + row * Cfg::YP + 2 * (t - 6));
                 }
                 v[2 * row] = w[6].x;
                 v[2 * row + 1] = w[6].y;
@@ -333,7 +341,7 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
                     const int s = itf % kStages;
                     unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
                     mbar_wait(&landed[s], (itf / kStages) & 1);
-                    if (fix_any && need_y) fix_phases(d, stage, ft, 96, need_l, need_r, wrap_top, wrap_bot);
+                    if (fix_any && need_y) fix_phases(d, stage, ft, 96, x0, need_l, need_r, wrap_top, wrap_bot);
                     asm volatile("bar.sync 2, 96;" ::: "memory");
                     if (ft == 0) mbar_arrive(&full[s]);
                     itf++;
@@ -356,20 +364,6 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
             const bool act1 = (gx >= tx * TXC) && (gy + 1 >= ty * TY);
             const bool active = act1;
             double *out_row = reinterpret_cast<double *>(a.out) + 2 * ((size_t)n * a.ld + (size_t)gy * Nx + gx);
-            /* byte offsets (inside a stage) of the chunks x-6..x-1, x+1..x+6 of the first row */
-            int xo[12];
-            unsigned xmask = 0;
-#pragma unroll
-            for (int q = 0; q < 12; q++) {
-                const int t = q < 6 ? q : q + 1;
-                const int gi = gx - R + t;
-                int off = ((r0 + HT) * Cfg::YP + 2 * xp + 2 * t) * 8;
-                if (xper) {
-                    if (gi < 0) { off = Cfg::OFF_L + (r0 * Cfg::SP + 2 * (gi + SWC)) * 8; xmask |= 1u << q; }
-                    else if (gi >= Nx) { off = Cfg::OFF_R + (r0 * Cfg::SP + 2 * (gi - Nx)) * 8; xmask |= 1u << q; }
-                }
-                xo[q] = off;
-            }
 #pragma unroll
             for (int u = 0; u < 7; u++)
 #pragma unroll
@@ -387,7 +381,7 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
             stage = ring + (size_t)s * Cfg::STAGE_BYTES;                                                 \
             mbar_wait(&full[s], (it / kStages) & 1);                                                     \
         }                                                                                                \
-        consume_plane<(U)>(d, a, stage, pp, active, act0, act1, xp, r0, xo, xmask, out_row,               \
+        consume_plane<(U)>(d, a, stage, pp, active, act0, act1, xp, r0, out_row,                          \
                            plane_doubles, in, acc, zplane);                                              \
         if (use_stage) {                                                                                 \
             __syncwarp();                                                                                \

@@ -155,7 +155,7 @@ def test_stream_kernel_vs_oracle(ctx_padded, port, N, BC):
     assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
 
 
-@pytest.fixture(scope="module", params=[1, 0], ids=["map2x2", "map1x4"])
+@pytest.fixture(scope="module", params=[3, 1, 0], ids=["map2x2_merged", "map2x2", "map1x4"])
 def ctx_dense(request):
     """Context on the dense (reference) column layout: stencil_stream_dense.cu, both thread mappings
     (2 x 2 points per thread = the default, 1 x 4 = the first version)."""
