@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 METRIC = "chebyshev_filter_gridpt_vectors_per_s"
 UNIT = "grid-pt*vectors/s"
 # DRAM bytes of one 128-column launch of the dense streaming kernel on the 160^3 grid (ncu capture, profiles/)
-NCU_TRAFFIC_BYTES = 13.80e9
+NCU_TRAFFIC_BYTES = 13.78e9
 
 
 def parse_args():
@@ -324,7 +324,7 @@ def run_ours(args):
     roofline = {
         "bound": "hbm", "kernel": ("stream_kpt_kernel" if cplx else "stream_dense_kernel" if os.environ.get("CHEFSI_B200_DENSE", "1") != "0" else "stream_orth_kernel") + " (fused stencil + Veff + recurrence)" if ctx.stats()["last_path"] == 1 else ("stencil_zmarch_kernel" if ctx.stats()["last_path"] == 2 else "stencil_general_kernel"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if (args.grid == 160 and block == 128 and ctx.stats()["last_path"] == 1 and os.environ.get("CHEFSI_B200_DENSE", "1") != "0") else None,
-        "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 128-column launch (profiles/r1_ncu_dense_map2x2.txt)",
+        "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 128-column launch (profiles/r1_ncu_dense_final.txt: 9.61 GB read + 4.17 GB write)",
         "peak_source": peak_src, "avg_launch_ms": st_ms / st_n if st_n else None,
         "algorithmic_bytes_per_launch": 8.0 * words * (3 * m - 1) * g.Nd * block / m,
         "timing": "per-launch CUDA events over one full step run back to back with the timed steps (sustained clocks)",
