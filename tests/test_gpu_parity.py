@@ -177,7 +177,8 @@ def ctx_dense(request):
                                    ((96, 96, 13), (0, 0, 0)), ((32, 32, 16), (1, 0, 1)), ((64, 32, 16), (0, 1, 0)),
                                    ((32, 64, 12), (1, 1, 1)), ((40, 70, 12), (0, 0, 1)), ((68, 36, 12), (0, 1, 0)),
                                    ((40, 39, 12), (0, 0, 0)), ((44, 37, 14), (0, 1, 0)),
-                                   ((38, 40, 12), (0, 0, 0)), ((70, 33, 12), (1, 1, 0))])
+                                   ((38, 40, 12), (0, 0, 0)), ((70, 33, 12), (1, 1, 0)),
+                                   ((34, 32, 12), (0, 0, 0)), ((36, 64, 12), (0, 0, 1))])
 def test_dense_stream_kernel_vs_oracle(ctx_dense, port, N, BC):
     """Dense-layout streaming kernel: single tiles that wrap on both sides, shifted (overlapping) last
     tiles, interior tiles (one TMA box), periodic-x strips, split periodic-y boxes, Dirichlet faces
