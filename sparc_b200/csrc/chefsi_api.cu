@@ -720,7 +720,10 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
         std::vector<int> sched;
         {
             const int q = chunk / 4, h = chunk / 2;
-            if (ncol >= 3 * chunk && q >= 8 && getenv("CHEFSI_B200_FLAT_CHUNKS") == nullptr) {
+            /* only for long pipelines: a chunk of < 32 columns costs the projector kernel as much as 32 (it works on
+               groups of 32 columns), so on a short block the ramp costs more than the copies it hides (measured at
+               128 columns per rank: 8.1e9 flat vs 5.7e9 ramped at N = 2) */
+            if (ncol >= 6 * chunk && q >= 8 && getenv("CHEFSI_B200_FLAT_CHUNKS") == nullptr) {
                 int rest = ncol - 2 * (q + h);
                 sched.push_back(q); sched.push_back(h);
                 while (rest > 0) { const int c1 = rest < chunk ? rest : chunk; sched.push_back(c1); rest -= c1; }
