@@ -335,7 +335,7 @@ def test_host_pipeline_ramped_chunks(port):
         c = ChefsiContext(0)
         g = P.make_grid((64, 64, 64), (28.8, 28.8, 28.8))
         veff = P.synthetic_veff(g)
-        x = P.random_columns(g.Nd, 100, seed=9)
+        x = P.random_columns(g.Nd, 200, seed=9)
         _setup(c, g, veff, None)
         a, b, a0 = P.chebyshev_bounds(g)
         X, Y = x.copy(), np.empty_like(x)
