@@ -48,4 +48,5 @@ def load_golden(name):
     return g, d["veff"].copy(), proj, d
 
 
-GOLDEN = ["orth_gamma", "orth_dirichlet_gamma", "si8lat_gamma", "orth_kpt", "si8lat_kpt", "type14_mixedbc_gamma"]
+GOLDEN = ["orth_gamma", "orth_dirichlet_gamma", "si8lat_gamma", "orth_kpt", "si8lat_kpt", "type14_mixedbc_gamma",
+          "stream_gamma", "stream_kpt"]

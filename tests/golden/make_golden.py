@@ -21,8 +21,14 @@ from oracle.bindings import Reference  # noqa: E402
 from sparc_b200 import problem as P  # noqa: E402
 from tests.cases import BOUNDS, KVEC, small_case  # noqa: E402
 
+# grids: the small one exercises the general kernels, the two "stream_*" ones are large enough for the TMA
+# streaming kernels (real: >= 32 x 32 x 12, k-point: >= 16 x 32 x 12), so those are pinned to reference-made
+# vectors as well and not only to the oracle restatement
+SMALL = ((12, 10, 14), (6.0, 5.2, 7.0))
 CASES = {
-    # name: (cell_typ, BC, complex, m)
+    # name: (cell_typ, BC, complex, m[, (N, L)])
+    "stream_gamma": (0, (0, 0, 0), False, 6, ((32, 32, 14), (16.0, 16.0, 7.0))),
+    "stream_kpt": (0, (0, 0, 0), True, 6, ((16, 32, 14), (8.0, 16.0, 7.0))),
     "orth_gamma": (0, (0, 0, 0), False, 8),
     "orth_dirichlet_gamma": (0, (1, 0, 1), False, 5),
     "si8lat_gamma": (17, (0, 0, 0), False, 8),
@@ -35,8 +41,13 @@ CASES = {
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     a, b, a0 = BOUNDS
-    for name, (ct, BC, cplx, m) in CASES.items():
-        g, veff, proj, x = small_case(ct, BC, N=(12, 10, 14), L=(6.0, 5.2, 7.0), ncol=2, complex_=cplx, seed=3)
+    only = set(sys.argv[1:])
+    for name, spec in CASES.items():
+        if only and name not in only:
+            continue
+        ct, BC, cplx, m = spec[:4]
+        N, L = spec[4] if len(spec) > 4 else SMALL
+        g, veff, proj, x = small_case(ct, BC, N=N, L=L, ncol=2, complex_=cplx, seed=3)
         ref = Reference(g, proj, veff, kvec=KVEC)
         Hx = ref.hamiltonian_mult(-0.25, x)
         Xo, Yo = ref.chebyshev_filter(x, m, a, b, a0)

@@ -60,6 +60,8 @@ def test_golden_vectors(ctx, name):
     ctx.ChebyshevFiltering(X, Y, int(d["m"]), a, b, a0)
     assert rel_fro(Y, d["Y_out"]) < TOL
     assert rel_fro(X, d["X_out"]) < TOL
+    if name.startswith("stream_"):  # the two fixtures sized for the TMA streaming kernels (real / k-point)
+        assert ctx.stats()["last_path"] == 1
 
 
 # ---------------------------------------------------------------- every cell type / BC vs the oracle
