@@ -83,7 +83,6 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
     if (getenv("CHEFSI_B200_DENSE")) ctx->dense_stream = atoi(getenv("CHEFSI_B200_DENSE"));
     if (getenv("CHEFSI_B200_STREAM_VARIANT")) ctx->stream_variant = atoi(getenv("CHEFSI_B200_STREAM_VARIANT"));
     if (getenv("CHEFSI_B200_ALPHA_REDUCE_MIN")) ctx->alpha_reduce_min = atoi(getenv("CHEFSI_B200_ALPHA_REDUCE_MIN"));
-    if (getenv("CHEFSI_B200_NLOC_SHAPE")) ctx->nloc_shape = atoi(getenv("CHEFSI_B200_NLOC_SHAPE"));
     if (getenv("CHEFSI_B200_TMA_L2PROMO")) ctx->tma_l2promo = atoi(getenv("CHEFSI_B200_TMA_L2PROMO")) & 3;
     *out = ctx;
     return 0;

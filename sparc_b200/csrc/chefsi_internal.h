@@ -132,7 +132,6 @@ struct chefsi_ctx {
     int tma_l2promo = 3;           /* CUtensorMapL2promotion of the streaming kernel's tensor maps */
     int dense_stream = 1;          /* 1: dense column layout + stencil_stream_dense.cu (default); 0: halo-padded layout */
     int stream_variant = 3;        /* dense streaming kernel: 0 = 1 x 4 points per thread, 1 = 2 x 2 points, 3 = 2 x 2 + periodic-x strips merged into the tile by the spare producer-group warps (default) */
-    int nloc_shape = 0;            /* pipeline shape of the fused projector kernel (nloc.cu: launch_mode) */
     unsigned int *d_sync = nullptr;
     unsigned int sync_arrivals = 0;
     char err[512] = {0};

@@ -369,18 +369,9 @@ template <int NP, int WORDS, int MODE>
 int launch_mode(chefsi_ctx *ctx, const NlocView &v, const double *aprev, double *anext, double *vec, size_t ld, int ncol,
                 double scale)
 {
-    /* pipeline shape: CHEFSI_B200_NLOC_SHAPE selects among the instantiated ones (default chosen by measurement,
-       profiles/r1_exp_nloc_shapes.log); only the FUSED mode (the one the filter runs per degree) has alternatives */
-    if (MODE == MODE_FUSED && WORDS == 1) {
-        switch (ctx->nloc_shape) {
-        case 1: return launch_shape<NP, WORDS, MODE, Shape<128, 2, 64>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
-        case 2: return launch_shape<NP, WORDS, MODE, Shape<256, 3, 64>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
-        case 3: return launch_shape<NP, WORDS, MODE, Shape<128, 3, 64>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
-        case 4: return launch_shape<NP, WORDS, MODE, Shape<128, 4, 32>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
-        case 5: return launch_shape<NP, WORDS, MODE, Shape<256, 2, 128>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
-        default: break;
-        }
-    }
+    /* pipeline shape: 256 threads, 2-stage ring of 64-point chunks.  128-thread CTAs, 3- and 4-stage rings and
+       128-point chunks were measured and are 3-30 % slower (profiles/r1_exp_nloc_shapes.log): the gather sits at
+       the HBM random-access rate, not at a latency the pipeline depth could hide. */
     return launch_shape<NP, WORDS, MODE, Shape<256, 2, 64>>(ctx, v, aprev, anext, vec, ld, ncol, scale);
 }
 
