@@ -28,8 +28,20 @@ if ROOT not in sys.path:
 
 METRIC = "chebyshev_filter_gridpt_vectors_per_s"
 UNIT = "grid-pt*vectors/s"
-# DRAM bytes of one 128-column launch of the dense streaming kernel on the 160^3 grid (ncu capture, profiles/)
-NCU_TRAFFIC_BYTES = 13.78e9
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from this round's
+# `ncu --set full` capture (scripts/ncu_traffic.py writes the file from the .ncu-rep; null when absent or when the
+# run's configuration differs from the captured one)
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+
+
+def ncu_traffic(kernel, grid, block):
+    try:
+        for e in json.load(open(NCU_TRAFFIC_FILE)):
+            if e["kernel"] == kernel and e["grid"] == grid and e["columns_per_launch"] == block:
+                return float(e["dram_bytes_per_launch"]), e["source"]
+    except Exception:
+        pass
+    return None, None
 
 
 def parse_args():
@@ -51,7 +63,9 @@ def parse_args():
     ap.add_argument("--cell-typ", type=int, default=0, help="lattice flavour (0 orthogonal; 11..17: problem.LATVEC_BY_CELL_TYP)")
     ap.add_argument("--no-veff", action="store_true", help="skip the local potential (experiment: cost of the Veff tile stream)")
     ap.add_argument("--e2e-cols", type=int, default=256)
-    ap.add_argument("--cpu-cols-per-core", type=int, default=1)
+    ap.add_argument("--cpu-cols-per-core", type=int, default=8,
+                    help="columns per host process of the CPU arm (>= 8 so the reference's Vnl dgemm is a GEMM, not a GEMV)")
+    ap.add_argument("--cpu-reps", type=int, default=1, help="repetitions of the cpu_baseline leg of the default arm (best of)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -131,31 +145,52 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+CPU_FIRST_COL = 100000  # global index of the first start vector the CPU arm filters (counter-based RNG: any block is reproducible)
+
+
 def _cpu_worker(job):
-    """One host process = one of the reference's band communicators (NP_BAND_PARAL = nproc,
-    domain unsplit): filter `ncols` columns with the reference's ChebyshevFiltering."""
-    (g, veff, proj, bounds, m, first_col, ncols, kind) = job
+    """One host process = one of the reference's band communicators (NP_BAND_PARAL = nproc, domain unsplit):
+    filter `ncols` columns with the reference's ChebyshevFiltering.  All processes start their filter together
+    (barrier), so they contend for the host's memory bandwidth exactly as ranks of one MPI job would.  Returns
+    (seconds inside the filter call, Y of the process's first column or None)."""
+    (g, veff, proj, bounds, m, first_col, ncols, kind, reps, want_y) = job
     from sparc_b200 import problem as P
     a, b, a0 = bounds
     x = P.random_columns(g.Nd, ncols, first_col=first_col, seed=1)
     if kind == "reference":
         from oracle.bindings import Reference
         ref = Reference(g, proj, veff)
+        run = lambda: ref.chebyshev_filter(x, m, a, b, a0)
+    else:
+        from oracle.bindings import Port
+        os.environ["OMP_NUM_THREADS"] = "1"
+        port = Port()
+        run = lambda: port.chebyshev_filter(g, proj, veff, x, m, a, b, a0)
+    times, y0 = [], None
+    for _ in range(reps):
+        _CPU_BARRIER.wait()
         t0 = time.perf_counter()
-        ref.chebyshev_filter(x, m, a, b, a0)
-        return time.perf_counter() - t0
-    from oracle.bindings import Port
-    os.environ["OMP_NUM_THREADS"] = "1"
-    port = Port()
-    t0 = time.perf_counter()
-    port.chebyshev_filter(g, proj, veff, x, m, a, b, a0)
-    return time.perf_counter() - t0
+        _, Y = run()
+        times.append(time.perf_counter() - t0)
+        if want_y:
+            y0 = Y[0].copy()
+        del Y
+    return times, y0
 
 
-def cpu_filter_rate(g, veff, proj, bounds, m, cols_per_core, reps=1):
-    """Throughput of the reference CPU path on this host: N = #cores independent processes, each
-    filtering `cols_per_core` columns (== the reference's NP_BAND_PARAL=N layout, which has zero
-    communication inside the filter).  Returns (rate, cores, kind, sample description)."""
+_CPU_BARRIER = None
+
+
+def _cpu_pool_init(barrier):
+    global _CPU_BARRIER
+    _CPU_BARRIER = barrier
+
+
+def cpu_filter_rate(g, veff, proj, bounds, m, cols_per_core, reps=1, want_y=False):
+    """Throughput of the reference CPU path on this host: N = #cores independent processes, each filtering
+    `cols_per_core` columns (== the reference's NP_BAND_PARAL = N layout, which has zero communication inside
+    the filter).  Time = max over the processes of the seconds inside their filter call,
+    best of `reps`.  Returns a dict (rate, cores, kind, sample, seconds per rep, first-column outputs)."""
     import multiprocessing as mp
     from oracle.bindings import build_port, reference_available
     kind = "reference" if reference_available() else "port"
@@ -163,50 +198,84 @@ def cpu_filter_rate(g, veff, proj, bounds, m, cols_per_core, reps=1):
         build_port()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cores = max(1, min(cores, int(os.environ.get("CHEFSI_BENCH_MAX_PROCS", "64"))))
-    jobs = [(g, veff, proj, bounds, m, 100000 + r * cols_per_core, cols_per_core, kind) for r in range(cores)]
     ctx = mp.get_context("fork")
-    best = None
-    with ctx.Pool(cores) as pool:
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            pool.map(_cpu_worker, jobs)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
+    barrier = ctx.Barrier(cores)
+    jobs = [(g, veff, proj, bounds, m, CPU_FIRST_COL + r * cols_per_core, cols_per_core, kind, reps, want_y)
+            for r in range(cores)]
+    with ctx.Pool(cores, initializer=_cpu_pool_init, initargs=(barrier,)) as pool:
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+    per_rep = [max(r[0][k] for r in res) for k in range(reps)]
+    best = min(per_rep)
     ncols = cores * cols_per_core
-    sample = (f"{ncols} columns of the same workload ({cores} processes x {cols_per_core} column(s), "
-              f"full degree-{m} filter incl. projectors), wall time incl. start-vector generation excluded")
-    return g.Nd * ncols / best, cores, kind, sample, best
+    sample = (f"{ncols} columns of the same workload ({cores} processes x {cols_per_core} columns = the reference's "
+              f"NP_BAND_PARAL={cores} layout, full degree-{m} filter incl. projectors); seconds = max over the processes "
+              f"of the time inside ChebyshevFiltering, processes started together, best of {reps}")
+    return {"rate": g.Nd * ncols / best, "cores": cores, "kind": kind, "sample": sample, "per_rep_s": per_rep,
+            "best_s": best, "ncols": ncols, "first_cols": [j[5] for j in jobs], "y0": [r[1] for r in res]}
 
 
 def run_reference(args):
+    """Reference arm: the reference's own compiled ChebyshevFiltering (oracle/_ref; the C port when the prebuilt
+    files are absent) on all host cores.  Bounded: one probe repetition sizes the run so that the whole arm ends
+    within a few minutes whatever --steps/--warmup ask for; the value is the best repetition."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     g, veff, proj, bounds = build_problem(args)
     m = args.degree
-    times = []
-    rate = cores = kind = sample = None
-    for i in range(args.warmup + args.steps):
-        rate, cores, kind, sample, dt = cpu_filter_rate(g, veff, proj, bounds, m, args.cpu_cols_per_core)
-        if i >= args.warmup:
-            times.append(dt)
-        if i == 0 and dt * (args.warmup + args.steps) > 600:  # keep the whole run within minutes
-            args.warmup, args.steps = 0, 1
-            times = [dt]
-            break
-    ncols = cores * args.cpu_cols_per_core
-    t = float(np.mean(times))
-    value = g.Nd * ncols / t
+    budget_s = float(os.environ.get("CHEFSI_BENCH_REF_BUDGET_S", "200"))
+    t0 = time.perf_counter()
+    r = cpu_filter_rate(g, veff, proj, bounds, m, args.cpu_cols_per_core, reps=1)
+    wall0 = time.perf_counter() - t0          # includes process start + table setup
+    times = list(r["per_rep_s"])
+    warm = 0
+    more = int(min(max(args.steps, 1), max(0, (budget_s - wall0) // max(wall0, 1e-9))))
+    if more >= 1:  # the probe becomes the warm-up, `more` timed repetitions follow in one pool
+        r = cpu_filter_rate(g, veff, proj, bounds, m, args.cpu_cols_per_core, reps=more)
+        times, warm = list(r["per_rep_s"]), 1
+    t = min(times)
+    value = g.Nd * r["ncols"] / t
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * t, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, proj), "step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": workload_name(args, proj), "step": r["sample"],
+                   "bounded": f"requested steps={args.steps} warmup={args.warmup}; ran {len(times)} timed + {warm} warm-up "
+                              f"repetition(s) inside a {budget_s:.0f} s budget; value = best repetition",
+                   "per_rep_s": times},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and so the first-touch placement of the pinned host buffers it allocates) to the CPUs of
+    the NUMA node the GPU hangs off.  Returns a description for the JSON line."""
+    info = {"gpu": index, "node": None, "cpus": None, "bound": False}
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out  # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info["cpus"] = len(use)
+        if use and os.environ.get("CHEFSI_BENCH_NO_NUMA_BIND") is None:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+    except Exception as e:  # containers without /sys access: report, do not fail
+        info["error"] = str(e)[:120]
+    return info
 
 
 # ------------------------------------------------------------------------------------------------
@@ -321,10 +390,13 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     achieved = alg_bytes / (st_ms * 1e-3) / 1e9 if st_ms > 0 else 0.0
+    path = ctx.stats()["last_path"]
+    kname = {1: "stream_kpt_kernel" if cplx else "stream_dense_kernel", 2: "stencil_zmarch_kernel", 3: "stencil_mixed_stream_kernel"}.get(path, "stencil_general_kernel")
+    traffic, traffic_src = ncu_traffic(kname, args.grid, block)
     roofline = {
-        "bound": "hbm", "kernel": ("stream_kpt_kernel" if cplx else "stream_dense_kernel" if os.environ.get("CHEFSI_B200_DENSE", "1") != "0" else "stream_orth_kernel") + " (fused stencil + Veff + recurrence)" if ctx.stats()["last_path"] == 1 else ("stencil_zmarch_kernel" if ctx.stats()["last_path"] == 2 else "stencil_general_kernel"),
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if (args.grid == 160 and block == 128 and ctx.stats()["last_path"] == 1 and os.environ.get("CHEFSI_B200_DENSE", "1") != "0") else None,
-        "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 128-column launch (profiles/r1_ncu_dense_final.txt: 9.61 GB read + 4.17 GB write)",
+        "bound": "hbm", "kernel": kname + " (fused stencil + Veff + recurrence)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peak_src, "avg_launch_ms": st_ms / st_n if st_n else None,
         "algorithmic_bytes_per_launch": 8.0 * words * (3 * m - 1) * g.Nd * block / m,
         "timing": "per-launch CUDA events over one full step run back to back with the timed steps (sustained clocks)",
@@ -332,35 +404,97 @@ def run_ours(args):
         "nloc_ms_per_degree": nl_ms / st_n if st_n else None,
     }
 
-    # ---- e2e: the same metric through the host-buffer C-ABI call (H2D + D2H inside the timed region) ----
-    e2e_cols = max(1, min(args.e2e_cols // world, ncol_local))
+    del slots  # free HBM for the parity block and the host entry point's own buffers
+    torch.cuda.empty_cache()
+
+    # ---- CPU baseline (rank 0, N = 1) and parity on the bench problem itself: the columns the reference arm filters
+    # are filtered on the GPU inside one full 128-column launch group and compared (untimed) ----
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        r = cpu_filter_rate(g, veff, proj, bounds, m, args.cpu_cols_per_core, reps=args.cpu_reps, want_y=not cplx)
+        cpu_baseline = {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        if not cplx:
+            pb = min(block, max(1, r["ncols"]))
+            trio = [torch.empty(pb * ld, dtype=torch.float64, device="cuda") for _ in range(3)]
+            ctx.fill_random_device(trio[0], pb, first_col=CPU_FIRST_COL, seed=1)
+            ys, _ = ctx.filter_device(trio[0], trio[1], trio[2], pb, m, a, b, a0)
+            ctx.synchronize()
+            num = den = 0.0
+            ncmp = 0
+            for fc, y_ref in zip(r["first_cols"], r["y0"]):
+                k = fc - CPU_FIRST_COL
+                if y_ref is None or k >= pb:
+                    continue
+                y_gpu = trio[ys][k * ld:k * ld + g.Nd].cpu().numpy()
+                num += float(np.sum((y_gpu - y_ref) ** 2))
+                den += float(np.sum(y_ref ** 2))
+                ncmp += 1
+            parity = {"rel_fro": (num / den) ** 0.5 if den > 0 else None, "columns_compared": ncmp,
+                      "columns_in_launch": pb, "against": r["kind"], "tolerance": 1e-10,
+                      "what": "Y = p_m(H) X0 of the bench problem, GPU (one launch group, device-resident entry point) vs the CPU arm's outputs on the same start vectors"}
+            del trio
+            torch.cuda.empty_cache()
+
+    # ---- e2e: the same metric through the host-buffer C-ABI call the SPARC shim makes (chefsi_chebyshev_filter with
+    # pinned HOST buffers; H2D of X and D2H of Y inside the timed region; X copy-back off = the shim's default) ----
+    e2e_cols = max(1, min(args.e2e_cols, ncol_local))      # PER RANK
     hdt = torch.complex128 if cplx else torch.float64
+    saved_aff = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa = bind_to_gpu_numa_node(local_rank)
     xh = torch.empty((e2e_cols, g.Nd), dtype=hdt).pin_memory()
     yh = torch.empty((e2e_cols, g.Nd), dtype=hdt).pin_memory()
     from sparc_b200 import problem as P
     xh.numpy()[:] = P.random_columns(g.Nd, 1, first_col=first_col, seed=1)[0]  # same column replicated: content is irrelevant to timing
-    del slots  # free HBM for the host entry point's own buffers
+    yh.zero_()
+    if saved_aff is not None and numa.get("bound"):
+        os.sched_setaffinity(0, saved_aff)
+    # the host limit, measured: pinned H2D and D2H copies of the same buffers running concurrently
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    nb = min(e2e_cols, 64)
+    dbuf_in = torch.empty((nb, g.Nd), dtype=hdt, device="cuda")
+    dbuf_out = torch.empty((nb, g.Nd), dtype=hdt, device="cuda")
+    link = None
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            dbuf_in.copy_(xh[:nb], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            yh[:nb].copy_(dbuf_out, non_blocking=True)
+        torch.cuda.synchronize()
+        link = nb * g.Nd * 8 * words / (time.perf_counter() - t0) / 1e9
+    del dbuf_in, dbuf_out
     torch.cuda.empty_cache()
-    ctx.ChebyshevFiltering(xh, yh, m, a, b, a0, copy_back_x=False)  # warm-up (allocations, page registration)
-    barrier()
-    t0 = time.perf_counter()
-    ctx.ChebyshevFiltering(xh, yh, m, a, b, a0, copy_back_x=False)
-    checksum = float(yh[0, :8].sum().real)  # device->host result is read on the host
-    t_e2e = time.perf_counter() - t0
+    ctx.ChebyshevFiltering(xh, yh, m, a, b, a0, copy_back_x=False)  # warm-up (allocations)
+    t_best = None
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        ctx.ChebyshevFiltering(xh, yh, m, a, b, a0, copy_back_x=False)
+        checksum = float(yh[0, :8].sum().real)  # device->host result is read on the host
+        t_rep = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t_rep], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_rep = float(t.item())
+        t_best = t_rep if t_best is None else min(t_best, t_rep)
+    cols_all = e2e_cols
+    link_min = link
     if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e_total_cols = e2e_cols * world
-    e2e = {"value": g.Nd * e2e_total_cols / t_e2e, "unit": UNIT,
+        t = torch.tensor([float(e2e_cols), -link], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t[:1], op=dist.ReduceOp.SUM)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.MAX)
+        cols_all, link_min = int(t[0].item()), -float(t[1].item())
+    e2e = {"value": g.Nd * cols_all / t_best, "unit": UNIT,
            "h2d_bytes_per_step": int(e2e_cols * g.Nd * 8 * words), "d2h_bytes_per_step": int(e2e_cols * g.Nd * 8 * words),
-           "columns": e2e_total_cols, "seconds": t_e2e, "checksum": checksum,
-           "api": "chefsi_chebyshev_filter (host buffers, pinned), X copy-back off as in the SPARC shim"}
-
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        rate, cores, kind, sample, _ = cpu_filter_rate(g, veff, proj, bounds, m, args.cpu_cols_per_core)
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+           "bytes_are": "per rank", "columns_per_rank": e2e_cols, "columns": cols_all, "seconds": t_best, "best_of": 3,
+           "checksum": checksum, "numa": numa,
+           "host_link_gbs_per_direction": link_min,
+           "host_link_note": "pinned H2D and D2H copies of the same buffers run concurrently (min over ranks); the e2e call "
+                             "moves 8 B per grid-pt*vector each way, so its ceiling is this rate / 8 B per rank",
+           "api": "chefsi_chebyshev_filter (host buffers, pinned), X copy-back off = the SPARC shim's default "
+                  "(sole caller eigenSolver.c:325 reuses X as scratch)"}
 
     if rank == 0:
         line = {
@@ -371,6 +505,7 @@ def run_ours(args):
                        "columns_per_launch": block, "per_h_apply_value": value * m,
                        "l2": "inputs per launch (>= 8 GB) far exceed the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "parity_rel_fro": parity["rel_fro"] if parity else None, "parity": parity,
             "clocks": clk.summary(),
         }
         print(json.dumps(line), flush=True)

@@ -93,6 +93,7 @@ typedef struct chefsi_ctx chefsi_ctx_t;
                                     /* (the caller reuses X as scratch, eigenSolver.c:364)   */
 
 /* ---- lifetime ---------------------------------------------------------------------- */
+int chefsi_device_count(void); /* usable CUDA devices (0 when there is none or the driver is absent) */
 int chefsi_create(chefsi_ctx_t **ctx, int device);
 void chefsi_destroy(chefsi_ctx_t *ctx);
 const char *chefsi_last_error(const chefsi_ctx_t *ctx);
@@ -181,6 +182,12 @@ typedef struct chefsi_stats {
     double last_nloc_ms;                /* summed device time of its projector kernels     */
     int last_stencil_launches;
     int last_path;                      /* 0 = 3-D brick kernel, 1 = TMA streaming kernel, 2 = z-march kernel */
+    int last_nloc_atomic;               /* 1: the last projector expand took the overlapping-sphere branch      */
+                                        /* (FP64 atomics, nlocVecRoutines.c:866-881 scatter-add)                */
+    int last_alpha_reduced;             /* 1: per-atom alpha sums were formed by alpha_reduce_kernel            */
+    unsigned int round_barrier_timeouts; /* times a streaming kernel's producer gave up on the round barrier (results are */
+                                        /* unaffected; a non-zero count means the xy-halo L2 sharing was lost: a perf cliff) */
+    int reserved_;
 } chefsi_stats_t;
 int chefsi_get_stats(const chefsi_ctx_t *ctx, chefsi_stats_t *out);
 /* when on, every kernel of a filter call is bracketed by CUDA events (adds host

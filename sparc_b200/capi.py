@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("CHEFSI_B200_LIB") or os.path.join(HERE, "libchefsi_b2
 
 # every symbol include/chefsi_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = (
-    "chefsi_create", "chefsi_destroy", "chefsi_last_error", "chefsi_version",
+    "chefsi_device_count", "chefsi_create", "chefsi_destroy", "chefsi_last_error", "chefsi_version",
     "chefsi_set_grid", "chefsi_set_projectors", "chefsi_set_veff", "chefsi_set_kpoint",
     "chefsi_chebyshev_filter", "chefsi_chebyshev_filter_kpt",
     "chefsi_hamiltonian_mult", "chefsi_hamiltonian_mult_kpt",
@@ -35,6 +35,10 @@ class ChefsiStats(C.Structure):
         ("last_nloc_ms", C.c_double),
         ("last_stencil_launches", C.c_int),
         ("last_path", C.c_int),
+        ("last_nloc_atomic", C.c_int),
+        ("last_alpha_reduced", C.c_int),
+        ("round_barrier_timeouts", C.c_uint),
+        ("reserved_", C.c_int),
     ]
 
 
@@ -57,6 +61,7 @@ def load_library() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     vp, dp, sz, i, d = C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double
     ip = C.POINTER(C.c_int)
+    lib.chefsi_device_count.argtypes = []
     lib.chefsi_create.argtypes = [C.POINTER(vp), i]
     lib.chefsi_destroy.argtypes = [vp]
     lib.chefsi_destroy.restype = None

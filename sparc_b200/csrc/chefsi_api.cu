@@ -42,6 +42,13 @@ extern "C" const char *chefsi_version(void) { return "chefsi_b200 0.1 (sm_100a, 
 
 extern "C" const char *chefsi_last_error(const chefsi_ctx_t *ctx) { return ctx ? ctx->err : g_create_err; }
 
+extern "C" int chefsi_device_count(void)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ndev;
+}
+
 extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
 {
     if (!out) return 1;
@@ -80,8 +87,6 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
     for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->force_general = getenv("CHEFSI_B200_FORCE_GENERAL") ? atoi(getenv("CHEFSI_B200_FORCE_GENERAL")) : 0;
     if (getenv("CHEFSI_B200_GRIDSYNC")) ctx->stream_gridsync = atoi(getenv("CHEFSI_B200_GRIDSYNC"));
-    if (getenv("CHEFSI_B200_DENSE")) ctx->dense_stream = atoi(getenv("CHEFSI_B200_DENSE"));
-    if (getenv("CHEFSI_B200_STREAM_VARIANT")) ctx->stream_variant = atoi(getenv("CHEFSI_B200_STREAM_VARIANT"));
     if (getenv("CHEFSI_B200_ALPHA_REDUCE_MIN")) ctx->alpha_reduce_min = atoi(getenv("CHEFSI_B200_ALPHA_REDUCE_MIN"));
     if (getenv("CHEFSI_B200_TMA_L2PROMO")) ctx->tma_l2promo = atoi(getenv("CHEFSI_B200_TMA_L2PROMO")) & 3;
     *out = ctx;
@@ -93,7 +98,6 @@ static void free_nloc(NlocDev &d)
     cudaFree(d.IP_displ); cudaFree(d.gamma); cudaFree(d.img_atom); cudaFree(d.img_ndc);
     cudaFree(d.pos_off); cudaFree(d.chiT_off); cudaFree(d.grid_pos); cudaFree(d.chiT); cudaFree(d.img_aoff);
     cudaFree(d.img_phase); cudaFree(d.atom_img_off); cudaFree(d.atom_img);
-    cudaFree(d.patch_src); cudaFree(d.patch_dst); cudaFree(d.patch_ph);
     free(d.h_img_coords);
     d = NlocDev();
 }
@@ -109,7 +113,6 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     cudaFree(ctx->d_alpha[0]);
     cudaFree(ctx->d_alpha[1]);
     cudaFree(ctx->d_alpha_sum);
-    for (int i = 0; i < 2; i++) { cudaFree(ctx->d_stage_in[i]); cudaFree(ctx->d_stage_out[i]); }
     for (int i = 0; i < 12; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     cudaFree(ctx->d_sync);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -167,15 +170,10 @@ extern "C" int chefsi_set_grid(chefsi_ctx_t *ctx, const chefsi_grid_t *g)
         if (per[d] && N[d] < g->FDn) return chefsi_fail(ctx, "periodic axis %d has fewer points than the FD radius", d);
     ctx->grid = *g;
     ctx->Nd = (size_t)g->Nx * g->Ny * g->Nz;
-    {   /* internal layout: halo-padded planes when the streaming kernel applies (see Layout) */
+    {   /* internal layout = the reference's dense layout, ld rounded up to 16 doubles (see Layout) */
         Layout &L = ctx->lay;
-        const bool padded = stream_layout_wanted(*g) && !ctx->force_general && !ctx->dense_stream;
         L.Nx = g->Nx; L.Ny = g->Ny; L.Nz = g->Nz;
-        L.px = padded ? 8 : 0;
-        L.py = padded ? 6 : 0;
-        L.Nxp = g->Nx + 2 * L.px;
-        L.Nyp = g->Ny + 2 * L.py;
-        L.plane = (size_t)L.Nxp * L.Nyp;
+        L.plane = (size_t)L.Nx * L.Ny;
         L.ld = (L.plane * g->Nz + 15) / 16 * 16;
         ctx->ld = L.ld;
         if (L.ld > 0x7fffffffULL) return chefsi_fail(ctx, "grid too large for 32-bit sphere indices");
@@ -251,17 +249,8 @@ extern "C" int chefsi_set_veff(chefsi_ctx_t *ctx, const double *veff_host)
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!veff_host) { ctx->have_veff = false; return 0; }
-    const Layout &L = ctx->lay;
-    if (L.px == 0 && L.py == 0) {
-        CHEFSI_CUDA(ctx, cudaMemcpyAsync(ctx->d_veff, veff_host, ctx->Nd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    } else { /* Nd doubles once per SCF step: repack on the host */
-        std::vector<double> tmp(L.ld, 0.0);
-        for (int k = 0; k < L.Nz; k++)
-            for (int j = 0; j < L.Ny; j++)
-                memcpy(&tmp[lay_pos(L, 0, j, k)], veff_host + ((size_t)k * L.Ny + j) * L.Nx, sizeof(double) * L.Nx);
-        CHEFSI_CUDA(ctx, cudaMemcpy(ctx->d_veff, tmp.data(), L.ld * sizeof(double), cudaMemcpyHostToDevice));
-    }
+    CHEFSI_CUDA(ctx, cudaMemcpyAsync(ctx->d_veff, veff_host, ctx->Nd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); /* the caller may reuse veff_host right away */
     ctx->have_veff = true;
     return 0;
 }
@@ -338,31 +327,6 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
         std::vector<int> cur(off.begin(), off.end() - 1);
         for (int s2 = 0; s2 < n_seg; s2++) lst[cur[seg_atom[s2]]++] = s2;
     }
-    /* sphere indices in the internal layout, and the list of sphere points mirrored in halo pads */
-    const Layout &L = ctx->lay;
-    std::vector<int> ppos((size_t)npos);
-    std::vector<int> psrc, pdst;
-    std::vector<unsigned char> done(ctx->Nd, 0);
-    for (long long t = 0; t < npos; t++) {
-        const int p = nl->grid_pos[t];
-        const int i = p % L.Nx, j = (p / L.Nx) % L.Ny, k = p / (L.Nx * L.Ny);
-        const size_t q = lay_pos(L, i, j, k);
-        ppos[t] = (int)q;
-        if ((L.px || L.py) && !done[p]) {
-            done[p] = 1;
-            if (L.px && !ctx->grid.BCx) {
-                if (i < L.px) { psrc.push_back((int)q); pdst.push_back((int)(q + L.Nx)); }
-                else if (i >= L.Nx - L.px) { psrc.push_back((int)q); pdst.push_back((int)(q - L.Nx)); }
-            }
-            if (L.py && !ctx->grid.BCy) {
-                if (j < L.py) { psrc.push_back((int)q); pdst.push_back((int)(q + (size_t)L.Ny * L.Nxp)); }
-                else if (j >= L.Ny - L.py) { psrc.push_back((int)q); pdst.push_back((int)(q - (size_t)L.Ny * L.Nxp)); }
-            }
-        }
-    }
-    d.n_patch = (int)psrc.size();
-    if (upload(ctx, &d.patch_src, psrc.data(), psrc.size())) return 1;
-    if (upload(ctx, &d.patch_dst, pdst.data(), pdst.size())) return 1;
     if (upload(ctx, &d.IP_displ, nl->IP_displ, (size_t)nl->n_atom + 1)) return 1;
     if (upload(ctx, &d.gamma, nl->gamma, (size_t)d.ntot)) return 1;
     if (upload(ctx, &d.img_atom, seg_atom.data(), (size_t)n_seg)) return 1;
@@ -373,7 +337,7 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
         poff[n_seg] = npos;
         if (upload(ctx, &d.pos_off, poff.data(), poff.size())) return 1;
     }
-    if (upload(ctx, &d.grid_pos, ppos.data(), (size_t)npos)) return 1;
+    if (upload(ctx, &d.grid_pos, nl->grid_pos, (size_t)npos)) return 1; /* internal layout == the reference's: indices as they are */
     {   /* Chi per image transposed to point-major and zero-padded to np_pad projectors (what the nloc
            kernel streams with 16-byte cp.async); per-segment offsets into it and of the alpha partials */
         std::vector<long long> toff((size_t)nl->n_img + 1, 0);
@@ -471,8 +435,8 @@ static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void
         ctx->stats.kernel_launches += n;
     }
     prof.begin(0);
-    if (stream_orth_supported(ctx, is_complex)) {
-        n = launch_stencil_stream_orth(ctx, a, is_complex);
+    if (stream_dense_supported(ctx, is_complex)) {
+        n = launch_stencil_stream_dense(ctx, a);
         ctx->stats.last_path = 1;
     } else if (is_complex && stream_kpt_supported(ctx)) {
         n = launch_stencil_stream_kpt(ctx, a);
@@ -494,10 +458,6 @@ static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void
     if (have_nl) {
         prof.begin(1);
         n = launch_nloc(ctx, nl_out ? NLOC_FUSED : NLOC_EXPAND, out, ctx->ld, ncol, s1, is_complex);
-        if (n > 0 && ctx->nl.overlap && ctx->stats.last_path == 1) { /* atomics path: refresh the pad images */
-            const int m2 = launch_nloc_halo_patch(ctx, out, ctx->ld, ncol, is_complex);
-            n = (m2 < 0) ? -1 : n + m2;
-        }
         prof.end();
         if (n < 0) return 1;
         ctx->stats.kernel_launches += n;
@@ -519,20 +479,6 @@ static int filter_device(chefsi_ctx *ctx, void *bufs[3], int ncol, int m, double
     const double gamma = 2.0 / sigma1;
     int X = 0, Y = 1, W = 2;
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    if (stream_orth_supported(ctx, is_complex)) {
-        /* the streaming kernel reads halos from the pads of the internal layout: images of X0 now, and
-           zeros on Dirichlet faces of the two buffers it will write (it only writes periodic images) */
-        int n = launch_halo_prepare(ctx, bufs[0], ncol, is_complex, 0);
-        if (n < 0) return 1;
-        ctx->stats.kernel_launches += n;
-        if (ctx->grid.BCx || ctx->grid.BCy) {
-            for (int t = 1; t < 3; t++) {
-                n = launch_halo_prepare(ctx, bufs[t], ncol, is_complex, 1);
-                if (n < 0) return 1;
-                ctx->stats.kernel_launches += n;
-            }
-        }
-    }
     /* with disjoint spheres every step's projector kernel also projects its (final) output, so the
        next step starts with alpha in hand: one stencil launch + one projector launch per degree */
     const bool chain = !ctx->nl.overlap;
@@ -573,11 +519,6 @@ static int hmult_device(chefsi_ctx *ctx, int ncol, double c, const void *x, void
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     Profiler prof(ctx);
-    if (stream_orth_supported(ctx, is_complex)) {
-        int n = launch_halo_prepare(ctx, const_cast<void *>(x), ncol, is_complex, 0);
-        if (n < 0) return 1;
-        ctx->stats.kernel_launches += n;
-    }
     const int rc = apply_step(ctx, prof, x, nullptr, Hx, ncol, c, 1.0, 0.0, is_complex, false, false);
     prof.finish();
     return rc;
@@ -606,24 +547,10 @@ extern "C" int chefsi_synchronize(chefsi_ctx_t *ctx)
  * What the reference's ChebyshevFiltering / Hamiltonian_vectors_mult bind to: X and Y live in host
  * memory (SPARC's Xorb / Yorb).  The block is cut into column chunks that flow through a three-stage
  * pipeline on three streams -- H2D copy of chunk k+1, filter of chunk k, D2H copy of chunk k-1 -- so
- * the call costs about max(PCIe in, compute, PCIe out) instead of their sum.  Dense staging buffers on
- * the device (two in, two out) decouple the copies from the internal (halo-padded) layout. */
-static int ensure_stage(chefsi_ctx *ctx, size_t bytes)
-{
-    if (bytes <= ctx->stage_bytes) return 0;
-    for (int i = 0; i < 2; i++) {
-        cudaFree(ctx->d_stage_in[i]); ctx->d_stage_in[i] = nullptr;
-        cudaFree(ctx->d_stage_out[i]); ctx->d_stage_out[i] = nullptr;
-    }
-    ctx->stage_bytes = 0;
-    for (int i = 0; i < 2; i++) {
-        CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_stage_in[i], bytes));
-        CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_stage_out[i], bytes));
-    }
-    ctx->stage_bytes = bytes;
-    return 0;
-}
-
+ * the call costs about max(PCIe in, compute, PCIe out) instead of their sum.  The device block IS the
+ * reference's layout (columns ld apart), so the copies go straight into / out of the recurrence buffers;
+ * chunks rotate through three buffer trios (with two, the chain D2H(k) -> H2D(k+2) -> filter(k+2) would
+ * expose a copy per chunk). */
 static int ensure_bufs(chefsi_ctx *ctx, size_t bytes_each)
 {
     if (bytes_each <= ctx->buf_bytes) return 0;
@@ -650,16 +577,14 @@ static int ensure_bufs2(chefsi_ctx *ctx, size_t bytes_each)
     return 0;
 }
 
-/* columns per chunk: small enough that the pipeline has ~8 chunks to overlap and that three blocks,
- * four staging blocks and alpha fit in the free device memory; large enough to fill the GPU */
+/* columns per chunk: small enough that the pipeline has ~8 chunks to overlap and that three buffer trios and
+ * alpha fit in the free device memory; large enough to fill the GPU */
 static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
 {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
-    free_b += 3 * ctx->buf_bytes + 6 * ctx->buf2_bytes + 2 * ctx->alpha_bytes + 4 * ctx->stage_bytes; /* what we already hold can be reused */
-    /* padded layout: 3 blocks + 4 dense staging blocks; dense layout: three trios, no staging */
-    const size_t per_col = ((ctx->lay.px || ctx->lay.py) ? 3 * ctx->ld * esz + 4 * ctx->Nd * esz : 9 * ctx->ld * esz) +
-                           2 * (size_t)ctx->nl.img_proj_total * esz;
+    free_b += 3 * ctx->buf_bytes + 6 * ctx->buf2_bytes + 2 * ctx->alpha_bytes; /* what we already hold can be reused */
+    const size_t per_col = 9 * ctx->ld * esz + 2 * (size_t)ctx->nl.img_proj_total * esz;
     size_t budget = (size_t)(0.85 * (double)free_b);
     const char *env = getenv("CHEFSI_B200_MAX_CHUNK_BYTES");
     if (env) { size_t v = strtoull(env, nullptr, 10); if (v && v < budget) budget = v; }
@@ -686,6 +611,24 @@ static int ensure_pipe_events(chefsi_ctx *ctx)
     return 0;
 }
 
+/* after a failure in the middle of a pipelined call: no async copy may still be reading or writing the caller's
+ * buffers when the call returns (the caller may free them), and the streams must be joinable for the next call */
+static int drain_streams(chefsi_ctx *ctx, int rc)
+{
+    cudaStreamSynchronize(ctx->h2d_stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->d2h_stream);
+    cudaGetLastError();
+    return rc;
+}
+#define CHEFSI_CUDA_DRAIN(ctx, call)                                                                      \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return drain_streams((ctx), chefsi_fail((ctx), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,   \
+                                                    cudaGetErrorString(e_)));                             \
+    } while (0)
+
 static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo, int ncol, int m, double a, double b,
                        double a0, int flags, bool is_complex)
 {
@@ -695,104 +638,58 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
     const int chunk = chunk_columns(ctx, ncol, esz);
-    /* dense layout: the device block IS the reference's layout (columns ld apart), so the copies go straight
-       into / out of the recurrence buffers; chunks rotate through three buffer trios (with two, the chain
-       D2H(k) -> H2D(k+2) -> filter(k+2) would expose a copy per chunk).  No staging, no pack / unpack passes
-       (6 of ~65 block passes per degree-20 call). */
-    const bool direct = (ctx->lay.px == 0 && ctx->lay.py == 0);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
-    if (direct) {
-        if (chunk < ncol && ensure_bufs2(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
-    } else if (ensure_stage(ctx, (size_t)chunk * ctx->Nd * esz)) return 1;
+    if (chunk < ncol && ensure_bufs2(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
     if (ensure_pipe_events(ctx)) return 1;
-    cudaEvent_t *ev_h2d = ctx->pipe_ev, *ev_in_free = ctx->pipe_ev + 3, *ev_out = ctx->pipe_ev + 6, *ev_d2h = ctx->pipe_ev + 9;
+    cudaEvent_t *ev_h2d = ctx->pipe_ev, *ev_out = ctx->pipe_ev + 6, *ev_d2h = ctx->pipe_ev + 9;
     const bool copy_x = !(flags & CHEFSI_FLAG_NO_X_COPYBACK);
-    const size_t row = ctx->Nd * esz;
+    const size_t row = ctx->Nd * esz, pitch = ctx->ld * esz;
     cudaEvent_t t0 = ctx->ev[2], t1 = ctx->ev[3];
     CHEFSI_CUDA(ctx, cudaEventRecord(t0, ctx->stream));
     CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, t0, 0)); /* order after earlier work of this context */
-    int k = 0;
-    if (direct) {
-        const size_t pitch = ctx->ld * esz;
-        /* Chunk schedule: the first H2D and the last D2H are the only copies nothing overlaps with, so the
-           pipeline ramps up and down through quarter- and half-size chunks (c/4, c/2, c, ..., c, c/2, c/4). */
-        std::vector<int> sched;
-        {
-            const int q = chunk / 4, h = chunk / 2;
-            /* only for long pipelines: a chunk of < 32 columns costs the projector kernel as much as 32 (it works on
-               groups of 32 columns), so on a short block the ramp costs more than the copies it hides (measured at
-               128 columns per rank: 8.1e9 flat vs 5.7e9 ramped at N = 2) */
-            if (ncol >= 6 * chunk && q >= 8 && getenv("CHEFSI_B200_FLAT_CHUNKS") == nullptr) {
-                int rest = ncol - 2 * (q + h);
-                sched.push_back(q); sched.push_back(h);
-                while (rest > 0) { const int c1 = rest < chunk ? rest : chunk; sched.push_back(c1); rest -= c1; }
-                sched.push_back(h); sched.push_back(q);
-            } else {
-                for (int c0 = 0; c0 < ncol; c0 += chunk) sched.push_back((ncol - c0 < chunk) ? ncol - c0 : chunk);
-            }
+    /* Chunk schedule: the first H2D and the last D2H are the only copies nothing overlaps with, so the
+       pipeline ramps up and down through quarter- and half-size chunks (c/4, c/2, c, ..., c, c/2, c/4). */
+    std::vector<int> sched;
+    {
+        const int q = chunk / 4, h = chunk / 2;
+        /* only for long pipelines: a chunk of < 32 columns costs the projector kernel as much as 32 (it works on
+           groups of 32 columns), so on a short block the ramp costs more than the copies it hides (measured at
+           128 columns per rank: 8.1e9 flat vs 5.7e9 ramped at N = 2) */
+        if (ncol >= 6 * chunk && q >= 8 && getenv("CHEFSI_B200_FLAT_CHUNKS") == nullptr) {
+            int rest = ncol - 2 * (q + h);
+            sched.push_back(q); sched.push_back(h);
+            while (rest > 0) { const int c1 = rest < chunk ? rest : chunk; sched.push_back(c1); rest -= c1; }
+            sched.push_back(h); sched.push_back(q);
+        } else {
+            for (int c0 = 0; c0 < ncol; c0 += chunk) sched.push_back((ncol - c0 < chunk) ? ncol - c0 : chunk);
         }
-        int c0 = 0;
-        for (size_t kk = 0; kk < sched.size(); c0 += sched[kk], kk++, k++) {
-            const int nc = sched[kk];
-            const int s = k % 3;
-            void **trio = s == 0 ? ctx->d_buf : (s == 1 ? ctx->d_buf2 : ctx->d_buf3);
-            /* trio s is free again when the copies of chunk k-3 out of it have finished */
-            if (k >= 3) CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, ev_d2h[s], 0));
-            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(trio[0], pitch, (const char *)X + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
-                                               cudaMemcpyHostToDevice, ctx->h2d_stream));
-            CHEFSI_CUDA(ctx, cudaEventRecord(ev_h2d[s], ctx->h2d_stream));
-            CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[s], 0));
-            int ys = 1, xs = 0;
-            if (filter_device(ctx, trio, nc, m, a, b, a0, is_complex, &ys, &xs)) return 1;
-            CHEFSI_CUDA(ctx, cudaEventRecord(ev_out[s], ctx->stream));
-            CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev_out[s], 0));
-            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Y + (size_t)c0 * ldo * esz, ldo * esz, trio[ys], pitch, row, nc,
-                                               cudaMemcpyDeviceToHost, ctx->d2h_stream));
-            if (copy_x)
-                CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)X + (size_t)c0 * ldi * esz, ldi * esz, trio[xs], pitch, row, nc,
-                                                   cudaMemcpyDeviceToHost, ctx->d2h_stream));
-            CHEFSI_CUDA(ctx, cudaEventRecord(ev_d2h[s], ctx->d2h_stream));
-        }
-    } else
-    for (int c0 = 0; c0 < ncol; c0 += chunk, k++) {
-        const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-        const int s = k & 1;
-        /* -- H2D: X chunk -> dense staging (needs stage_in[s] free: packed, and X copy-back of chunk k-2 done) */
-        if (k >= 2) CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, copy_x ? ev_d2h[s] : ev_in_free[s], 0));
-        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_stage_in[s], row, (const char *)X + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
-                                           cudaMemcpyHostToDevice, ctx->h2d_stream));
-        CHEFSI_CUDA(ctx, cudaEventRecord(ev_h2d[s], ctx->h2d_stream));
-        /* -- compute: pack, filter, unpack into the out staging */
-        CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[s], 0));
-        int n = launch_pack(ctx, ctx->d_stage_in[s], ctx->Nd, ctx->d_buf[0], nc, is_complex);
-        if (n < 0) return 1;
-        ctx->stats.kernel_launches += n;
-        CHEFSI_CUDA(ctx, cudaEventRecord(ev_in_free[s], ctx->stream));
+    }
+    int c0 = 0, k = 0;
+    for (size_t kk = 0; kk < sched.size(); c0 += sched[kk], kk++, k++) {
+        const int nc = sched[kk];
+        const int s = k % 3;
+        void **trio = s == 0 ? ctx->d_buf : (s == 1 ? ctx->d_buf2 : ctx->d_buf3);
+        /* trio s is free again when the copies of chunk k-3 out of it have finished */
+        if (k >= 3) CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->h2d_stream, ev_d2h[s], 0));
+        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(trio[0], pitch, (const char *)X + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
+                                                 cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CHEFSI_CUDA_DRAIN(ctx, cudaEventRecord(ev_h2d[s], ctx->h2d_stream));
+        CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[s], 0));
         int ys = 1, xs = 0;
-        if (filter_device(ctx, ctx->d_buf, nc, m, a, b, a0, is_complex, &ys, &xs)) return 1;
-        if (k >= 2) CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[s], 0)); /* stage_out[s] drained */
-        n = launch_unpack(ctx, ctx->d_buf[ys], ctx->d_stage_out[s], ctx->Nd, nc, is_complex);
-        if (n < 0) return 1;
-        ctx->stats.kernel_launches += n;
-        if (copy_x) {
-            n = launch_unpack(ctx, ctx->d_buf[xs], ctx->d_stage_in[s], ctx->Nd, nc, is_complex);
-            if (n < 0) return 1;
-            ctx->stats.kernel_launches += n;
-        }
-        CHEFSI_CUDA(ctx, cudaEventRecord(ev_out[s], ctx->stream));
-        /* -- D2H */
-        CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev_out[s], 0));
-        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Y + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_stage_out[s], row, row, nc,
-                                           cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (filter_device(ctx, trio, nc, m, a, b, a0, is_complex, &ys, &xs)) return drain_streams(ctx, 1);
+        CHEFSI_CUDA_DRAIN(ctx, cudaEventRecord(ev_out[s], ctx->stream));
+        CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev_out[s], 0));
+        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync((char *)Y + (size_t)c0 * ldo * esz, ldo * esz, trio[ys], pitch, row, nc,
+                                                 cudaMemcpyDeviceToHost, ctx->d2h_stream));
         if (copy_x)
-            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)X + (size_t)c0 * ldi * esz, ldi * esz, ctx->d_stage_in[s], row, row, nc,
-                                               cudaMemcpyDeviceToHost, ctx->d2h_stream));
-        CHEFSI_CUDA(ctx, cudaEventRecord(ev_d2h[s], ctx->d2h_stream));
+            CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync((char *)X + (size_t)c0 * ldi * esz, ldi * esz, trio[xs], pitch, row, nc,
+                                                     cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        CHEFSI_CUDA_DRAIN(ctx, cudaEventRecord(ev_d2h[s], ctx->d2h_stream));
     }
     /* join: the compute stream waits for the last copies, then the host waits for it */
-    for (int s = 0; s < (direct ? 3 : 2) && s < k; s++) CHEFSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[s], 0));
-    CHEFSI_CUDA(ctx, cudaEventRecord(t1, ctx->stream));
-    CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < 3 && s < k; s++) CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[s], 0));
+    CHEFSI_CUDA_DRAIN(ctx, cudaEventRecord(t1, ctx->stream));
+    CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) ctx->stats.last_filter_ms = ms; else cudaGetLastError();
     return 0;
@@ -817,34 +714,18 @@ static int hmult_host(chefsi_ctx *ctx, int ncol, double c, const void *x, size_t
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
     const int chunk = chunk_columns(ctx, ncol, esz);
-    const bool direct = (ctx->lay.px == 0 && ctx->lay.py == 0); /* dense layout: no staging (see filter_host) */
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
-    if (!direct && ensure_stage(ctx, (size_t)chunk * ctx->Nd * esz)) return 1;
     const size_t row = ctx->Nd * esz, pitch = ctx->ld * esz;
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-        if (direct) {
-            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_buf[0], pitch, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
-                                               cudaMemcpyHostToDevice, ctx->stream));
-            if (hmult_device(ctx, nc, c, ctx->d_buf[0], ctx->d_buf[1], is_complex)) return 1;
-            CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Hx + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_buf[1], pitch, row, nc,
-                                               cudaMemcpyDeviceToHost, ctx->stream));
-            CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            continue;
-        }
-        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_stage_in[0], row, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
-                                           cudaMemcpyHostToDevice, ctx->stream));
-        int n = launch_pack(ctx, ctx->d_stage_in[0], ctx->Nd, ctx->d_buf[0], nc, is_complex);
-        if (n < 0) return 1;
-        ctx->stats.kernel_launches += n;
-        if (hmult_device(ctx, nc, c, ctx->d_buf[0], ctx->d_buf[1], is_complex)) return 1;
-        n = launch_unpack(ctx, ctx->d_buf[1], ctx->d_stage_out[0], ctx->Nd, nc, is_complex);
-        if (n < 0) return 1;
-        ctx->stats.kernel_launches += n;
-        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync((char *)Hx + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_stage_out[0], row, row, nc,
-                                           cudaMemcpyDeviceToHost, ctx->stream));
-        CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(ctx->d_buf[0], pitch, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
+                                                 cudaMemcpyHostToDevice, ctx->stream));
+        if (hmult_device(ctx, nc, c, ctx->d_buf[0], ctx->d_buf[1], is_complex)) return drain_streams(ctx, 1);
+        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync((char *)Hx + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_buf[1], pitch, row, nc,
+                                                 cudaMemcpyDeviceToHost, ctx->stream));
     }
+    /* one synchronisation per call: the chunks reuse d_buf in stream order */
+    CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 extern "C" int chefsi_hamiltonian_mult(chefsi_ctx_t *ctx, int ncol, double c, const double *x, size_t ldi, double *Hx,
@@ -871,6 +752,7 @@ extern "C" int chefsi_fill_random_device(chefsi_ctx_t *ctx, void *buf, int ncol,
     return 0;
 }
 
+/* dense block with an arbitrary leading dimension <-> internal layout (which differs only in ld): strided D2D copies */
 extern "C" int chefsi_pack_device(chefsi_ctx_t *ctx, const void *dense, size_t ld_dense, void *packed, int ncol,
                                   int is_complex)
 {
@@ -878,9 +760,10 @@ extern "C" int chefsi_pack_device(chefsi_ctx_t *ctx, const void *dense, size_t l
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ld_dense < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int n = launch_pack(ctx, dense, ld_dense, packed, ncol, is_complex != 0);
-    if (n < 0) return 1;
-    ctx->stats.kernel_launches += n;
+    const size_t esz = is_complex ? 16 : 8;
+    if (ncol > 0)
+        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(packed, ctx->ld * esz, dense, ld_dense * esz, ctx->Nd * esz, ncol,
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
 }
 extern "C" int chefsi_unpack_device(chefsi_ctx_t *ctx, const void *packed, void *dense, size_t ld_dense, int ncol,
@@ -890,9 +773,10 @@ extern "C" int chefsi_unpack_device(chefsi_ctx_t *ctx, const void *packed, void 
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ld_dense < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int n = launch_unpack(ctx, packed, dense, ld_dense, ncol, is_complex != 0);
-    if (n < 0) return 1;
-    ctx->stats.kernel_launches += n;
+    const size_t esz = is_complex ? 16 : 8;
+    if (ncol > 0)
+        CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(dense, ld_dense * esz, packed, ctx->ld * esz, ctx->Nd * esz, ncol,
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
 }
 
@@ -916,6 +800,14 @@ extern "C" int chefsi_get_stats(const chefsi_ctx_t *ctx, chefsi_stats_t *out)
 {
     if (!ctx || !out) return 1;
     *out = ctx->stats;
+    if (ctx->d_sync) { /* word 1 of the round-barrier block counts producers that gave up waiting */
+        unsigned int t = 0;
+        if (cudaSetDevice(ctx->device) == cudaSuccess &&
+            cudaMemcpyAsync(&t, ctx->d_sync + 1, sizeof(t), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+            cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+            out->round_barrier_timeouts = t;
+        else cudaGetLastError();
+    }
     return 0;
 }
 /* ---- domain-split building blocks (see include/chefsi_b200.h) ---------------------------------------- */
@@ -926,11 +818,6 @@ extern "C" int chefsi_stencil_step_device(chefsi_ctx_t *ctx, const double *x, co
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     Profiler prof(ctx);
-    if (stream_orth_supported(ctx, false)) {
-        int n = launch_halo_prepare(ctx, const_cast<double *>(x), ncol, false, 0);
-        if (n < 0) return 1;
-        ctx->stats.kernel_launches += n;
-    }
     const int rc = apply_step(ctx, prof, x, xprev, out, ncol, c, s1, s2, false, false, false, /*with_nl=*/false);
     prof.finish();
     return rc;
@@ -942,11 +829,11 @@ extern "C" int chefsi_nloc_project_device(chefsi_ctx_t *ctx, const double *x, in
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ctx->nl.n_img == 0 || ctx->nl.ntot == 0) return chefsi_fail(ctx, "nloc_project: no projectors on this context");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->alpha_reduce_min = -1; /* this context always keeps per-atom sums */
+    const int saved_min = ctx->alpha_reduce_min;
+    ctx->alpha_reduce_min = -1; /* per-atom sums wanted for THIS call only: later filter calls keep their own threshold */
     int n = launch_nloc(ctx, NLOC_PROJECT, const_cast<double *>(x), ctx->ld, ncol, 0.0, false);
-    if (n < 0) return 1;
-    ctx->stats.kernel_launches += n;
-    n = launch_alpha_reduce(ctx, ncol, false);
+    if (n >= 0) { ctx->stats.kernel_launches += n; n = launch_alpha_reduce(ctx, ncol, false); }
+    ctx->alpha_reduce_min = saved_min;
     if (n < 0) return 1;
     ctx->stats.kernel_launches += n;
     CHEFSI_CUDA(ctx, cudaMemcpyAsync(alpha_out, ctx->d_alpha_sum, sizeof(double) * (size_t)ctx->nl.ntot * ncol,
@@ -960,13 +847,16 @@ extern "C" int chefsi_nloc_expand_device(chefsi_ctx_t *ctx, double *out, int nco
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ctx->nl.n_img == 0 || ctx->nl.ntot == 0) return chefsi_fail(ctx, "nloc_expand: no projectors on this context");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int saved_min = ctx->alpha_reduce_min;
     ctx->alpha_reduce_min = -1;
-    if (nloc_ensure_alpha(ctx, ncol, false)) return 1;
-    CHEFSI_CUDA(ctx, cudaMemcpyAsync(ctx->d_alpha_sum, alpha_in, sizeof(double) * (size_t)ctx->nl.ntot * ncol,
-                                     cudaMemcpyDeviceToDevice, ctx->stream));
+    if (nloc_ensure_alpha(ctx, ncol, false)) { ctx->alpha_reduce_min = saved_min; return 1; }
+    cudaError_t ce = cudaMemcpyAsync(ctx->d_alpha_sum, alpha_in, sizeof(double) * (size_t)ctx->nl.ntot * ncol,
+                                     cudaMemcpyDeviceToDevice, ctx->stream);
+    if (ce != cudaSuccess) { ctx->alpha_reduce_min = saved_min; return chefsi_fail(ctx, "nloc_expand: %s", cudaGetErrorString(ce)); }
     ctx->alpha_sum_external = 1; /* expand reads the buffer as it is */
     const int n = launch_nloc(ctx, NLOC_EXPAND, out, ctx->ld, ncol, scale, false);
     ctx->alpha_sum_external = 0;
+    ctx->alpha_reduce_min = saved_min;
     if (n < 0) return 1;
     ctx->stats.kernel_launches += n;
     return 0;

@@ -21,21 +21,19 @@ struct MixedComp {
     double wm[CHEFSI_MAXR + 1]; /* already scaled by a = -1/2 */
 };
 
-/* Device-resident layout of one orbital column ("internal layout").
- * Grid point (i,j,k) lives at ((k*Nyp + j+py)*Nxp + i+px).  For grids that qualify for the streaming
- * kernel the xy-planes carry a halo pad (px = 8, py = 6) that holds the periodic images (or zeros on
- * Dirichlet faces), so that a haloed tile of a plane is ONE in-bounds TMA box; otherwise px = py = 0
- * and the layout is the reference's dense x-fastest one.  Columns are ld elements apart. */
+/* Device-resident layout of one orbital column ("internal layout") = the reference's dense x-fastest layout
+ * (lapVecRoutines.c:313): grid point (i,j,k) lives at (k*Ny + j)*Nx + i; columns are ld elements apart
+ * (ld >= Nd, a multiple of 16 doubles because TMA strides are multiples of 16 bytes).  Halos are never stored:
+ * the streaming kernels get periodic images through wrapped TMA boxes and Dirichlet zeros through the TMA
+ * out-of-bounds fill, the z-march kernels wrap when they commit a plane to their ring. */
 struct Layout {
     int Nx, Ny, Nz;
-    int px, py;
-    int Nxp, Nyp;
-    size_t plane;   /* Nxp * Nyp */
+    size_t plane;   /* Nx * Ny */
     size_t ld;      /* elements between columns (>= plane * Nz, multiple of 16) */
 };
 __host__ __device__ __forceinline__ size_t lay_pos(const Layout &L, int i, int j, int k)
 {
-    return ((size_t)k * L.Nyp + (j + L.py)) * L.Nxp + (i + L.px);
+    return ((size_t)k * L.Ny + j) * L.Nx + i;
 }
 
 struct StencilDesc {
@@ -85,9 +83,6 @@ struct NlocDev {
     /* host copies needed to rebuild phases */
     double *h_img_coords = nullptr;
     long long total_pts = 0;
-    /* sphere points whose value is mirrored in a halo pad: (src, dst) positions in the internal layout */
-    int *patch_src = nullptr, *patch_dst = nullptr, *patch_ph = nullptr;
-    int n_patch = 0;
 };
 
 struct chefsi_ctx {
@@ -100,17 +95,13 @@ struct chefsi_ctx {
     size_t Nd = 0, ld = 0;
     Layout lay{};
     double *d_veff = nullptr;    /* Veff in the internal layout (one column) */
-    double *d_zero = nullptr;    /* unused spare */
-    void *d_stage_in[2] = {nullptr, nullptr};  /* dense staging blocks of the host entry points' pipeline */
-    void *d_stage_out[2] = {nullptr, nullptr};
     cudaEvent_t pipe_ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t stage_bytes = 0;
     bool have_veff = false;
     NlocDev nl;
     double kvec[3] = {0, 0, 0};
     /* scratch owned by the host entry points */
     void *d_buf[3] = {nullptr, nullptr, nullptr};
-    void *d_buf2[3] = {nullptr, nullptr, nullptr}; /* second and third trio: dense-layout host pipeline (chunks rotate) */
+    void *d_buf2[3] = {nullptr, nullptr, nullptr}; /* second and third trio of the host pipeline (chunks rotate through three) */
     void *d_buf3[3] = {nullptr, nullptr, nullptr};
     size_t buf2_bytes = 0;
     size_t buf_bytes = 0;
@@ -130,8 +121,6 @@ struct chefsi_ctx {
     int force_general = 0;         /* 1: no TMA streaming kernel; 2: neither streaming nor z-march (3-D brick kernel only) */
     int stream_gridsync = 1;       /* round barrier between the streaming kernel's producers */
     int tma_l2promo = 3;           /* CUtensorMapL2promotion of the streaming kernel's tensor maps */
-    int dense_stream = 1;          /* 1: dense column layout + stencil_stream_dense.cu (default); 0: halo-padded layout */
-    int stream_variant = 3;        /* dense streaming kernel: 0 = 1 x 4 points per thread, 1 = 2 x 2 points, 3 = 2 x 2 + periodic-x strips merged into the tile by the spare producer-group warps (default) */
     unsigned int *d_sync = nullptr;
     unsigned int sync_arrivals = 0;
     char err[512] = {0};
@@ -152,10 +141,7 @@ bool stream_kpt_supported(const chefsi_ctx *ctx);
 int launch_stencil_stream_kpt(chefsi_ctx *ctx, const StepArgs &a);
 bool stencil_zmarch_supported(const chefsi_ctx *ctx);
 int launch_stencil_zmarch(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
-bool stream_layout_wanted(const chefsi_grid_t &g);
-bool stream_orth_supported(const chefsi_ctx *ctx, bool is_complex);
-int launch_stencil_stream_orth(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
-bool stream_dense_wanted(const chefsi_grid_t &g, int variant);
+bool stream_dense_supported(const chefsi_ctx *ctx, bool is_complex);
 int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a);
 
 /* nloc.cu: see launch_nloc for the three modes */
@@ -165,16 +151,8 @@ int nloc_padded_nproj(int max_nproj);
 int launch_alpha_reduce(chefsi_ctx *ctx, int ncol, bool is_complex);
 int nloc_ensure_alpha(chefsi_ctx *ctx, int ncol, bool is_complex); /* (re)allocate the alpha buffers for ncol columns */
 
-int launch_nloc_halo_patch(chefsi_ctx *ctx, void *out, size_t ld, int ncol, bool is_complex);
-
 /* util.cu */
 int launch_fill_random(chefsi_ctx *ctx, void *buf, int ncol, long long first_col, unsigned long long seed,
                        bool is_complex);
-/* dense (ld_dense elements between columns, Nd used) <-> internal layout */
-int launch_pack(chefsi_ctx *ctx, const void *dense, size_t ld_dense, void *packed, int ncol, bool is_complex);
-int launch_unpack(chefsi_ctx *ctx, const void *packed, void *dense, size_t ld_dense, int ncol, bool is_complex);
-/* fill the halo pads of ncol columns: periodic images (times Bloch phase if complex) or zeros;
- * zero_only = 1 just clears them (scratch buffers on Dirichlet faces) */
-int launch_halo_prepare(chefsi_ctx *ctx, void *buf, int ncol, bool is_complex, int zero_only);
 
 #endif

@@ -18,8 +18,7 @@
  *     B  contract lanes <-> columns, warps <-> points: a lane keeps beta[NP] = scale*Gamma*alpha_prev and
  *                 acc[NP] in registers; per point one conflict-free LDS of V, NP/2 broadcast LDS.128 of
  *                 Chi, NP FMAs "expand" (v += Chi beta), NP FMAs "project" (acc += Chi v);
- *     C  scatter  lanes <-> points again, the updated tile goes back with coalesced stores, together
- *                 with the periodic images in the halo pads of the streaming layout.
+ *     C  scatter  lanes <-> points again, the updated tile goes back with coalesced stores.
  *   Modes: PROJECT (alpha of the input only), FUSED (expand with alpha_prev into `out`, then project the
  *   now final `out` for the NEXT Chebyshev step: one read + one write of the sphere points per step),
  *   EXPAND (last step / single H apply), EXPAND_ATOMIC (spheres overlap: FP64 atomics, no read).
@@ -66,7 +65,6 @@ struct NlocView {
     const double2 *img_phase;
     const int *atom_img_off, *atom_img;
     const double *alpha_sum; /* != NULL: per-atom sums of the partials (alpha_reduce_kernel), atom a at IP_displ[a] * ncol * WORDS */
-    int Nxp, Nyp, px, py, Nx, Ny, mirx, miry; /* halo-pad geometry (mirx/miry: periodic pads present) */
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,8 +83,6 @@ template <int NP, class SH> struct Smem {
     double V[SH::S][kCols][SH::kPitch];
     double chi[SH::S][SH::KP][NP];
     int pos[SH::S][SH::KP];
-    int mx[SH::S][SH::KP];
-    int my[SH::S][SH::KP];
 };
 
 /* vec: MODE_PROJECT -> the input block x (read only); otherwise the output block (read-modify-write).
@@ -179,17 +175,7 @@ nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__
         load_pos(k + 1);
         if (warp == 0) {
 #pragma unroll
-            for (int h = 0; h < H; h++) {
-                int mx = 0, my = 0;
-                if (ps[h] >= 0 && (nl.mirx | nl.miry)) {
-                    const int i = ps[h] % nl.Nxp - nl.px, j = (ps[h] / nl.Nxp) % nl.Nyp - nl.py;
-                    if (nl.mirx) { if (i < nl.px) mx = nl.Nx; else if (i >= nl.Nx - nl.px) mx = -nl.Nx; }
-                    if (nl.miry) { if (j < nl.py) my = nl.Ny * nl.Nxp; else if (j >= nl.Ny - nl.py) my = -nl.Ny * nl.Nxp; }
-                }
-                S.pos[buf][lane + 32 * h] = ps[h];
-                S.mx[buf][lane + 32 * h] = mx;
-                S.my[buf][lane + 32 * h] = my;
-            }
+            for (int h = 0; h < H; h++) S.pos[buf][lane + 32 * h] = ps[h];
         }
         if (MODE != MODE_EXPAND_ATOMIC) {
 #pragma unroll
@@ -263,7 +249,6 @@ nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__
                 const int pl = lane + 32 * h;
                 const int ps = S.pos[buf][pl];
                 if (ps < 0) continue;
-                const int mx = S.mx[buf][pl], my = S.my[buf][pl];
 #pragma unroll
                 for (int c = 0; c < kCPW; c++) {
                     const int cl = warp * kCPW + c;
@@ -275,8 +260,6 @@ nloc_kernel(const NlocView nl, const double *__restrict__ alpha_prev, double *__
                         atomicAdd(base + (size_t)ps * WORDS, v);
                     } else {
                         base[(size_t)ps * WORDS] = v;
-                        if (mx) base[(size_t)(ps + mx) * WORDS] = v;
-                        if (my) base[(size_t)(ps + my) * WORDS] = v;
                     }
                 }
             }
@@ -330,17 +313,6 @@ __global__ void alpha_reduce_kernel(const NlocView nl, const double *__restrict_
         for (int jj = nl.atom_img_off[atom]; jj < nl.atom_img_off[atom + 1]; jj++)
             acc += alpha[(size_t)nl.img_aoff[nl.atom_img[jj]] * rowlen + t];
         asum[(size_t)ip0 * rowlen + t] = acc;
-    }
-}
-
-template <int WORDS>
-__global__ void nloc_patch_kernel(double *__restrict__ out, const size_t ld, const int *__restrict__ src,
-                                  const int *__restrict__ dst, const int n)
-{
-    double *col = out + (size_t)blockIdx.y * ld * WORDS;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-#pragma unroll
-        for (int w = 0; w < WORDS; w++) col[(size_t)dst[t] * WORDS + w] = col[(size_t)src[t] * WORDS + w];
     }
 }
 
@@ -452,14 +424,12 @@ int launch_nloc(chefsi_ctx *ctx, int mode, void *vec, size_t ld, int ncol, doubl
     if (d.n_img == 0 || d.ntot == 0 || ncol <= 0) return 0;
     const int words = is_complex ? 2 : 1;
     if (ensure_alpha(ctx, ncol, words)) return -1;
-    const Layout &L = ctx->lay;
     NlocView v{d.IP_displ, d.gamma, d.img_atom, d.img_ndc, d.img_aoff, d.pos_off, d.chiT_off, d.grid_pos, d.chiT,
-               d.img_phase, d.atom_img_off, d.atom_img, nullptr,
-               L.Nxp, L.Nyp, L.px, L.py, L.Nx, L.Ny,
-               (L.px && !ctx->grid.BCx) ? 1 : 0, (L.py && !ctx->grid.BCy) ? 1 : 0};
+               d.img_phase, d.atom_img_off, d.atom_img, nullptr};
     int kmode = mode;
     if (mode == NLOC_FUSED && d.overlap) { chefsi_fail(ctx, "nloc: fused mode needs disjoint spheres"); return -1; }
     if (mode == NLOC_EXPAND && d.overlap) kmode = MODE_EXPAND_ATOMIC;
+    if (mode != NLOC_PROJECT) { ctx->stats.last_nloc_atomic = (kmode == MODE_EXPAND_ATOMIC); ctx->stats.last_alpha_reduced = 0; }
     const double *aprev = reinterpret_cast<const double *>(ctx->d_alpha[ctx->alpha_cur]);
     int n_extra = 0;
     if (mode != NLOC_PROJECT && d.max_parts > ctx->alpha_reduce_min) { /* consumers read per-atom sums instead of looping over many partials */
@@ -468,6 +438,7 @@ int launch_nloc(chefsi_ctx *ctx, int mode, void *vec, size_t ld, int ncol, doubl
             if (n_extra < 0) return -1;
         }
         v.alpha_sum = (const double *)ctx->d_alpha_sum;
+        ctx->stats.last_alpha_reduced = 1;
     }
     double *anext = reinterpret_cast<double *>(ctx->d_alpha[mode == NLOC_FUSED ? ctx->alpha_cur ^ 1 : ctx->alpha_cur]);
     double *p = reinterpret_cast<double *>(vec);
@@ -489,17 +460,4 @@ int launch_nloc(chefsi_ctx *ctx, int mode, void *vec, size_t ld, int ncol, doubl
     if (n < 0) return -1;
     if (mode == NLOC_FUSED) ctx->alpha_cur ^= 1;
     return n + n_extra;
-}
-
-int launch_nloc_halo_patch(chefsi_ctx *ctx, void *out, size_t ld, int ncol, bool is_complex)
-{
-    NlocDev &d = ctx->nl;
-    if (d.n_patch == 0 || ncol <= 0) return 0;
-    if (ncol > 65535) { chefsi_fail(ctx, "nloc patch: too many columns per call"); return -1; }
-    dim3 grid((unsigned)((d.n_patch + 255) / 256), (unsigned)ncol);
-    if (is_complex) nloc_patch_kernel<2><<<grid, 256, 0, ctx->stream>>>((double *)out, ld, d.patch_src, d.patch_dst, d.n_patch);
-    else nloc_patch_kernel<1><<<grid, 256, 0, ctx->stream>>>((double *)out, ld, d.patch_src, d.patch_dst, d.n_patch);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { chefsi_fail(ctx, "nloc patch launch: %s", cudaGetErrorString(e)); return -1; }
-    return 1;
 }

@@ -19,7 +19,7 @@
  *      three-term recurrence scaling (eigenSolver.c:763-768,787-794) before the single store.
  *
  * This is the catch-all path (small grids, odd sizes, non-orthogonal and k-point runs).  The
- * large orthogonal workload goes through stencil_stream_orth.cu instead.
+ * large orthogonal workload goes through stencil_stream_dense.cu instead.
  */
 #include "chefsi_internal.h"
 #include "cplx.cuh"

@@ -4,29 +4,29 @@
  *
  *   out = s1 * ( (-1/2 Lap + Veff + c) x ) - s2 * xprev          (FP64, radius-6 star stencil)
  *
- * Same job and same consumer arithmetic as stencil_stream_orth.cu (it replaces, per Chebyshev degree,
- * the reference's haloed copy + stencil_3axis_thread_radius6, lapVecRoutines.c:185-227 called from
- * :586, + the three scale/axpy/swap passes of ChebyshevFiltering, eigenSolver.c:764-768,787-794), but
- * the columns are stored exactly as the reference stores them (x fastest, no halo pads), so
- *   - the DRAM traffic of a step is the algorithmic 24 B per grid point plus halo misses -- the padded
- *     layout read 18 % pad bytes with every plane and wrote the periodic images back;
- *   - nothing has to be packed, unpacked or patched around the step (util.cu pack/halo kernels and the
- *     image stores of the projector kernel drop out).
+ * It replaces, per Chebyshev degree, the reference's haloed copy + stencil_3axis_thread_radius6
+ * (lapVecRoutines.c:185-227 called from :586) + the three scale/axpy/swap passes of ChebyshevFiltering
+ * (eigenSolver.c:764-768,787-794).  The columns are stored exactly as the reference stores them (x fastest, no
+ * halo pads), so the DRAM traffic of a step is the algorithmic 24 B per grid point plus halo misses and nothing
+ * has to be packed, unpacked or patched around the step.
  *
- * What replaces the pads: the haloed (TX+12+2) x (8+TY+6) tile of a plane is still fetched by TMA, but
+ * 2.5-D streaming: one persistent CTA per SM; a work item is (column, 32 x 32 xy-tile); the CTA marches the whole
+ * z extent.  A producer lane streams per z-plane the haloed (TX+12+2) x (8+TY+6) tile of the input, the Veff tile
+ * and the xprev tile of the plane that completes 6 planes later by TMA into a 5-stage shared-memory ring with
+ * full / empty mbarriers; the consumer warps keep z in registers (the last 6 input planes and 7 partial outputs
+ * of their 2 x 2 points).  Halos without pads:
  *   - Dirichlet faces and tile parts outside the grid come from the TMA out-of-bounds zero fill;
  *   - a periodic y face splits the tile into up to three boxes (top halo rows / body / bottom halo rows)
  *     whose y coordinates are wrapped separately; they land in consecutive rows of the same shared tile
  *     (8 top rows instead of 6 keep every box start 128-byte aligned);
- *   - a periodic x face adds a 10-column strip box from the other side of the grid; the consumer
- *     threads whose +-6 window crosses the face read those 16-byte chunks from the strip through
- *     per-thread offsets computed once per work item (6 registers, 6 integer adds per plane).
+ *   - a periodic x face adds a 10-column strip box from the other side of the grid, which the three spare
+ *     warps of the producer warpgroup copy into the zero-filled halo columns of the landed tile before they
+ *     hand the stage to the consumers (so every x window is read with constant offsets).
  * Tiles never hang over the grid edge: the last tile of a row/column is shifted inwards (x0 = Nx - TX)
  * and the threads that would recompute its neighbour's points are masked.
- *
- * Everything else (persistent CTA per SM, producer warp + 5-stage mbarrier ring, 4 points per thread,
- * z in registers, round barrier between producers so xy-halos hit L2) is as described in
- * stencil_stream_orth.cu and DESIGN.md section 4.
+ * The producers of all CTAs pass a round barrier (global counter) before each item, so neighbouring tiles of a
+ * column are marched at the same z and their xy-halos hit in L2 (DRAM reads 13.9 -> 10.8 GB per launch).
+ * See DESIGN.md section 4 for the measurements behind each choice.
  */
 #include <cuda.h>
 
@@ -86,117 +86,16 @@ struct DenseMaps {
     CUtensorMap veff;     /* XP x TY                                               */
 };
 
-/* ---- one plane step of a consumer thread -------------------------------------------------- */
-/* U = (p + 7) mod 7 (compile time): register-queue rotation by renaming.                      */
-template <class Cfg, int U>
-__device__ __forceinline__ void consume_plane(const DenseDesc &d, const StepArgs &a, const unsigned char *stage, int p,
-                                              bool active, int qx, int ry, const int (&xo)[6], double *__restrict__ out_row,
-                                              size_t plane_elems, double (&in)[7][4], double (&acc)[7][4], bool plane_is_zero)
-{
-    const int Nz = d.Nz;
-    const bool interior = (p >= 0) && (p < Nz);
-    const int o = p - R;
-    const bool emit = active && o >= 0 && o < Nz;
-    const double *ytile = reinterpret_cast<const double *>(stage);
-    const double *vtile = reinterpret_cast<const double *>(stage + Cfg::OFF_V);
-    const double *xtile = reinterpret_cast<const double *>(stage + Cfg::OFF_X);
-
-    double v[4] = {0, 0, 0, 0};
-    if (active && !plane_is_zero) {
-        const double *rowp = ytile + (ry + HT) * Cfg::YP + 4 * qx; /* haloed row, element 0 = x0-6+4qx */
-        if (interior) {
-            double xr[16];
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                /* chunks 0..2 / 5..7 may lie across a periodic x face: their address was resolved per item */
-                const double2 w = (t == 3 || t == 4) ? *reinterpret_cast<const double2 *>(rowp + 2 * t)
-                                                     : *reinterpret_cast<const double2 *>(stage + xo[t < 3 ? t : t - 2]);
-                xr[2 * t] = w.x;
-                xr[2 * t + 1] = w.y;
-            }
-            double ve[4] = {0, 0, 0, 0};
-            if (a.veff) {
-                const double2 w0 = *reinterpret_cast<const double2 *>(vtile + ry * Cfg::XP + 4 * qx);
-                const double2 w1 = *reinterpret_cast<const double2 *>(vtile + ry * Cfg::XP + 4 * qx + 2);
-                ve[0] = w0.x; ve[1] = w0.y; ve[2] = w1.x; ve[3] = w1.y;
-            }
-            double t4[4], sx[4], sy[4], sz[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                v[j] = xr[R + j];
-                t4[j] = (d.coef0 + a.c + ve[j]) * v[j];
-                sx[j] = d.wx[1] * (xr[R + j - 1] + xr[R + j + 1]);
-                sz[j] = d.wz[1] * in[(U - 1 + 7) % 7][j];
-            }
-#pragma unroll
-            for (int r = 2; r <= R; r++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    sx[j] = fma(d.wx[r], xr[R + j - r] + xr[R + j + r], sx[j]);
-                    sz[j] = fma(d.wz[r], in[(U - r + 7) % 7][j], sz[j]);
-                }
-#pragma unroll
-            for (int r = 1; r <= R; r++) {
-                const double2 u0 = *reinterpret_cast<const double2 *>(rowp - r * Cfg::YP + R);
-                const double2 u1 = *reinterpret_cast<const double2 *>(rowp - r * Cfg::YP + R + 2);
-                const double2 d0 = *reinterpret_cast<const double2 *>(rowp + r * Cfg::YP + R);
-                const double2 d1 = *reinterpret_cast<const double2 *>(rowp + r * Cfg::YP + R + 2);
-                if (r == 1) {
-                    sy[0] = d.wy[1] * (u0.x + d0.x);
-                    sy[1] = d.wy[1] * (u0.y + d0.y);
-                    sy[2] = d.wy[1] * (u1.x + d1.x);
-                    sy[3] = d.wy[1] * (u1.y + d1.y);
-                } else {
-                    sy[0] = fma(d.wy[r], u0.x + d0.x, sy[0]);
-                    sy[1] = fma(d.wy[r], u0.y + d0.y, sy[1]);
-                    sy[2] = fma(d.wy[r], u1.x + d1.x, sy[2]);
-                    sy[3] = fma(d.wy[r], u1.y + d1.y, sy[3]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[U][j] = (t4[j] + sx[j]) + (sy[j] + sz[j]);
-        } else {
-            const double2 w0 = *reinterpret_cast<const double2 *>(rowp + R);
-            const double2 w1 = *reinterpret_cast<const double2 *>(rowp + R + 2);
-            v[0] = w0.x; v[1] = w0.y; v[2] = w1.x; v[3] = w1.y;
-        }
-    }
-    if (p >= 0) { /* scatter the z terms into the 6 accumulators behind this plane */
-#pragma unroll
-        for (int r = 1; r <= R; r++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[(U - r + 7) % 7][j] = fma(d.wz[r], v[j], acc[(U - r + 7) % 7][j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) in[U][j] = v[j];
-
-    if (emit) {
-        double res[4];
-        if (a.s2 != 0.0) {
-            const double2 w0 = *reinterpret_cast<const double2 *>(xtile + ry * Cfg::XP + 4 * qx);
-            const double2 w1 = *reinterpret_cast<const double2 *>(xtile + ry * Cfg::XP + 4 * qx + 2);
-            res[0] = fma(-a.s2, w0.x, a.s1 * acc[(U + 1) % 7][0]);
-            res[1] = fma(-a.s2, w0.y, a.s1 * acc[(U + 1) % 7][1]);
-            res[2] = fma(-a.s2, w1.x, a.s1 * acc[(U + 1) % 7][2]);
-            res[3] = fma(-a.s2, w1.y, a.s1 * acc[(U + 1) % 7][3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) res[j] = a.s1 * acc[(U + 1) % 7][j];
-        }
-        stg256(out_row + (size_t)o * plane_elems, res);
-    }
-}
-
-/* ---- 2 x 2 thread tile (VAR 1) ---------------------------------------------------------------
+/* ---- one plane step of a consumer thread: 2 x 2 thread tile ------------------------------------
+ * U = (p + 7) mod 7 (compile time): register-queue rotation by renaming.
  * A thread owns the x pair (2 xp, 2 xp + 1) of rows r0 and r0 + 1 (point index 2*row + j).  Per plane it
  * reads 2 x 7 chunks for the two x windows, 12 chunks for the rows r0-6 .. r0-1 and r0+2 .. r0+7 (each
- * halo row serves both output rows) and 2 + 2 chunks of Veff / xprev: 30 LDS.128 per 4 points instead of
- * the 36 of the 1 x 4 mapping.  A quarter warp reads 8 consecutive chunks of one row: conflict free for
- * any pitch.  xmask bit q set: chunk q of the x window lies in a periodic-x strip (row pitch SW).      */
-template <class Cfg, int U, bool MERGED>
+ * halo row serves both output rows) and 2 + 2 chunks of Veff / xprev: 30 LDS.128 per 4 points.  A quarter
+ * warp reads 8 consecutive chunks of one row: conflict free for any pitch.                            */
+template <class Cfg, int U>
 __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepArgs &a, const unsigned char *stage, int p,
-                                                bool active, bool act0, bool act1, int xp, int r0, const int (&xo)[6],
-                                                unsigned xmask, double *__restrict__ out_row, size_t plane_elems,
+                                                bool active, bool act0, bool act1, int xp, int r0,
+                                                double *__restrict__ out_row, size_t plane_elems,
                                                 double (&in)[7][4], double (&acc)[7][4], bool plane_is_zero)
 {
     const int Nz = d.Nz;
@@ -214,17 +113,9 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
             double xr[2][14];
 #pragma unroll
             for (int t = 0; t < 7; t++) {
-                double2 w0, w1;
-                if (t == 3 || MERGED) { /* MERGED: the strips were copied into the tile's halo columns */
-                    w0 = *reinterpret_cast<const double2 *>(cp + 2 * (t - 3));
-                    w1 = *reinterpret_cast<const double2 *>(cp + 2 * (t - 3) + Cfg::YP);
-                } else {
-                    const int q = t < 3 ? t : t - 1;
-                    const int off0 = xo[q];
-                    const int off1 = off0 + (((xmask >> q) & 1u) ? SW * 8 : Cfg::YP * 8);
-                    w0 = *reinterpret_cast<const double2 *>(stage + off0);
-                    w1 = *reinterpret_cast<const double2 *>(stage + off1);
-                }
+                /* the periodic-x strips were merged into the tile's halo columns: constant offsets */
+                const double2 w0 = *reinterpret_cast<const double2 *>(cp + 2 * (t - 3));
+                const double2 w1 = *reinterpret_cast<const double2 *>(cp + 2 * (t - 3) + Cfg::YP);
                 xr[0][2 * t] = w0.x; xr[0][2 * t + 1] = w0.y;
                 xr[1][2 * t] = w1.x; xr[1][2 * t + 1] = w1.y;
             }
@@ -234,8 +125,7 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
                 const double2 w1 = *reinterpret_cast<const double2 *>(vtile + (r0 + 1) * Cfg::XP + 2 * xp);
                 ve[0] = w0.x; ve[1] = w0.y; ve[2] = w1.x; ve[3] = w1.y;
             }
-            /* d.w*, d.coef0 carry the recurrence scale s1 (and the shift c) in this mapping, see launch_cfg:
-               40 FP64 instructions per point instead of 43 */
+            /* d.w*, d.coef0 carry the recurrence scale s1 (and the shift c), see launch_cfg: 40 FP64 instructions per point */
             double sx[4], sy[4], sz[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -308,7 +198,7 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
     }
 }
 
-template <int WX, int WY, int VAR>
+template <int WX, int WY>
 __global__ void __launch_bounds__(TileCfg<WX, WY>::THREADS, 1)
 stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constant__ DenseDesc d, const StepArgs a,
                     const int nitems, unsigned int *__restrict__ sync_counter, const unsigned int sync_base)
@@ -318,7 +208,7 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
     unsigned char *ring = smem_raw;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kStages * Cfg::STAGE_BYTES);
     uint64_t *empty = full + kStages;
-    uint64_t *landed = empty + kStages; /* VAR 3: TMA completion; the merge warps turn it into `full` */
+    uint64_t *landed = empty + kStages; /* TMA completion; the merge warps turn it into `full` */
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -339,7 +229,7 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
     if (warp >= Cfg::CONSUMER_WARPS) {
         /* ================= producer warpgroup (one elected lane issues the TMA boxes) ================= */
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::PRODUCER_REGS));
-        uint64_t *tb = (VAR == 3) ? landed : full; /* barrier the TMA boxes of a stage complete on */
+        uint64_t *tb = landed; /* barrier the TMA boxes of a stage complete on */
         if (warp == Cfg::CONSUMER_WARPS && lane == 0) {
             unsigned int round = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, round++) {
@@ -354,7 +244,10 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
                 const uint32_t ybytes = (uint32_t)(Cfg::YP * Cfg::YROWS * 8 + (need_l ? SW * Cfg::TY * 8 : 0) +
                                                    (need_r ? SW * Cfg::TY * 8 : 0));
                 if (sync_counter) {
-                    /* round barrier between the producers of all (co-resident) CTAs: see stencil_stream_orth.cu */
+                    /* round barrier between the producers of all (co-resident) CTAs: neighbouring tiles of a column are
+                       marched at the same z, so their xy-halos hit in L2.  A barrier that does not complete within
+                       ~2^22 polls (a CTA not resident: never with the cooperative launch) gives up -- the result is
+                       unaffected -- and says so in sync_counter[1], which chefsi_get_stats reports. */
                     const unsigned int in_round = (unsigned int)min((long long)gridDim.x, (long long)nitems - (long long)round * gridDim.x);
                     const unsigned int done_before = round * gridDim.x;
                     __threadfence();
@@ -362,6 +255,7 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
                     const unsigned int target = sync_base + done_before + in_round;
                     unsigned int spins = 0;
                     while ((int)(*(volatile unsigned int *)sync_counter - target) < 0 && ++spins < (1u << 22)) __nanosleep(64);
+                    if (spins >= (1u << 22)) atomicAdd(sync_counter + 1, 1u);
                 }
                 for (int p = -R; p < Nz + R; p++) {
                     int kz = p;
@@ -393,7 +287,7 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
                     it++;
                 }
             }
-        } else if (VAR == 3 && warp > Cfg::CONSUMER_WARPS) {
+        } else if (warp > Cfg::CONSUMER_WARPS) {
             /* ---- merge warps (the three spare warps of the producer warpgroup): same (item, plane) sequence as the
                producer lane; they copy the periodic-x strips of a landed stage into the zero-filled halo columns of
                its tile, so that the consumers read every x window with constant offsets ---- */
@@ -440,43 +334,20 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
     } else {
         /* ================= consumer warps ================= */
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
-        /* VAR 0: a thread owns 4 consecutive x of one row (qx: quad index, ry: row).
-           VAR 1: a thread owns a 2 x 2 patch (qx: x-pair index, ry: first of its two rows). */
-        int qx, ry;
-        if (VAR == 0) {
-            const int wx = warp % WX, wy = warp / WX;
-            qx = wx * 4 + (lane & 3);
-            ry = wy * 8 + (lane >> 2);
-        } else {
-            qx = lane & 15;
-            ry = warp * 4 + 2 * (lane >> 4);
-        }
+        /* a thread owns a 2 x 2 patch (qx: x-pair index, ry: first of its two rows) */
+        const int qx = lane & 15;
+        const int ry = warp * 4 + 2 * (lane >> 4);
         double in[7][4], acc[7][4];
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
             const int tx = tile % d.ntx, ty = tile / d.ntx;
             const int x0 = tile_origin(tx, Cfg::TX, Nx), y0 = tile_origin(ty, Cfg::TY, Ny);
-            const int gx = x0 + (VAR == 0 ? 4 : 2) * qx, gy = y0 + ry;
+            const int gx = x0 + 2 * qx, gy = y0 + ry;
             /* a shifted last tile overlaps its neighbour: only the not yet covered points are computed */
             const bool act0 = (gx >= tx * Cfg::TX) && (gy >= ty * Cfg::TY);
-            const bool act1 = (gx >= tx * Cfg::TX) && (gy + 1 >= ty * Cfg::TY); /* second row of a 2 x 2 patch */
-            const bool active = (VAR == 0) ? act0 : act1;
+            const bool act1 = (gx >= tx * Cfg::TX) && (gy + 1 >= ty * Cfg::TY); /* second row of the 2 x 2 patch */
+            const bool active = act1;
             double *out_row = reinterpret_cast<double *>(a.out) + (size_t)n * a.ld + (size_t)gy * Nx + gx;
-            /* byte offsets (inside a stage) of the 16-byte chunks of this thread's x window that may lie across a
-               periodic x face (VAR 0: chunks 0,1,2,5,6,7 of 8; VAR 1: chunks 0,1,2,4,5,6 of 7, first row) */
-            int xo[6];
-            unsigned xmask = 0;
-#pragma unroll
-            for (int q = 0; q < 6; q++) {
-                const int t = (VAR == 0) ? (q < 3 ? q : q + 2) : (q < 3 ? q : q + 1);
-                const int gi = gx - R + 2 * t;
-                int off = ((ry + HT) * Cfg::YP + (VAR == 0 ? 4 : 2) * qx + 2 * t) * 8;
-                if (xper) {
-                    if (gi < 0) { off = Cfg::OFF_L + (ry * SW + gi + SW) * 8; xmask |= 1u << q; }
-                    else if (gi >= Nx) { off = Cfg::OFF_R + (ry * SW + gi - Nx) * 8; xmask |= 1u << q; }
-                }
-                xo[q] = off;
-            }
 #pragma unroll
             for (int u = 0; u < 7; u++)
 #pragma unroll
@@ -494,11 +365,7 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
             stage = ring + (size_t)s * Cfg::STAGE_BYTES;                                                 \
             mbar_wait(&full[s], (it / kStages) & 1);                                                     \
         }                                                                                                \
-        if (VAR == 0)                                                                                    \
-            consume_plane<Cfg, (U)>(d, a, stage, pp, active, qx, ry, xo, out_row, plane_elems, in, acc, zplane); \
-        else                                                                                             \
-            consume_plane22<Cfg, (U), VAR == 3>(d, a, stage, pp, active, act0, act1, qx, ry, xo, xmask, out_row, \
-                                                plane_elems, in, acc, zplane);                           \
+        consume_plane22<Cfg, (U)>(d, a, stage, pp, active, act0, act1, qx, ry, out_row, plane_elems, in, acc, zplane); \
         if (use_stage) {                                                                                 \
             __syncwarp();                                                                                \
             if (lane == 0) mbar_arrive(&empty[s]);                                                       \
@@ -536,7 +403,7 @@ bool make_map(CUtensorMap *map, const void *base, const Layout &L, int ncol, int
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int WX, int WY, int VAR>
+template <int WX, int WY>
 int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
 {
     using Cfg = TileCfg<WX, WY>;
@@ -549,10 +416,9 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
     d.nty = (g.Ny + Cfg::TY - 1) / Cfg::TY;
     d.coef0 = ctx->desc.coef0;
     for (int r = 0; r <= R; r++) { d.wx[r] = ctx->desc.wx[r]; d.wy[r] = ctx->desc.wy[r]; d.wz[r] = ctx->desc.wz[r]; }
-    if (VAR >= 1) { /* the 2 x 2 mapping applies s1 (and c) through the weights: out = (s1 H') x - s2 xprev */
-        d.coef0 = a.s1 * (d.coef0 + a.c);
-        for (int r = 0; r <= R; r++) { d.wx[r] *= a.s1; d.wy[r] *= a.s1; d.wz[r] *= a.s1; }
-    }
+    /* s1 (and c) are applied through the weights: out = (s1 H') x - s2 xprev */
+    d.coef0 = a.s1 * (d.coef0 + a.c);
+    for (int r = 0; r <= R; r++) { d.wx[r] *= a.s1; d.wy[r] *= a.s1; d.wz[r] *= a.s1; }
     const long long nitems = (long long)a.ncol * d.ntx * d.nty;
     if (nitems > 0x7fffffffLL) { chefsi_fail(ctx, "stream kernel: too many work items"); return -1; }
 
@@ -566,8 +432,8 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
         chefsi_fail(ctx, "cuTensorMapEncodeTiled failed");
         return -1;
     }
-    static_assert(VAR == 0 || (Cfg::TX == 32 && Cfg::TY == 4 * Cfg::CONSUMER_WARPS && Cfg::CONSUMER_WARPS % 4 == 0), "2 x 2 mapping: 16 pairs x 4 rows per warp");
-    auto kern = stream_dense_kernel<WX, WY, VAR>;
+    static_assert(Cfg::TX == 32 && Cfg::TY == 4 * Cfg::CONSUMER_WARPS && Cfg::CONSUMER_WARPS % 4 == 0, "2 x 2 mapping: 16 pairs x 4 rows per warp");
+    auto kern = stream_dense_kernel<WX, WY>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(stream): %s", cudaGetErrorString(e)); return -1; }
     const int grid = (int)((nitems < ctx->num_sms) ? nitems : ctx->num_sms);
@@ -608,14 +474,16 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
 }  // namespace
 
 /* The dense streaming kernel needs: orthogonal cell, FD radius 6, real data, Nx even (a thread owns aligned x
- * pairs and TMA strides must be 16-byte multiples; the 1 x 4 mapping owns quads: Nx a multiple of 4), at least one full 32 x 32 tile
- * per plane, and -- for a periodic y face -- a tile row count such that no 6-row halo box straddles
- * the face (Ny mod 32 is 0 or >= 6).  Everything else goes through the general kernel. */
-bool stream_dense_wanted(const chefsi_grid_t &g, int variant)
+ * pairs and TMA strides must be 16-byte multiples), at least one full 32 x 32 tile per plane, and -- for a periodic
+ * y face -- a tile row count such that no 6-row halo box straddles the face (Ny mod 32 is 0 or >= 6).  Everything
+ * else goes through the z-march kernels. */
+bool stream_dense_supported(const chefsi_ctx *ctx, bool is_complex)
 {
     using Cfg = TileCfg<2, 4>;
+    const chefsi_grid_t &g = ctx->grid;
+    if (ctx->force_general || is_complex) return false;
     if (g.cell_typ != 0 || g.FDn != R) return false;
-    if (g.Nx % (variant == 0 ? 4 : 2) != 0) return false;
+    if (g.Nx % 2 != 0) return false;
     if (g.Nx < Cfg::TX || g.Ny < Cfg::TY || g.Nz < 2 * R) return false;
     if (g.BCy == 0 && g.Ny % Cfg::TY != 0 && g.Ny % Cfg::TY < R) return false;
     return true;
@@ -624,7 +492,5 @@ bool stream_dense_wanted(const chefsi_grid_t &g, int variant)
 int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a)
 {
     if (a.ncol <= 0) return 0;
-    if (ctx->stream_variant == 0) return launch_cfg<2, 4, 0>(ctx, a);
-    if (ctx->stream_variant == 1) return launch_cfg<2, 4, 1>(ctx, a);
-    return launch_cfg<2, 4, 3>(ctx, a);
+    return launch_cfg<2, 4>(ctx, a);
 }

@@ -282,7 +282,7 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
                 const bool need_l = xper && (x0 - R < 0), need_r = xper && (x0 + TXC + R > Nx);
                 const uint32_t ybytes = (uint32_t)(Cfg::YP * Cfg::YROWS * 8 + (need_l ? Cfg::SP * TY * 8 : 0) +
                                                    (need_r ? Cfg::SP * TY * 8 : 0));
-                if (sync_counter) { /* round barrier between the producers of all CTAs: see stencil_stream_orth.cu */
+                if (sync_counter) { /* round barrier between the producers of all CTAs: see stencil_stream_dense.cu */
                     const unsigned int in_round = (unsigned int)min((long long)gridDim.x, (long long)nitems - (long long)round * gridDim.x);
                     const unsigned int done_before = round * gridDim.x;
                     __threadfence();
@@ -290,6 +290,7 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
                     const unsigned int target = sync_base + done_before + in_round;
                     unsigned int spins = 0;
                     while ((int)(*(volatile unsigned int *)sync_counter - target) < 0 && ++spins < (1u << 22)) __nanosleep(64);
+                    if (spins >= (1u << 22)) atomicAdd(sync_counter + 1, 1u); /* gave up: reported by chefsi_get_stats */
                 }
                 for (int p = -R; p < Nz + R; p++) {
                     int kz = p;
@@ -427,8 +428,7 @@ bool make_map(CUtensorMap *map, const void *base, const Layout &L, int words, in
 bool stream_kpt_supported(const chefsi_ctx *ctx)
 {
     const chefsi_grid_t &g = ctx->grid;
-    if (ctx->force_general || !ctx->dense_stream || ctx->stream_variant == 0) return false;
-    if (ctx->lay.px || ctx->lay.py) return false;
+    if (ctx->force_general) return false;
     if (g.cell_typ != 0 || g.FDn != R) return false;
     if (g.Nx % 2 != 0) return false;
     if (g.Nx < TXC || g.Ny < TY || g.Nz < 2 * R) return false;

@@ -309,7 +309,7 @@ int launch_t(chefsi_ctx *ctx, const StepArgs &a)
 
 bool stencil_zmarch_supported(const chefsi_ctx *ctx)
 {
-    return ctx->force_general < 2 && ctx->grid.FDn == F && ctx->lay.px == 0 && ctx->lay.py == 0;
+    return ctx->force_general < 2 && ctx->grid.FDn == F;
 }
 
 int launch_stencil_zmarch(chefsi_ctx *ctx, const StepArgs &a, bool is_complex)

@@ -1,6 +1,6 @@
 /*
  * tma_ring.cuh -- the PTX building blocks shared by the TMA-streamed stencil kernels (stencil_stream_dense.cu,
- * stencil_stream_kpt.cu, stencil_stream_orth.cu): shared-memory mbarriers, the tiled TMA load that completes on
+ * stencil_stream_kpt.cu): shared-memory mbarriers, the tiled TMA load that completes on
  * one, vector stores, and the driver entry point that encodes tensor maps.  sm_100a.
  */
 #ifndef CHEFSI_TMA_RING_CUH

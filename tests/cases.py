@@ -25,6 +25,46 @@ def small_case(cell_typ=0, BC=(0, 0, 0), N=(14, 13, 15), L=(7.0, 6.5, 7.5), ncol
     return g, veff, proj, np.ascontiguousarray(x)
 
 
+def sphere_overlap_count(proj, Nd):
+    """Number of grid points that lie in more than one rc-sphere (image).  > 0 means the CUDA path must take
+    the unchained PROJECT / EXPAND_ATOMIC branch (nlocVecRoutines.c:866-881 scatter-adds overlapping spheres)."""
+    cnt = np.bincount(proj.grid_pos, minlength=Nd)
+    return int((cnt > 1).sum())
+
+
+# Overlapping rc-spheres (VERDICT r1 "weak" 1): two atoms closer than rc1 + rc2, an atom whose own periodic
+# images overlap (2 rc > cell length along one axis, so the reference's beta = 1 accumulation over images,
+# nlocVecRoutines.c:821-827, and its overlapping scatter-add, :866-881, both matter), and enough sphere points
+# per atom that the segmented alpha partials exceed alpha_reduce_min = 8 (alpha_reduce_kernel runs).
+OVERLAP_CASES = {
+    # name: (N, L, BC, cell_typ, frac, rc, nproj)
+    "general_small": ((14, 13, 15), (7.0, 6.5, 7.5), (0, 0, 0), 0,
+                      [[0.3, 0.4, 0.5], [0.45, 0.4, 0.5], [0.8, 0.1, 0.9]], [2.1, 1.7, 3.6], [5, 9, 18]),
+    "general_typ17": ((14, 13, 15), (7.0, 6.5, 7.5), (0, 0, 0), 17,
+                      [[0.3, 0.4, 0.5], [0.45, 0.4, 0.5], [0.8, 0.1, 0.9]], [2.1, 1.7, 3.4], [5, 9, 18]),
+    "stream": ((32, 32, 12), (14.4, 14.4, 5.4), (0, 0, 0), 0,
+               [[0.5, 0.5, 0.5], [0.58, 0.5, 0.5], [0.02, 0.97, 0.1]], [3.0, 2.0, 2.9], [18, 7, 13]),
+    "stream_dirichlet": ((32, 32, 16), (14.4, 14.4, 7.2), (1, 0, 1), 0,
+                         [[0.5, 0.5, 0.5], [0.6, 0.55, 0.5], [0.3, 0.02, 0.4]], [2.6, 2.2, 2.4], [18, 7, 13]),
+    "stream_26proj": ((32, 32, 12), (14.4, 14.4, 5.4), (0, 0, 0), 0,
+                      [[0.25, 0.5, 0.5], [0.3, 0.55, 0.45]], [2.9, 2.2], [26, 32]),
+}
+
+
+def overlap_case(name, complex_=False, ncol=3, seed=0):
+    N, L, BC, ct, frac, rc, nproj = OVERLAP_CASES[name]
+    if complex_ and name.startswith("stream"):
+        N = (N[0] // 2,) + tuple(N[1:])       # the k-point streaming kernel tiles 16 complex x 32
+        L = (L[0] / 2,) + tuple(L[1:])
+    g = P.make_grid(N, L, BC=BC, latvec=P.LATVEC_BY_CELL_TYP[ct])
+    veff = P.synthetic_veff(g)
+    proj = P.make_projectors(g, np.array(frac), rc=rc, nproj=nproj, seed=13)
+    x = P.random_columns(g.Nd, ncol, first_col=0, seed=seed + 31)
+    if complex_:
+        x = x + 1j * P.random_columns(g.Nd, ncol, first_col=1000, seed=seed + 31)
+    return g, veff, proj, np.ascontiguousarray(x)
+
+
 # (a, b, a0) used with the small cases: b above the spectrum of -1/2 Lap + Veff for h ~ 0.5
 BOUNDS = (0.5, 40.0, -0.6)
 
@@ -49,4 +89,8 @@ def load_golden(name):
 
 
 GOLDEN = ["orth_gamma", "orth_dirichlet_gamma", "si8lat_gamma", "orth_kpt", "si8lat_kpt", "type14_mixedbc_gamma",
-          "stream_gamma", "stream_kpt"]
+          "stream_gamma", "stream_kpt", "overlap_gamma", "overlap_kpt"]
+
+# dumps of real ChebyshevFiltering[_kpt] calls inside the reference's SCF runs of its own test systems (real psp8 Chi
+# tables, real Gamma, SCF Veff and bounds; tests/golden/make_sparc_dumps.py).  No Hx / c_shift entries.
+SPARC_GOLDEN = ["sparc_si8", "sparc_batio3", "sparc_si8_kpt"]

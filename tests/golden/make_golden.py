@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 
 from oracle.bindings import Reference  # noqa: E402
 from sparc_b200 import problem as P  # noqa: E402
-from tests.cases import BOUNDS, KVEC, small_case  # noqa: E402
+from tests.cases import BOUNDS, KVEC, overlap_case, small_case, sphere_overlap_count  # noqa: E402
 
 # grids: the small one exercises the general kernels, the two "stream_*" ones are large enough for the TMA
 # streaming kernels (real: >= 32 x 32 x 12, k-point: >= 16 x 32 x 12), so those are pinned to reference-made
@@ -35,19 +35,28 @@ CASES = {
     "orth_kpt": (0, (0, 0, 0), True, 6),
     "si8lat_kpt": (17, (0, 0, 0), True, 6),
     "type14_mixedbc_gamma": (14, (0, 1, 0), False, 5),
+    # overlapping rc-spheres (tests.cases.OVERLAP_CASES["stream"]): two atoms closer than rc1 + rc2, one atom whose
+    # own periodic images overlap along z, 9 alpha partials on one atom; sized for the TMA streaming kernels
+    "overlap_gamma": ("overlap:stream", None, False, 6),
+    "overlap_kpt": ("overlap:stream", None, True, 6),
 }
 
 
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
-    a, b, a0 = BOUNDS
     only = set(sys.argv[1:])
     for name, spec in CASES.items():
         if only and name not in only:
             continue
         ct, BC, cplx, m = spec[:4]
-        N, L = spec[4] if len(spec) > 4 else SMALL
-        g, veff, proj, x = small_case(ct, BC, N=N, L=L, ncol=2, complex_=cplx, seed=3)
+        if isinstance(ct, str) and ct.startswith("overlap:"):
+            g, veff, proj, x = overlap_case(ct.split(":")[1], complex_=cplx, ncol=2, seed=3)
+            assert sphere_overlap_count(proj, g.Nd) > 0
+            a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+        else:
+            N, L = spec[4] if len(spec) > 4 else SMALL
+            g, veff, proj, x = small_case(ct, BC, N=N, L=L, ncol=2, complex_=cplx, seed=3)
+            a, b, a0 = BOUNDS
         ref = Reference(g, proj, veff, kvec=KVEC)
         Hx = ref.hamiltonian_mult(-0.25, x)
         Xo, Yo = ref.chebyshev_filter(x, m, a, b, a0)

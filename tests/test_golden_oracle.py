@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from sparc_b200 import problem as P
-from tests.cases import GOLDEN, load_golden, rel_fro
+from tests.cases import GOLDEN, SPARC_GOLDEN, load_golden, rel_fro
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -19,6 +19,17 @@ def test_port_reproduces_reference_vectors(port, name):
     Xo, Yo = port.chebyshev_filter(g, proj, veff, d["X0"], int(d["m"]), a, b, a0, kvec=k)
     assert rel_fro(Yo, d["Y_out"]) < 1e-12
     assert rel_fro(Xo, d["X_out"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", SPARC_GOLDEN)
+def test_port_reproduces_real_sparc_filter_calls(port, name):
+    """One mid-SCF ChebyshevFiltering[_kpt] call of the reference's own Si8 / BaTiO3 / Si8_kpt runs (dumped at the
+    function's entry and exit): real pseudopotential projectors (BaTiO3: overlapping spheres)."""
+    g, veff, proj, d = load_golden(name)
+    a, b, a0 = d["bounds"]
+    Xo, Yo = port.chebyshev_filter(g, proj, veff, d["X0"], int(d["m"]), a, b, a0, kvec=tuple(d["kvec"]))
+    assert rel_fro(Yo, d["Y_out"]) < 1e-11
+    assert rel_fro(Xo, d["X_out"]) < 1e-11
 
 
 def _plane_wave(g, mvec, kfrac=(0, 0, 0)):

@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 from sparc_b200 import problem as P
-from tests.cases import BOUNDS, GOLDEN, KVEC, load_golden, rel_fro, small_case
+from tests.cases import (BOUNDS, GOLDEN, KVEC, OVERLAP_CASES, SPARC_GOLDEN, load_golden, overlap_case, rel_fro, small_case,
+                         sphere_overlap_count)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -19,21 +20,6 @@ TOL = 1e-10
 def ctx():
     from sparc_b200.chefsi import ChefsiContext
     c = ChefsiContext(0)
-    yield c
-    c.close()
-
-
-@pytest.fixture(scope="module")
-def ctx_padded():
-    """Context on the halo-padded column layout (stencil_stream_orth.cu; CHEFSI_B200_DENSE=0), the
-    first streaming kernel of round 1, kept selectable."""
-    import os
-    from sparc_b200.chefsi import ChefsiContext
-    os.environ["CHEFSI_B200_DENSE"] = "0"
-    try:
-        c = ChefsiContext(0)
-    finally:
-        del os.environ["CHEFSI_B200_DENSE"]
     yield c
     c.close()
 
@@ -62,6 +48,23 @@ def test_golden_vectors(ctx, name):
     assert rel_fro(X, d["X_out"]) < TOL
     if name.startswith("stream_"):  # the two fixtures sized for the TMA streaming kernels (real / k-point)
         assert ctx.stats()["last_path"] == 1
+
+
+@pytest.mark.parametrize("name", SPARC_GOLDEN)
+def test_real_sparc_filter_calls(ctx, name):
+    """Dumps of real ChebyshevFiltering[_kpt] calls from the reference's SCF runs of Si8 (cell_typ 17), BaTiO3
+    (orthogonal, 32 projectors on Ba, overlapping spheres) and Si8_kpt (complex, cell_typ 17): real psp8/spline Chi,
+    real Gamma, the SCF's Veff and bounds; outputs are the reference routine's own (tests/golden/make_sparc_dumps.py)."""
+    g, veff, proj, d = load_golden(name)
+    _setup(ctx, g, veff, proj, tuple(d["kvec"]))
+    a, b, a0 = d["bounds"]
+    X = np.ascontiguousarray(d["X0"]).copy()
+    Y = np.empty_like(X)
+    ctx.ChebyshevFiltering(X, Y, int(d["m"]), a, b, a0)
+    assert rel_fro(Y, d["Y_out"]) < TOL
+    assert rel_fro(X, d["X_out"]) < TOL
+    if name == "sparc_batio3":
+        assert ctx.stats()["last_nloc_atomic"] == 1   # real overlapping spheres: the scatter-add branch
 
 
 # ---------------------------------------------------------------- every cell type / BC vs the oracle
@@ -134,45 +137,61 @@ def test_fd_radius_four(ctx, port):
     assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, 0.1, x)) < TOL
 
 
-# ---------------------------------------------------------------- streaming orthogonal kernel
-@pytest.mark.parametrize("N,BC", [((32, 32, 24), (0, 0, 0)), ((48, 40, 20), (0, 0, 0)), ((36, 24, 16), (0, 0, 0)),
-                                   ((32, 32, 16), (1, 0, 1)), ((64, 32, 16), (0, 1, 0)), ((32, 16, 12), (1, 1, 1))])
-def test_stream_kernel_vs_oracle(ctx_padded, port, N, BC):
-    """Shapes that take the padded-layout streaming path (incl. ragged tiles, Dirichlet faces)."""
-    ctx = ctx_padded
-    g = P.make_grid(N, tuple(0.45 * n for n in N), BC=BC)
-    veff = P.synthetic_veff(g)
-    proj = P.make_projectors(g, np.array([[0.02, 0.5, 0.97], [0.5, 0.5, 0.5]]), rc=[2.4, 2.0], nproj=[18, 7])
-    x = P.random_columns(g.Nd, 3, seed=11)
-    _setup(ctx, g, veff, proj)
-    a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+# ---------------------------------------------------------------- overlapping rc-spheres
+@pytest.mark.parametrize("name", sorted(OVERLAP_CASES))
+@pytest.mark.parametrize("complex_", [False, True])
+def test_overlapping_spheres(ctx, port, name, complex_):
+    """Atoms closer than rc1 + rc2 and atoms whose own periodic images overlap: the unchained
+    PROJECT-per-step sequence with the FP64-atomic expand (nloc.cu MODE_EXPAND_ATOMIC) and, where an atom has
+    more than 8 alpha partials, alpha_reduce_kernel -- the branch Si8 and BaTiO3 take inside SPARC -- against
+    the oracle at 1e-10 (reference: beta = 1 accumulation over images nlocVecRoutines.c:821-827, overlapping
+    scatter-add :866-881)."""
+    g, veff, proj, x = overlap_case(name, complex_=complex_, ncol=5)
+    assert sphere_overlap_count(proj, g.Nd) > 0
+    kvec = tuple(kk if bc == 0 else 0.0 for kk, bc in zip(KVEC, g.BC))
+    _setup(ctx, g, veff, proj, kvec)
     Hx = np.empty_like(x)
     ctx.Hamiltonian_vectors_mult(-0.3, x, Hx)
-    assert ctx.stats()["last_path"] == 1
-    assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, -0.3, x)) < TOL
-    X = x.copy()
-    Y = np.empty_like(X)
-    ctx.ChebyshevFiltering(X, Y, 8, a, b, a0)
-    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 8, a, b, a0)
+    st = ctx.stats()
+    assert st["last_nloc_atomic"] == 1
+    assert st["last_path"] == (1 if name.startswith("stream") else 2)
+    if name in ("general_small", "general_typ17", "stream"):
+        assert st["last_alpha_reduced"] == 1   # 9 alpha partials on one atom
+    assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, -0.3, x, kvec=kvec)) < TOL
+    a, b, a0 = 0.5, (1.01 * g.max_eig_mhalf_lap() + 0.5) if g.cell_typ == 0 else 40.0, -0.6
+    X, Y = x.copy(), np.empty_like(x)
+    ctx.ChebyshevFiltering(X, Y, 9, a, b, a0)
+    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 9, a, b, a0, kvec=kvec)
     assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
 
 
-@pytest.fixture(scope="module", params=[3, 1, 0], ids=["map2x2_merged", "map2x2", "map1x4"])
-def ctx_dense(request):
-    """Context on the dense (reference) column layout: stencil_stream_dense.cu, both thread mappings
-    (2 x 2 points per thread = the default, 1 x 4 = the first version)."""
+def test_overlapping_spheres_many_columns(ctx, port):
+    """The overlapping-sphere branch on more than one 32-column projector group (70 columns) and with the
+    alpha partial threshold forced both ways."""
     import os
     from sparc_b200.chefsi import ChefsiContext
-    os.environ["CHEFSI_B200_DENSE"] = "1"
-    os.environ["CHEFSI_B200_STREAM_VARIANT"] = str(request.param)
-    try:
-        c = ChefsiContext(0)
-    finally:
-        del os.environ["CHEFSI_B200_DENSE"]
-        del os.environ["CHEFSI_B200_STREAM_VARIANT"]
-    c.variant = request.param
-    yield c
-    c.close()
+    g, veff, proj, x = overlap_case("stream", ncol=70)
+    a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 5, a, b, a0)
+    for thr in ("0", "1000"):
+        os.environ["CHEFSI_B200_ALPHA_REDUCE_MIN"] = thr
+        try:
+            c = ChefsiContext(0)
+        finally:
+            del os.environ["CHEFSI_B200_ALPHA_REDUCE_MIN"]
+        _setup(c, g, veff, proj)
+        X, Y = x.copy(), np.empty_like(x)
+        c.ChebyshevFiltering(X, Y, 5, a, b, a0)
+        assert c.stats()["last_alpha_reduced"] == (1 if thr == "0" else 0)
+        c.close()
+        assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+
+
+# ---------------------------------------------------------------- streaming orthogonal kernel
+@pytest.fixture(scope="module")
+def ctx_dense(ctx):
+    """The dense-layout TMA streaming kernel (stencil_stream_dense.cu) is the only real orthogonal streaming kernel."""
+    return ctx
 
 
 @pytest.mark.parametrize("N,BC", [((32, 32, 24), (0, 0, 0)), ((48, 40, 20), (0, 0, 0)), ((36, 38, 16), (0, 0, 0)),
@@ -182,7 +201,7 @@ def ctx_dense(request):
                                    ((38, 40, 12), (0, 0, 0)), ((70, 33, 12), (1, 1, 0)),
                                    ((34, 32, 12), (0, 0, 0)), ((36, 64, 12), (0, 0, 1))])
 def test_dense_stream_kernel_vs_oracle(ctx_dense, port, N, BC):
-    """Dense-layout streaming kernel: single tiles that wrap on both sides, shifted (overlapping) last
+    """Streaming kernel: single tiles that wrap on both sides, shifted (overlapping) last
     tiles, interior tiles (one TMA box), periodic-x strips, split periodic-y boxes, Dirichlet faces
     (TMA zero fill)."""
     ctx = ctx_dense
@@ -194,9 +213,7 @@ def test_dense_stream_kernel_vs_oracle(ctx_dense, port, N, BC):
     a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
     Hx = np.empty_like(x)
     ctx.Hamiltonian_vectors_mult(-0.3, x, Hx)
-    # Nx = 38, 70 (even, not a multiple of 4) stream only with the 2 x 2 mapping; the 1 x 4 mapping owns quads
-    expect_stream = 1 if (N[0] % 4 == 0 or ctx_dense.variant != 0) else 2   # 2: the z-march kernel takes it
-    assert ctx.stats()["last_path"] == expect_stream
+    assert ctx.stats()["last_path"] == 1
     assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, -0.3, x)) < TOL
     X = x.copy()
     Y = np.empty_like(X)
@@ -390,6 +407,42 @@ def test_full_size_plane_wave_and_linearity(ctx):
     Ys = np.empty_like(Xs)
     ctx.ChebyshevFiltering(Xs, Ys, m, a, b, a0)
     assert rel_fro(Ys[2], Ys[0] + 2.0 * Ys[1]) < TOL
+
+
+def test_bench_problem_parity(ctx, port):
+    """The exact bench.py workload (BASELINE.json configs[4]: 160^3, 864 Al atoms x 18 projectors = whole,
+    unsegmented sphere images, NP = 20 FUSED projector mode, degree 20) filtered inside ONE 128-column launch
+    group (> 148 work items: persistent CTAs, round barrier) through the device-resident entry point bench.py
+    times; three of its columns are compared with the reference's own ChebyshevFiltering (the compiled reference
+    when its prebuilt library travelled, else the C restatement)."""
+    import argparse
+    import torch
+    import bench
+    from oracle.bindings import Reference, reference_available
+    args = argparse.Namespace(grid=160, cell_typ=0, no_nloc=False, ncell=6)
+    g, veff, proj, (a, b, a0) = bench.build_problem(args)
+    assert proj.n_atom == 864 and proj.n_img >= 864
+    _setup(ctx, g, veff, proj)
+    ld, ncol, m = ctx.device_ld, 128, 20
+    first = bench.CPU_FIRST_COL
+    bufs = [torch.empty(ncol * ld, dtype=torch.float64, device="cuda") for _ in range(3)]
+    ctx.fill_random_device(bufs[0], ncol, first_col=first, seed=1)
+    ys, xs = ctx.filter_device(bufs[0], bufs[1], bufs[2], ncol, m, a, b, a0)
+    ctx.synchronize()
+    st = ctx.stats()
+    assert st["last_path"] == 1 and st["last_nloc_atomic"] == 0
+    cols = [0, 77, 127]
+    x = np.concatenate([P.random_columns(g.Nd, 1, first_col=first + k, seed=1) for k in cols])
+    if reference_available():
+        Xw, Yw = Reference(g, proj, veff).chebyshev_filter(x, m, a, b, a0)
+    else:
+        Xw, Yw = port.chebyshev_filter(g, proj, veff, x, m, a, b, a0)
+    for q, k in enumerate(cols):
+        y = bufs[ys][k * ld:k * ld + g.Nd].cpu().numpy()
+        xo = bufs[xs][k * ld:k * ld + g.Nd].cpu().numpy()
+        assert rel_fro(y, Yw[q]) < TOL and rel_fro(xo, Xw[q]) < TOL
+    del bufs
+    torch.cuda.empty_cache()
 
 
 def test_device_resident_entry_point_and_rng(ctx, port):

@@ -9,7 +9,7 @@ CUDA path is held to.
 import numpy as np
 import pytest
 
-from tests.cases import BOUNDS, KVEC, rel_fro, small_case
+from tests.cases import BOUNDS, KVEC, OVERLAP_CASES, overlap_case, rel_fro, small_case, sphere_overlap_count
 
 CELL_TYPES = [0, 11, 12, 13, 14, 15, 16, 17]
 BCS = [(0, 0, 0), (0, 1, 0), (1, 1, 1)]
@@ -83,3 +83,22 @@ def test_fd_radius_other_than_six(port, ref_cls):
         g, veff, proj, x = small_case(cell_typ, FDn=4)
         ref = ref_cls(g, proj, veff)
         assert rel_fro(port.hamiltonian_mult(g, proj, veff, 0.1, x), ref.hamiltonian_mult(0.1, x)) < TOL
+
+
+@pytest.mark.parametrize("name", sorted(OVERLAP_CASES))
+@pytest.mark.parametrize("complex_", [False, True])
+def test_overlapping_spheres(port, ref_cls, name, complex_):
+    """Overlapping rc-spheres: atoms closer than rc1 + rc2 and atoms whose own periodic images overlap.  The
+    reference accumulates the images of an atom into one alpha block with beta = 1 (nlocVecRoutines.c:821-827) and
+    scatter-adds every image's Chi alpha onto Hx (:866-881), so a grid point in two spheres receives both."""
+    g, veff, proj, x = overlap_case(name, complex_=complex_, ncol=2)
+    assert sphere_overlap_count(proj, g.Nd) > 0
+    kvec = tuple(kk if bc == 0 else 0.0 for kk, bc in zip(KVEC, g.BC))
+    ref = ref_cls(g, proj, veff, kvec=kvec)
+    want = ref.vnl_mult(x, np.zeros_like(x))
+    got = port.vnl_mult(g, proj, x, np.zeros_like(x), kvec=kvec)
+    assert rel_fro(got, want) < TOL
+    a, b, a0 = 0.5, (1.01 * g.max_eig_mhalf_lap() + 0.5) if g.cell_typ == 0 else 40.0, -0.6
+    Xr, Yr = ref.chebyshev_filter(x, 7, a, b, a0)
+    Xp, Yp = port.chebyshev_filter(g, proj, veff, x, 7, a, b, a0, kvec=kvec)
+    assert rel_fro(Yp, Yr) < 1e-12 and rel_fro(Xp, Xr) < 1e-12
