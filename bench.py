@@ -391,7 +391,7 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     achieved = alg_bytes / (st_ms * 1e-3) / 1e9 if st_ms > 0 else 0.0
     path = ctx.stats()["last_path"]
-    kname = {1: "stream_kpt_kernel" if cplx else "stream_dense_kernel", 2: "stencil_zmarch_kernel", 3: "stencil_mixed_stream_kernel"}.get(path, "stencil_general_kernel")
+    kname = {1: "stream_kpt_kernel" if cplx else "stream_dense_kernel", 2: "stencil_zmarch_kernel", 3: "stream_mixed_kernel"}.get(path, "stencil_general_kernel")
     traffic, traffic_src = ncu_traffic(kname, args.grid, block)
     roofline = {
         "bound": "hbm", "kernel": kname + " (fused stencil + Veff + recurrence)",

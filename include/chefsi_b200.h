@@ -181,7 +181,7 @@ typedef struct chefsi_stats {
     double last_stencil_ms;             /* summed device time of its stencil-step kernels  */
     double last_nloc_ms;                /* summed device time of its projector kernels     */
     int last_stencil_launches;
-    int last_path;                      /* 0 = 3-D brick kernel, 1 = TMA streaming kernel, 2 = z-march kernel */
+    int last_path;                      /* 0 = 3-D brick kernel, 1 = TMA streaming kernel (orthogonal), 2 = z-march kernel, 3 = TMA streaming kernel (non-orthogonal) */
     int last_nloc_atomic;               /* 1: the last projector expand took the overlapping-sphere branch      */
                                         /* (FP64 atomics, nlocVecRoutines.c:866-881 scatter-add)                */
     int last_alpha_reduced;             /* 1: per-atom alpha sums were formed by alpha_reduce_kernel            */

@@ -443,7 +443,11 @@ static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void
         ctx->stats.last_path = 1;
     } else {
         n = -2;
-        if (stencil_zmarch_supported(ctx)) {
+        if (stream_mixed_supported(ctx, is_complex)) {
+            n = launch_stencil_stream_mixed(ctx, a); /* -2: tables without the structure the kernel folds */
+            ctx->stats.last_path = 3;
+        }
+        if (n == -2 && stencil_zmarch_supported(ctx)) {
             n = launch_stencil_zmarch(ctx, a, is_complex); /* -2: this case does not fit (shared memory) */
             ctx->stats.last_path = 2;
         }

@@ -143,6 +143,8 @@ bool stencil_zmarch_supported(const chefsi_ctx *ctx);
 int launch_stencil_zmarch(chefsi_ctx *ctx, const StepArgs &a, bool is_complex);
 bool stream_dense_supported(const chefsi_ctx *ctx, bool is_complex);
 int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a);
+bool stream_mixed_supported(const chefsi_ctx *ctx, bool is_complex);
+int launch_stencil_stream_mixed(chefsi_ctx *ctx, const StepArgs &a); /* -2: coefficient tables without the expected structure */
 
 /* nloc.cu: see launch_nloc for the three modes */
 enum { NLOC_PROJECT = 0, NLOC_FUSED = 1, NLOC_EXPAND = 2 };

@@ -222,6 +222,46 @@ def test_dense_stream_kernel_vs_oracle(ctx_dense, port, N, BC):
     assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
 
 
+@pytest.mark.parametrize("cell_typ", [11, 12, 13, 14, 15, 16, 17])
+@pytest.mark.parametrize("N,BC", [((32, 32, 14), (0, 0, 0)), ((64, 40, 13), (0, 0, 0)), ((38, 70, 12), (0, 0, 0)),
+                                   ((32, 32, 16), (1, 0, 1)), ((36, 64, 12), (0, 1, 0)), ((40, 39, 12), (1, 1, 1)),
+                                   ((96, 32, 12), (0, 0, 1))])
+def test_mixed_stream_kernel_vs_oracle(ctx, port, cell_typ, N, BC):
+    """Non-orthogonal TMA streaming kernel (stencil_stream_mixed.cu): every mixed-derivative flavour (x-y in-plane
+    two-stage term through the per-warp D tile, x-z / y-z terms through the register z-queue), single tiles that wrap
+    on both sides (corner halos from the strips), shifted last tiles, interior tiles, Dirichlet faces, with
+    projectors; H apply and a degree-8 filter against the oracle's two-stage composition."""
+    g = P.make_grid(N, tuple(0.45 * n for n in N), BC=BC, latvec=P.LATVEC_BY_CELL_TYP[cell_typ])
+    assert g.cell_typ == cell_typ
+    veff = P.synthetic_veff(g)
+    proj = P.make_projectors(g, np.array([[0.02, 0.5, 0.97], [0.5, 0.5, 0.5]]), rc=[2.4, 2.0], nproj=[18, 7])
+    x = P.random_columns(g.Nd, 3, seed=17)
+    _setup(ctx, g, veff, proj)
+    Hx = np.empty_like(x)
+    ctx.Hamiltonian_vectors_mult(-0.3, x, Hx)
+    assert ctx.stats()["last_path"] == 3
+    assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, -0.3, x)) < TOL
+    a, b, a0 = 0.5, 150.0, -0.6
+    X, Y = x.copy(), np.empty_like(x)
+    ctx.ChebyshevFiltering(X, Y, 8, a, b, a0)
+    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, 8, a, b, a0)
+    assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+
+
+def test_mixed_stream_many_columns(ctx, port):
+    """More work items than SMs on the non-orthogonal streaming kernel (persistent CTAs, round barrier)."""
+    g = P.make_grid((64, 64, 12), (28.8, 28.8, 5.4), latvec=P.SI8_LATVEC)
+    veff = P.synthetic_veff(g)
+    x = P.random_columns(g.Nd, 80, seed=5)
+    _setup(ctx, g, veff, None)
+    a, b, a0 = 0.5, 150.0, -0.6
+    X, Y = x.copy(), np.empty_like(x)
+    ctx.ChebyshevFiltering(X, Y, 4, a, b, a0)
+    assert ctx.stats()["last_path"] == 3
+    Xw, Yw = port.chebyshev_filter(g, None, veff, x, 4, a, b, a0)
+    assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+
+
 @pytest.mark.parametrize("N,BC", [((16, 32, 12), (0, 0, 0)), ((32, 32, 16), (0, 0, 0)), ((40, 38, 14), (0, 0, 0)),
                                    ((48, 64, 12), (0, 0, 0)), ((18, 39, 13), (0, 0, 0)), ((34, 70, 12), (0, 0, 0)),
                                    ((32, 32, 16), (1, 0, 1)), ((36, 32, 12), (0, 1, 0)), ((32, 40, 12), (1, 1, 1)),
