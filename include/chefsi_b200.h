@@ -18,6 +18,8 @@
  *   chefsi_hamiltonian_mult        <- Hamiltonian_vectors_mult      src/hamiltonianVecRoutines.c:45-121
  *   chefsi_hamiltonian_mult_kpt    <- Hamiltonian_vectors_mult_kpt  src/hamiltonianVecRoutines.c:132-242
  *                                     (decl. src/include/hamiltonianVecRoutines.h:30-47)
+ *   chefsi_laplacian_mult[_kpt]    <- Lap_vec_mult[_kpt]            src/lapVecRoutines.c:37-58, src/lapVecRoutinesKpt.c
+ *                                     (the Laplacian of the Poisson residual, src/lapVecRoutines.c:61-79)
  *   chefsi_set_grid                <- the SPARC_OBJ fields read by Lap_plus_diag_vec_mult_{orth,nonorth}[_kpt]
  *                                     (src/lapVecRoutines.c:306,940; src/lapVecRoutinesKpt.c:179,567)
  *   chefsi_set_projectors          <- ATOM_NLOC_INFLUENCE_OBJ / NLOC_PROJ_OBJ / PSD_OBJ.Gamma / IP_displ
@@ -95,6 +97,17 @@ typedef struct chefsi_ctx chefsi_ctx_t;
 /* ---- lifetime ---------------------------------------------------------------------- */
 int chefsi_device_count(void); /* usable CUDA devices (0 when there is none or the driver is absent) */
 int chefsi_create(chefsi_ctx_t **ctx, int device);
+/* One context that owns `ndev` GPUs of a box (device ordinals in `devices`): SPARC's band-parallel axis inside one
+ * process (NP_BAND_PARAL = ndev, src/parallelization.c:403-428).  The host-buffer entry points split their columns
+ * NB = ceil(ncol / ndev) per device and run the devices concurrently; chefsi_set_veff / chefsi_set_projectors upload to
+ * the first device and replicate with ncclBroadcast over NVLink (Transfer_Veff_loc's MPI_Bcast,
+ * src/electronicGroundState.c:1313-1385); NCCL is loaded at run time, cudaMemcpyPeer is used when it is absent.
+ * The device-resident entry points take single-device contexts only. */
+int chefsi_create_multi(chefsi_ctx_t **ctx, const int *devices, int ndev);
+/* devices of the context (1 for a single-device context), whether the replication runs over NCCL, and the
+ * number / bytes of broadcasts so far */
+int chefsi_multi_info(const chefsi_ctx_t *ctx, int *ndev, int *uses_nccl, unsigned long long *bcast_calls,
+                      unsigned long long *bcast_bytes);
 void chefsi_destroy(chefsi_ctx_t *ctx);
 const char *chefsi_last_error(const chefsi_ctx_t *ctx);
 const char *chefsi_version(void);
@@ -117,6 +130,13 @@ int chefsi_hamiltonian_mult(chefsi_ctx_t *ctx, int ncol, double c, const double 
                             double *Hx, size_t ldo);
 int chefsi_hamiltonian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double c, const void *x,
                                 size_t ldi, void *Hx, size_t ldo);
+
+/* y = (a Lap + c) x: no potential, no projectors (Lap_vec_mult: Lap_plus_diag_vec_mult_* with b = 0, v = NULL,
+ * lapVecRoutines.c:37-58,321-322).  a must be non-zero.  Same kernels as the Hamiltonian apply. */
+int chefsi_laplacian_mult(chefsi_ctx_t *ctx, int ncol, double a, double c, const double *x, size_t ldi,
+                          double *y, size_t ldo);
+int chefsi_laplacian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double a, double c, const void *x, size_t ldi,
+                              void *y, size_t ldo);
 
 /* ---- device-resident entry points ---------------------------------------------------
  * Buffers are device pointers (256-byte aligned) holding ncol columns in the library's INTERNAL

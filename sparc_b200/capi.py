@@ -14,10 +14,10 @@ LIB_PATH = os.environ.get("CHEFSI_B200_LIB") or os.path.join(HERE, "libchefsi_b2
 
 # every symbol include/chefsi_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = (
-    "chefsi_device_count", "chefsi_create", "chefsi_destroy", "chefsi_last_error", "chefsi_version",
+    "chefsi_device_count", "chefsi_create", "chefsi_create_multi", "chefsi_multi_info", "chefsi_destroy", "chefsi_last_error", "chefsi_version",
     "chefsi_set_grid", "chefsi_set_projectors", "chefsi_set_veff", "chefsi_set_kpoint",
     "chefsi_chebyshev_filter", "chefsi_chebyshev_filter_kpt",
-    "chefsi_hamiltonian_mult", "chefsi_hamiltonian_mult_kpt",
+    "chefsi_hamiltonian_mult", "chefsi_hamiltonian_mult_kpt", "chefsi_laplacian_mult", "chefsi_laplacian_mult_kpt",
     "chefsi_device_ld",
     "chefsi_chebyshev_filter_device", "chefsi_chebyshev_filter_kpt_device",
     "chefsi_hamiltonian_mult_device", "chefsi_hamiltonian_mult_kpt_device",
@@ -63,6 +63,8 @@ def load_library() -> C.CDLL:
     ip = C.POINTER(C.c_int)
     lib.chefsi_device_count.argtypes = []
     lib.chefsi_create.argtypes = [C.POINTER(vp), i]
+    lib.chefsi_create_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i]
+    lib.chefsi_multi_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     lib.chefsi_destroy.argtypes = [vp]
     lib.chefsi_destroy.restype = None
     lib.chefsi_last_error.argtypes = [vp]
@@ -76,6 +78,8 @@ def load_library() -> C.CDLL:
         getattr(lib, name).argtypes = [vp, dp, sz, dp, sz, i, i, d, d, d, i]
     for name in ("chefsi_hamiltonian_mult", "chefsi_hamiltonian_mult_kpt"):
         getattr(lib, name).argtypes = [vp, i, d, dp, sz, dp, sz]
+    for name in ("chefsi_laplacian_mult", "chefsi_laplacian_mult_kpt"):
+        getattr(lib, name).argtypes = [vp, i, d, d, dp, sz, dp, sz]
     lib.chefsi_device_ld.argtypes = [vp]
     lib.chefsi_device_ld.restype = sz
     for name in ("chefsi_chebyshev_filter_device", "chefsi_chebyshev_filter_kpt_device"):

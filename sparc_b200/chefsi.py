@@ -52,13 +52,21 @@ class ChefsiContext:
 
     FLAG_NO_X_COPYBACK = 1
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """``device``: a CUDA ordinal, or a list of ordinals for one context that owns several GPUs
+        (``chefsi_create_multi``: columns of host blocks are split like SPARC's NP_BAND_PARAL)."""
         self._lib = capi.load_library()
         h = C.c_void_p()
-        if self._lib.chefsi_create(C.byref(h), int(device)) != 0:
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(v) for v in device])
+            rc = self._lib.chefsi_create_multi(C.byref(h), devs, len(device))
+            self.device = int(device[0])
+        else:
+            rc = self._lib.chefsi_create(C.byref(h), int(device))
+            self.device = int(device)
+        if rc != 0:
             raise capi.ChefsiError(self._lib.chefsi_last_error(None).decode())
         self._h = h
-        self.device = int(device)
         self.grid = None
         self._keep = []
 
@@ -121,6 +129,12 @@ class ChefsiContext:
 
     Hamiltonian_vectors_mult_kpt = Hamiltonian_vectors_mult
 
+    def Lap_vec_mult(self, c, x, Lapx, a=1.0):
+        """Lapx = (a Lap + c) x (src/lapVecRoutines.c:37: a = 1; no potential, no projectors)."""
+        ncol, ldi = x.shape
+        fn = self._lib.chefsi_laplacian_mult_kpt if _is_complex(x) else self._lib.chefsi_laplacian_mult
+        self._check(fn(self._h, ncol, float(a), float(c), _addr(x), ldi, _addr(Lapx), Lapx.shape[1]))
+
     # -- device-resident entry points -------------------------------------------------------------
     def filter_device(self, bufA, bufB, bufC, ncol, m, a, b, a0, is_complex=False):
         """Enqueue one filter on device buffers; returns (y_slot, x_slot) in {0,1,2}."""
@@ -172,6 +186,12 @@ class ChefsiContext:
         s = capi.ChefsiStats()
         self._check(self._lib.chefsi_get_stats(self._h, C.byref(s)))
         return {f: getattr(s, f) for f, _ in s._fields_}
+
+    def multi_info(self) -> dict:
+        nd, nccl = C.c_int(0), C.c_int(0)
+        calls, nbytes = C.c_ulonglong(0), C.c_ulonglong(0)
+        self._check(self._lib.chefsi_multi_info(self._h, C.byref(nd), C.byref(nccl), C.byref(calls), C.byref(nbytes)))
+        return {"devices": nd.value, "nccl": bool(nccl.value), "broadcasts": calls.value, "broadcast_bytes": nbytes.value}
 
     @property
     def stream(self) -> int:

@@ -88,12 +88,13 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
     ctx->force_general = getenv("CHEFSI_B200_FORCE_GENERAL") ? atoi(getenv("CHEFSI_B200_FORCE_GENERAL")) : 0;
     if (getenv("CHEFSI_B200_GRIDSYNC")) ctx->stream_gridsync = atoi(getenv("CHEFSI_B200_GRIDSYNC"));
     if (getenv("CHEFSI_B200_ALPHA_REDUCE_MIN")) ctx->alpha_reduce_min = atoi(getenv("CHEFSI_B200_ALPHA_REDUCE_MIN"));
+    if (getenv("CHEFSI_B200_FAST_SMALL")) ctx->fast_small = atoi(getenv("CHEFSI_B200_FAST_SMALL"));
     if (getenv("CHEFSI_B200_TMA_L2PROMO")) ctx->tma_l2promo = atoi(getenv("CHEFSI_B200_TMA_L2PROMO")) & 3;
     *out = ctx;
     return 0;
 }
 
-static void free_nloc(NlocDev &d)
+void chefsi_free_nloc(NlocDev &d)
 {
     cudaFree(d.IP_displ); cudaFree(d.gamma); cudaFree(d.img_atom); cudaFree(d.img_ndc);
     cudaFree(d.pos_off); cudaFree(d.chiT_off); cudaFree(d.grid_pos); cudaFree(d.chiT); cudaFree(d.img_aoff);
@@ -105,14 +106,16 @@ static void free_nloc(NlocDev &d)
 extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
 {
     if (!ctx) return;
+    if (ctx->multi) { multi_destroy(ctx); return; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    free_nloc(ctx->nl);
+    chefsi_free_nloc(ctx->nl);
     cudaFree(ctx->d_veff);
     for (int i = 0; i < 3; i++) { cudaFree(ctx->d_buf[i]); cudaFree(ctx->d_buf2[i]); cudaFree(ctx->d_buf3[i]); }
     cudaFree(ctx->d_alpha[0]);
     cudaFree(ctx->d_alpha[1]);
     cudaFree(ctx->d_alpha_sum);
+    for (int i = 0; i < 3; i++) if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
     for (int i = 0; i < 12; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     cudaFree(ctx->d_sync);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -160,6 +163,7 @@ static int update_nloc_phases(chefsi_ctx *ctx)
 extern "C" int chefsi_set_grid(chefsi_ctx_t *ctx, const chefsi_grid_t *g)
 {
     if (!ctx || !g) return 1;
+    if (ctx->multi) return multi_set_grid(ctx, g);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     if (g->FDn < 1 || g->FDn > CHEFSI_MAX_FDN) return chefsi_fail(ctx, "FDn %d out of range", g->FDn);
     if (!(g->cell_typ == 0 || (g->cell_typ >= 11 && g->cell_typ <= 17)))
@@ -229,7 +233,7 @@ extern "C" int chefsi_set_grid(chefsi_ctx_t *ctx, const chefsi_grid_t *g)
     ctx->have_veff = false;
     ctx->have_grid = true;
     /* projector tables refer to grid indices: drop them */
-    free_nloc(ctx->nl);
+    chefsi_free_nloc(ctx->nl);
     return 0;
 }
 
@@ -237,6 +241,7 @@ extern "C" int chefsi_set_kpoint(chefsi_ctx_t *ctx, double k1, double k2, double
 {
     if (!ctx) return 1;
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ctx->multi) return multi_set_kpoint(ctx, k1, k2, k3);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->kvec[0] = k1; ctx->kvec[1] = k2; ctx->kvec[2] = k3;
     update_phases(ctx);
@@ -247,6 +252,7 @@ extern "C" int chefsi_set_veff(chefsi_ctx_t *ctx, const double *veff_host)
 {
     if (!ctx) return 1;
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ctx->multi) return multi_set_veff(ctx, veff_host);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!veff_host) { ctx->have_veff = false; return 0; }
     CHEFSI_CUDA(ctx, cudaMemcpyAsync(ctx->d_veff, veff_host, ctx->Nd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -269,8 +275,9 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
 {
     if (!ctx) return 1;
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ctx->multi) return multi_set_projectors(ctx, nl);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
-    free_nloc(ctx->nl);
+    chefsi_free_nloc(ctx->nl);
     if (!nl || nl->n_img == 0 || nl->n_atom == 0) return 0;
     NlocDev &d = ctx->nl;
     d.n_atom = nl->n_atom;
@@ -363,6 +370,7 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
         if (upload(ctx, &d.chiT_off, soff.data(), soff.size())) return 1;
         if (upload(ctx, &d.img_aoff, aoff.data(), aoff.size())) return 1;
         if (upload(ctx, &d.chiT, chiT.data(), chiT.size())) return 1;
+        d.n_chiT = (long long)chiT.size();
     }
     if (upload(ctx, &d.atom_img_off, off.data(), off.size())) return 1;
     if (upload(ctx, &d.atom_img, lst.data(), lst.size())) return 1;
@@ -419,11 +427,11 @@ struct Profiler {
  *         fused projector kernel); otherwise they are computed here from x.
  * nl_out: after adding Vnl x, also project `out` for the next step (only legal when spheres are disjoint). */
 static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void *xprev, void *out, int ncol, double c,
-                      double s1, double s2, bool is_complex, bool nl_in, bool nl_out, bool with_nl = true)
+                      double s1, double s2, bool is_complex, bool nl_in, bool nl_out, bool with_nl = true, bool with_veff = true)
 {
     StepArgs a;
     a.x = x; a.xprev = xprev; a.out = out;
-    a.veff = ctx->have_veff ? ctx->d_veff : nullptr;
+    a.veff = (with_veff && ctx->have_veff) ? ctx->d_veff : nullptr;
     a.ld = ctx->ld; a.ncol = ncol; a.c = c; a.s1 = s1; a.s2 = s2;
     int n;
     const bool have_nl = with_nl && ctx->nl.n_img > 0 && ctx->nl.ntot > 0;
@@ -469,9 +477,12 @@ static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void
     return 0;
 }
 
+static const char kMultiDeviceApi[] = "device-resident entry points take a single-device context (a multi-device context splits HOST blocks)";
+
 static int filter_device(chefsi_ctx *ctx, void *bufs[3], int ncol, int m, double a, double b, double a0, bool is_complex,
                          int *y_slot, int *x_slot)
 {
+    if (ctx->multi) return chefsi_fail(ctx, kMultiDeviceApi);
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (m < 1) return chefsi_fail(ctx, "Chebyshev degree must be >= 1");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -520,6 +531,7 @@ extern "C" int chefsi_chebyshev_filter_kpt_device(chefsi_ctx_t *ctx, void *bufA,
 
 static int hmult_device(chefsi_ctx *ctx, int ncol, double c, const void *x, void *Hx, bool is_complex)
 {
+    if (ctx->multi) return chefsi_fail(ctx, kMultiDeviceApi);
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     Profiler prof(ctx);
@@ -539,6 +551,7 @@ extern "C" int chefsi_hamiltonian_mult_kpt_device(chefsi_ctx_t *ctx, int ncol, d
 extern "C" int chefsi_synchronize(chefsi_ctx_t *ctx)
 {
     if (!ctx) return 1;
+    if (ctx->multi) return multi_synchronize(ctx);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -585,6 +598,10 @@ static int ensure_bufs2(chefsi_ctx *ctx, size_t bytes_each)
  * alpha fit in the free device memory; large enough to fill the GPU */
 static int chunk_columns(chefsi_ctx *ctx, int ncol, size_t esz)
 {
+    /* a small block that fits the buffers this context already holds: no driver query (cudaMemGetInfo costs more
+       than a single-column H apply on an SCF-test-sized grid) */
+    if (ctx->fast_small && (size_t)ncol * ctx->Nd * esz <= ((size_t)64 << 20) && (size_t)ncol * ctx->ld * esz <= ctx->buf_bytes)
+        return ncol;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
     free_b += 3 * ctx->buf_bytes + 6 * ctx->buf2_bytes + 2 * ctx->alpha_bytes; /* what we already hold can be reused */
@@ -615,6 +632,49 @@ static int ensure_pipe_events(chefsi_ctx *ctx)
     return 0;
 }
 
+/* ---- pinned staging of small pageable blocks ---------------------------------------------------------------- */
+static const size_t kStageMax = (size_t)16 << 20;
+
+static bool host_is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+/* true when the call should stage: small block, pageable caller memory */
+static bool want_staging(chefsi_ctx *ctx, const void *h_in, const void *h_out, size_t bytes)
+{
+    if (!ctx->fast_small || bytes == 0 || bytes > kStageMax) return false;
+    if (!host_is_pageable(h_in) && !host_is_pageable(h_out)) return false;
+    if (ctx->h_pin_bytes < kStageMax) {
+        for (int i = 0; i < 3; i++)
+            if (cudaHostAlloc(&ctx->h_pin[i], kStageMax, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->h_pin[i] = nullptr; return false; }
+        ctx->h_pin_bytes = kStageMax;
+    }
+    return true;
+}
+/* host block (columns ldh_bytes apart) -> device block (columns pitch apart) through pinned slot `slot`, on ctx->stream */
+static int staged_h2d(chefsi_ctx *ctx, int slot, void *dev, size_t pitch, const void *host, size_t ldh_bytes, size_t row, int ncol)
+{
+    char *pin = (char *)ctx->h_pin[slot];
+    for (int n = 0; n < ncol; n++) memcpy(pin + (size_t)n * row, (const char *)host + (size_t)n * ldh_bytes, row);
+    if (pitch == row || ncol == 1) CHEFSI_CUDA(ctx, cudaMemcpyAsync(dev, pin, row * ncol, cudaMemcpyHostToDevice, ctx->stream));
+    else CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(dev, pitch, pin, row, row, ncol, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+static int staged_d2h_begin(chefsi_ctx *ctx, int slot, const void *dev, size_t pitch, size_t row, int ncol)
+{
+    char *pin = (char *)ctx->h_pin[slot];
+    if (pitch == row || ncol == 1) CHEFSI_CUDA(ctx, cudaMemcpyAsync(pin, dev, row * ncol, cudaMemcpyDeviceToHost, ctx->stream));
+    else CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(pin, row, dev, pitch, row, ncol, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+static void staged_d2h_finish(chefsi_ctx *ctx, int slot, void *host, size_t ldh_bytes, size_t row, int ncol)
+{
+    const char *pin = (const char *)ctx->h_pin[slot];
+    for (int n = 0; n < ncol; n++) memcpy((char *)host + (size_t)n * ldh_bytes, pin + (size_t)n * row, row);
+}
+
 /* after a failure in the middle of a pipelined call: no async copy may still be reading or writing the caller's
  * buffers when the call returns (the caller may free them), and the streams must be joinable for the next call */
 static int drain_streams(chefsi_ctx *ctx, int rc)
@@ -639,10 +699,28 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ncol <= 0) return 0;
     if (ldi < ctx->Nd || ldo < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
+    if (ctx->multi) return multi_filter_host(ctx, X, ldi, Y, ldo, ncol, m, a, b, a0, flags, is_complex);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
     const int chunk = chunk_columns(ctx, ncol, esz);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
+    if (chunk == ncol && want_staging(ctx, X, Y, (size_t)ncol * ctx->Nd * esz)) {
+        /* one small chunk in pageable memory: pinned staging, one stream, one synchronisation */
+        const size_t row = ctx->Nd * esz, pitch = ctx->ld * esz;
+        CHEFSI_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+        if (staged_h2d(ctx, 0, ctx->d_buf[0], pitch, X, ldi * esz, row, ncol)) return drain_streams(ctx, 1);
+        int ys = 1, xs = 0;
+        if (filter_device(ctx, ctx->d_buf, ncol, m, a, b, a0, is_complex, &ys, &xs)) return drain_streams(ctx, 1);
+        if (staged_d2h_begin(ctx, 1, ctx->d_buf[ys], pitch, row, ncol)) return drain_streams(ctx, 1);
+        if (!(flags & CHEFSI_FLAG_NO_X_COPYBACK) && staged_d2h_begin(ctx, 2, ctx->d_buf[xs], pitch, row, ncol)) return drain_streams(ctx, 1);
+        CHEFSI_CUDA_DRAIN(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+        CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
+        staged_d2h_finish(ctx, 1, Y, ldo * esz, row, ncol);
+        if (!(flags & CHEFSI_FLAG_NO_X_COPYBACK)) staged_d2h_finish(ctx, 2, X, ldi * esz, row, ncol);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.last_filter_ms = ms; else cudaGetLastError();
+        return 0;
+    }
     if (chunk < ncol && ensure_bufs2(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
     if (ensure_pipe_events(ctx)) return 1;
     cudaEvent_t *ev_h2d = ctx->pipe_ev, *ev_out = ctx->pipe_ev + 6, *ev_d2h = ctx->pipe_ev + 9;
@@ -715,11 +793,20 @@ static int hmult_host(chefsi_ctx *ctx, int ncol, double c, const void *x, size_t
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ncol <= 0) return 0;
     if (ldi < ctx->Nd || ldo < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
+    if (ctx->multi) return multi_hmult_host(ctx, ncol, c, x, ldi, Hx, ldo, is_complex);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
     const int chunk = chunk_columns(ctx, ncol, esz);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
     const size_t row = ctx->Nd * esz, pitch = ctx->ld * esz;
+    if (chunk == ncol && want_staging(ctx, x, Hx, (size_t)ncol * row)) {
+        if (staged_h2d(ctx, 0, ctx->d_buf[0], pitch, x, ldi * esz, row, ncol)) return drain_streams(ctx, 1);
+        if (hmult_device(ctx, ncol, c, ctx->d_buf[0], ctx->d_buf[1], is_complex)) return drain_streams(ctx, 1);
+        if (staged_d2h_begin(ctx, 1, ctx->d_buf[1], pitch, row, ncol)) return drain_streams(ctx, 1);
+        CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
+        staged_d2h_finish(ctx, 1, Hx, ldo * esz, row, ncol);
+        return 0;
+    }
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
         CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(ctx->d_buf[0], pitch, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
@@ -743,11 +830,66 @@ extern "C" int chefsi_hamiltonian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double c
     return ctx ? hmult_host(ctx, ncol, c, x, ldi, Hx, ldo, true) : 1;
 }
 
+/* ---- (a Lap + c) x: the operator of the Poisson residual ------------------------------------------------------
+ * Lap_vec_mult (src/lapVecRoutines.c:37-58) = Lap_plus_diag_vec_mult_{orth,nonorth} with b = 0, v = NULL
+ * (:321-322): no potential, no projectors.  The kernels evaluate s1 ((-1/2 Lap + c') x), so s1 = -2 a, c' = c / s1. */
+static int lapmult_host(chefsi_ctx *ctx, int ncol, double a, double c, const void *x, size_t ldi, void *y, size_t ldo,
+                        bool is_complex)
+{
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ncol <= 0) return 0;
+    if (a == 0.0) return chefsi_fail(ctx, "laplacian_mult: a must be non-zero");
+    if (ldi < ctx->Nd || ldo < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
+    if (ctx->multi) return multi_lapmult_host(ctx, ncol, a, c, x, ldi, y, ldo, is_complex);
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
+    const int chunk = chunk_columns(ctx, ncol, esz);
+    if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
+    const size_t row = ctx->Nd * esz, pitch = ctx->ld * esz;
+    const double s1 = -2.0 * a;
+    Profiler prof(ctx);
+    if (chunk == ncol && want_staging(ctx, x, y, (size_t)ncol * row)) {
+        if (staged_h2d(ctx, 0, ctx->d_buf[0], pitch, x, ldi * esz, row, ncol)) return drain_streams(ctx, 1);
+        if (apply_step(ctx, prof, ctx->d_buf[0], nullptr, ctx->d_buf[1], ncol, c / s1, s1, 0.0, is_complex, false, false,
+                       /*with_nl=*/false, /*with_veff=*/false))
+            return drain_streams(ctx, 1);
+        if (staged_d2h_begin(ctx, 1, ctx->d_buf[1], pitch, row, ncol)) return drain_streams(ctx, 1);
+        CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
+        staged_d2h_finish(ctx, 1, y, ldo * esz, row, ncol);
+        prof.finish();
+        return 0;
+    }
+    for (int c0 = 0; c0 < ncol; c0 += chunk) {
+        const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
+        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(ctx->d_buf[0], pitch, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
+                                                 cudaMemcpyHostToDevice, ctx->stream));
+        if (apply_step(ctx, prof, ctx->d_buf[0], nullptr, ctx->d_buf[1], nc, c / s1, s1, 0.0, is_complex, false, false,
+                       /*with_nl=*/false, /*with_veff=*/false))
+            return drain_streams(ctx, 1);
+        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync((char *)y + (size_t)c0 * ldo * esz, ldo * esz, ctx->d_buf[1], pitch, row, nc,
+                                                 cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
+    prof.finish();
+    return 0;
+}
+extern "C" int chefsi_laplacian_mult(chefsi_ctx_t *ctx, int ncol, double a, double c, const double *x, size_t ldi, double *y,
+                                     size_t ldo)
+{
+    return ctx ? lapmult_host(ctx, ncol, a, c, x, ldi, y, ldo, false) : 1;
+}
+extern "C" int chefsi_laplacian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double a, double c, const void *x, size_t ldi, void *y,
+                                         size_t ldo)
+{
+    return ctx ? lapmult_host(ctx, ncol, a, c, x, ldi, y, ldo, true) : 1;
+}
+
 /* ---- misc ---------------------------------------------------------------------------------------- */
 extern "C" int chefsi_fill_random_device(chefsi_ctx_t *ctx, void *buf, int ncol, long long first_col,
                                          unsigned long long seed, int is_complex)
 {
     if (!ctx) return 1;
+    if (ctx->multi) return chefsi_fail(ctx, kMultiDeviceApi);
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     const int n = launch_fill_random(ctx, buf, ncol, first_col, seed, is_complex != 0);
@@ -761,6 +903,7 @@ extern "C" int chefsi_pack_device(chefsi_ctx_t *ctx, const void *dense, size_t l
                                   int is_complex)
 {
     if (!ctx) return 1;
+    if (ctx->multi) return chefsi_fail(ctx, kMultiDeviceApi);
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ld_dense < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -774,6 +917,7 @@ extern "C" int chefsi_unpack_device(chefsi_ctx_t *ctx, const void *packed, void 
                                     int is_complex)
 {
     if (!ctx) return 1;
+    if (ctx->multi) return chefsi_fail(ctx, kMultiDeviceApi);
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ld_dense < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -788,7 +932,7 @@ extern "C" int chefsi_host_register(chefsi_ctx_t *ctx, void *ptr, size_t bytes)
 {
     if (!ctx || !ptr || !bytes) return 1;
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable); /* portable: every device of a multi-device context copies from it */
     if (e != cudaSuccess) { cudaGetLastError(); return chefsi_fail(ctx, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e)); }
     return 0;
 }
@@ -804,6 +948,7 @@ extern "C" int chefsi_get_stats(const chefsi_ctx_t *ctx, chefsi_stats_t *out)
 {
     if (!ctx || !out) return 1;
     *out = ctx->stats;
+    if (ctx->multi) return 0; /* the leader's copy is refreshed by every split call (sum of launches, max of times) */
     if (ctx->d_sync) { /* word 1 of the round-barrier block counts producers that gave up waiting */
         unsigned int t = 0;
         if (cudaSetDevice(ctx->device) == cudaSuccess &&
@@ -819,6 +964,7 @@ extern "C" int chefsi_stencil_step_device(chefsi_ctx_t *ctx, const double *x, co
                                           double c, double s1, double s2)
 {
     if (!ctx) return 1;
+    if (ctx->multi) return chefsi_fail(ctx, kMultiDeviceApi);
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     Profiler prof(ctx);
@@ -830,6 +976,7 @@ extern "C" int chefsi_stencil_step_device(chefsi_ctx_t *ctx, const double *x, co
 extern "C" int chefsi_nloc_project_device(chefsi_ctx_t *ctx, const double *x, int ncol, double *alpha_out)
 {
     if (!ctx || !alpha_out) return 1;
+    if (ctx->multi) return chefsi_fail(ctx, kMultiDeviceApi);
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ctx->nl.n_img == 0 || ctx->nl.ntot == 0) return chefsi_fail(ctx, "nloc_project: no projectors on this context");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -848,6 +995,7 @@ extern "C" int chefsi_nloc_project_device(chefsi_ctx_t *ctx, const double *x, in
 extern "C" int chefsi_nloc_expand_device(chefsi_ctx_t *ctx, double *out, int ncol, double scale, const double *alpha_in)
 {
     if (!ctx || !alpha_in) return 1;
+    if (ctx->multi) return chefsi_fail(ctx, kMultiDeviceApi);
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ctx->nl.n_img == 0 || ctx->nl.ntot == 0) return chefsi_fail(ctx, "nloc_expand: no projectors on this context");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -870,6 +1018,20 @@ extern "C" int chefsi_set_profiling(chefsi_ctx_t *ctx, int on)
 {
     if (!ctx) return 1;
     ctx->profiling = on;
+    if (ctx->multi) multi_set_profiling(ctx, on);
     return 0;
 }
 extern "C" void *chefsi_stream(chefsi_ctx_t *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int chefsi_multi_info(const chefsi_ctx_t *ctx, int *ndev, int *uses_nccl, unsigned long long *bcast_calls,
+                                 unsigned long long *bcast_bytes)
+{
+    if (!ctx) return 1;
+    if (ndev) *ndev = multi_size(ctx);
+    if (uses_nccl) *uses_nccl = multi_uses_nccl(ctx);
+    unsigned long long c = 0, b = 0;
+    multi_bcast_stats(ctx, &c, &b);
+    if (bcast_calls) *bcast_calls = c;
+    if (bcast_bytes) *bcast_bytes = b;
+    return 0;
+}

@@ -82,10 +82,14 @@ struct NlocDev {
     int *atom_img = nullptr;
     /* host copies needed to rebuild phases */
     double *h_img_coords = nullptr;
-    long long total_pts = 0;
+    long long total_pts = 0;      /* elements of grid_pos */
+    long long n_chiT = 0;         /* elements of chiT */
 };
 
+struct MultiState; /* multi.cu */
+
 struct chefsi_ctx {
+    MultiState *multi = nullptr; /* != NULL: a leader context that owns one single-device child per GPU (multi.cu) */
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -105,6 +109,12 @@ struct chefsi_ctx {
     void *d_buf3[3] = {nullptr, nullptr, nullptr};
     size_t buf2_bytes = 0;
     size_t buf_bytes = 0;
+    /* small blocks in pageable host memory (the SCF test systems; single columns of Lanczos / the Poisson residual) go
+       through these pinned staging buffers: one memcpy + one truly asynchronous copy instead of the driver's
+       pageable path */
+    void *h_pin[3] = {nullptr, nullptr, nullptr};
+    size_t h_pin_bytes = 0;
+    int fast_small = 1;
     void *d_alpha[2] = {nullptr, nullptr}; /* per-image alpha partials: [cur] belongs to the current input */
     int alpha_sum_external = 0;            /* 1: d_alpha_sum was produced by chefsi_nloc_project_device: expand must not rebuild it */
     int alpha_reduce_min = 8;              /* atoms with more alpha partials than this get them summed by alpha_reduce_kernel */
@@ -152,6 +162,23 @@ int launch_nloc(chefsi_ctx *ctx, int mode, void *vec, size_t ld, int ncol, doubl
 int nloc_padded_nproj(int max_nproj);
 int launch_alpha_reduce(chefsi_ctx *ctx, int ncol, bool is_complex);
 int nloc_ensure_alpha(chefsi_ctx *ctx, int ncol, bool is_complex); /* (re)allocate the alpha buffers for ncol columns */
+
+/* multi.cu: the leader context's side of every entry point it supports */
+int multi_size(const chefsi_ctx *lead);
+int multi_uses_nccl(const chefsi_ctx *lead);
+void multi_destroy(chefsi_ctx *lead);
+int multi_set_grid(chefsi_ctx *lead, const chefsi_grid_t *g);
+int multi_set_kpoint(chefsi_ctx *lead, double k1, double k2, double k3);
+int multi_set_veff(chefsi_ctx *lead, const double *veff_host);
+int multi_set_projectors(chefsi_ctx *lead, const chefsi_nloc_t *nl);
+int multi_filter_host(chefsi_ctx *lead, void *X, size_t ldi, void *Y, size_t ldo, int ncol, int m, double a, double b, double a0,
+                      int flags, bool is_complex);
+int multi_hmult_host(chefsi_ctx *lead, int ncol, double c, const void *x, size_t ldi, void *Hx, size_t ldo, bool is_complex);
+int multi_lapmult_host(chefsi_ctx *lead, int ncol, double a, double c, const void *x, size_t ldi, void *y, size_t ldo, bool is_complex);
+int multi_synchronize(chefsi_ctx *lead);
+void multi_set_profiling(chefsi_ctx *lead, int on);
+void multi_bcast_stats(const chefsi_ctx *lead, unsigned long long *calls, unsigned long long *bytes);
+void chefsi_free_nloc(NlocDev &d);
 
 /* util.cu */
 int launch_fill_random(chefsi_ctx *ctx, void *buf, int ncol, long long first_col, unsigned long long seed,

@@ -52,6 +52,9 @@ void Hamiltonian_vectors_mult_kpt_ref(const SPARC_OBJ *pSPARC, int DMnd, int *DM
                                       double c, double _Complex *x, const int ldi, double _Complex *Hx, const int ldo,
                                       int spin, int kpt, MPI_Comm comm);
 
+void Lap_vec_mult_ref(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c, double *x,
+                      const int ldi, double *Lapx, const int ldo, MPI_Comm comm);
+
 /* ------------------------------------------------------------------------------------------------ */
 static struct {
     chefsi_ctx_t *ctx;
@@ -64,7 +67,8 @@ static struct {
     /* host registration of the caller's orbital arrays (pinned for full-rate async copies) */
     struct { void *base; size_t bytes; } pinned[64];
     int npinned;
-    unsigned long long n_filter, n_hmult, n_forward;
+    unsigned long long n_filter, n_hmult, n_forward, n_lap;
+    double t_lap;
     double t_filter;
     double t_init, t_sync, t_hmult;  /* seconds in context creation, table/Veff synchronisation, H-apply calls */
     unsigned long long n_filter_fwd; /* ChebyshevFiltering calls forwarded to the reference, and their seconds */
@@ -91,8 +95,17 @@ static void shim_report(void)
                         "%llu calls forwarded to the reference (of which %llu ChebyshevFiltering calls, %.3f s)\n",
                 G.n_filter, G.t_filter, G.n_hmult, G.n_forward, G.n_filter_fwd, G.t_filter_fwd);
     if (G.verbose)
+        fprintf(stderr, "[chefsi_b200 shim] %llu Lap_vec_mult calls (Poisson residual, Kerker mixing, Lanczos of the Laplacian) %.3f s\n",
+                G.n_lap, G.t_lap);
+    if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] context creation %.3f s, Hamiltonian_vectors_mult calls %.3f s, grid/projector/Veff "
                         "synchronisation %.3f s (included in the call times)\n", G.t_init, G.t_hmult, G.t_sync);
+    if (G.ctx && G.verbose) {
+        int nd = 1, nccl = 0;
+        unsigned long long calls = 0, bytes = 0;
+        chefsi_multi_info(G.ctx, &nd, &nccl, &calls, &bytes);
+        if (nd > 1) fprintf(stderr, "[chefsi_b200 shim] %d devices, %llu broadcasts of Veff / projector tables (%.1f MB) over %s\n", nd, calls, bytes / 1e6, nccl ? "NCCL" : "cudaMemcpyPeer");
+    }
     if (G.ctx) { chefsi_destroy(G.ctx); G.ctx = NULL; }
 }
 
@@ -122,6 +135,26 @@ static void shim_init(void)
     if (!dev && lr && ndev > 0) device = atoi(lr) % ndev;
     shim_register_report();
     const double t_init0 = MPI_Wtime();
+    /* CHEFSI_B200_DEVICES="0,1,2,3": this rank owns several GPUs (SPARC's NP_BAND_PARAL axis inside one process,
+       SURVEY.md 8b "in the np=1 stub build one process may own all 8 GPUs"): the columns of every block are split over
+       them, Veff and the projector tables are replicated with an NCCL broadcast (chefsi_create_multi) */
+    const char *devs = getenv("CHEFSI_B200_DEVICES");
+    if (devs && strchr(devs, ',')) {
+        int list[64], n = 0;
+        char buf[256];
+        strncpy(buf, devs, sizeof(buf) - 1);
+        buf[sizeof(buf) - 1] = 0;
+        for (char *tok = strtok(buf, ","); tok && n < 64; tok = strtok(NULL, ",")) list[n++] = atoi(tok);
+        if (chefsi_create_multi(&G.ctx, list, n) != 0) {
+            fprintf(stderr, "[chefsi_b200 shim] cannot create the multi-GPU context (%s): %s\n", devs, chefsi_last_error(NULL));
+            exit(EXIT_FAILURE);
+        }
+        G.t_init += MPI_Wtime() - t_init0;
+        int nd = 0, nccl = 0;
+        chefsi_multi_info(G.ctx, &nd, &nccl, NULL, NULL);
+        if (G.verbose) fprintf(stderr, "[chefsi_b200 shim] %s on %d devices (%s), replication over %s\n", chefsi_version(), nd, devs, nccl ? "NCCL" : "cudaMemcpyPeer");
+        return;
+    }
     if (chefsi_create(&G.ctx, device) != 0) {
         fprintf(stderr, "[chefsi_b200 shim] cannot create the CUDA context: %s\n", chefsi_last_error(NULL));
         exit(EXIT_FAILURE);
@@ -495,6 +528,12 @@ void ChebyshevFiltering(SPARC_OBJ *pSPARC, int *DMVertices, double *X, int ldi, 
     *time_info = MPI_Wtime() - t1;
     G.n_filter++;
     G.t_filter += *time_info;
+    if (G.verbose > 1) {
+        chefsi_stats_t st;
+        chefsi_get_stats(G.ctx, &st);
+        fprintf(stderr, "[chefsi_b200 shim] ChebyshevFiltering #%llu: %d columns, degree %d: %.3f ms (device %.3f ms, kernel path %d)\n",
+                G.n_filter, ncol, m, 1e3 * *time_info, st.last_filter_ms, st.last_path);
+    }
 }
 
 void ChebyshevFiltering_kpt(SPARC_OBJ *pSPARC, int *DMVertices, double _Complex *X, int ldi, double _Complex *Y, int ldo,
@@ -582,4 +621,37 @@ void Hamiltonian_vectors_mult_kpt(const SPARC_OBJ *pSPARC, int DMnd, int *DMVert
     if (chefsi_hamiltonian_mult_kpt(G.ctx, ncol, c, x, (size_t)ldi, Hx, (size_t)ldo) != 0) shim_fatal("chefsi_hamiltonian_mult_kpt");
     G.n_hmult++;
     G.t_hmult += MPI_Wtime() - t1;
+}
+
+/* (Lap + c) x -- src/lapVecRoutines.c:37-58.  The Laplacian of the Poisson residual (poisson_residual :61-79, called by
+ * the AAR solver once per iteration), of the Kerker preconditioner (mixing.c:490) and of Lanczos on the Laplacian
+ * (eigenSolver.c:2212,2254): SURVEY.md 8f-4.  On the non-orthogonal test systems this operator, left on the CPU, was
+ * 80 % of the SCF wall time once the filter ran on the GPU (Au_fcc211: 5 447 calls x 3.5 ms). */
+void Lap_vec_mult(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c, double *x,
+                  const int ldi, double *Lapx, const int ldo, MPI_Comm comm)
+{
+    int why = 0;
+    if (getenv("CHEFSI_B200_DISABLE") || getenv("CHEFSI_B200_NO_LAP")) why = 1;
+    else if (!(pSPARC->cell_typ == 0 || (pSPARC->cell_typ >= 11 && pSPARC->cell_typ <= 17)) || pSPARC->CyclixFlag) why = 2;
+    else if (pSPARC->order / 2 > CHEFSI_MAX_FDN) why = 7;
+    else {
+        int nproc = 1;
+        MPI_Comm_size(comm, &nproc);
+        const int FDn = pSPARC->order / 2;
+        if (nproc != 1) why = 8;
+        else if (DMnd != pSPARC->Nd || DMVertices[0] != 0 || DMVertices[1] != pSPARC->Nx - 1 || DMVertices[2] != 0 ||
+                 DMVertices[3] != pSPARC->Ny - 1 || DMVertices[4] != 0 || DMVertices[5] != pSPARC->Nz - 1) why = 9;
+        else if ((pSPARC->BCx == 0 && pSPARC->Nx < FDn) || (pSPARC->BCy == 0 && pSPARC->Ny < FDn) || (pSPARC->BCz == 0 && pSPARC->Nz < FDn)) why = 11;
+    }
+    if (why) {
+        G.n_forward++;
+        Lap_vec_mult_ref(pSPARC, DMnd, DMVertices, ncol, c, x, ldi, Lapx, ldo, comm);
+        return;
+    }
+    shim_init();
+    const double t1 = MPI_Wtime();
+    shim_sync_grid(pSPARC);
+    if (chefsi_laplacian_mult(G.ctx, ncol, 1.0, c, x, (size_t)ldi, Lapx, (size_t)ldo) != 0) shim_fatal("chefsi_laplacian_mult");
+    G.n_lap++;
+    G.t_lap += MPI_Wtime() - t1;
 }

@@ -129,6 +129,25 @@ def test_no_projectors_no_veff_lanczos_style_call(ctx, port):
     assert rel_fro(Hx, port.hamiltonian_mult(g, None, veff, 0.0, x)) < TOL
 
 
+@pytest.mark.parametrize("cell_typ,N,BC,path", [(0, (14, 13, 15), (0, 0, 0), 2), (17, (14, 13, 15), (0, 1, 0), 2),
+                                                (0, (32, 32, 16), (0, 0, 0), 1), (0, (40, 39, 12), (1, 1, 1), 1),
+                                                (17, (32, 32, 14), (0, 0, 0), 3), (14, (64, 40, 13), (0, 0, 1), 3)])
+def test_lap_vec_mult(ctx, port, cell_typ, N, BC, path):
+    """Lap_vec_mult (lapVecRoutines.c:37-58): (Lap + c) x without potential and projectors -- the operator of the
+    Poisson residual / Kerker preconditioner -- on every stencil kernel, single column and a small block,
+    with a potential and projectors set on the context (they must not be applied)."""
+    g = P.make_grid(N, tuple(0.45 * n for n in N), BC=BC, latvec=P.LATVEC_BY_CELL_TYP[cell_typ])
+    veff = P.synthetic_veff(g)
+    proj = P.make_projectors(g, np.array([[0.3, 0.5, 0.6]]), rc=[2.0], nproj=[5])
+    _setup(ctx, g, veff, proj)
+    for ncol, c in ((1, 0.0), (3, -0.02)):
+        x = P.random_columns(g.Nd, ncol, seed=23)
+        y = np.empty_like(x)
+        ctx.Lap_vec_mult(c, x, y)
+        assert ctx.stats()["last_path"] == path
+        assert rel_fro(y, port.lap_plus_diag(g, 1.0, 0.0, c, None, x)) < TOL
+
+
 def test_fd_radius_four(ctx, port):
     g, veff, proj, x = small_case(17, FDn=4)
     _setup(ctx, g, veff, proj)

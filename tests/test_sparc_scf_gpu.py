@@ -58,3 +58,16 @@ def test_scf_energy_matches_reference(name, tmp_path):
           f"{n_filter} filter calls, {n_hmult} H applies on the GPU, {n_fwd} forwarded")
     assert n_filter > 0 and n_fwd == 0, "the CUDA path did not serve the filter calls"
     assert abs(e - e_ref) <= TOL_HA_PER_ATOM
+
+
+def test_scf_on_a_multi_device_context(tmp_path):
+    """SPARC + drop-in with one rank owning several GPUs (CHEFSI_B200_DEVICES): the shim creates a multi-device
+    context, every block's columns are split over the devices, Veff / projector tables are broadcast.  On a one-GPU box
+    the list names device 0 twice (same code path, peer copies instead of NCCL)."""
+    import torch
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    e, e_ref, log, out = run_case("BaTiO3", tmp_path, {"CHEFSI_B200_DEVICES": devs})
+    assert "on 2 devices" in log and "broadcasts of Veff" in log, log[-1500:]
+    m = re.search(r"(\d+) ChebyshevFiltering calls .*?(\d+) Hamiltonian_vectors_mult calls, (\d+) calls forwarded", log)
+    assert m and int(m.group(1)) > 0 and int(m.group(3)) == 0
+    assert abs(e - e_ref) <= TOL_HA_PER_ATOM
