@@ -93,6 +93,10 @@ typedef struct chefsi_ctx chefsi_ctx_t;
 /* flags for the filter entry points */
 #define CHEFSI_FLAG_NO_X_COPYBACK 1 /* host entry points: do not copy the clobbered X back   */
                                     /* (the caller reuses X as scratch, eigenSolver.c:364)   */
+#define CHEFSI_FLAG_KEEP_Y 2        /* keep Y = p_m(H) X0 on the device for chefsi_subspace_project / _rotate (real data,  */
+                                    /* single-device context; needs a successful chefsi_subspace_reserve)                  */
+#define CHEFSI_FLAG_NO_Y_COPYBACK 4 /* with KEEP_Y: do not copy Y to the host at all (the caller's next steps are           */
+                                    /* chefsi_subspace_project and chefsi_subspace_rotate, which read the device copy)      */
 
 /* ---- lifetime ---------------------------------------------------------------------- */
 int chefsi_device_count(void); /* usable CUDA devices (0 when there is none or the driver is absent) */
@@ -137,6 +141,20 @@ int chefsi_laplacian_mult(chefsi_ctx_t *ctx, int ncol, double a, double c, const
                           double *y, size_t ldo);
 int chefsi_laplacian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double a, double c, const void *x, size_t ldi,
                               void *y, size_t ldo);
+
+/* ---- Rayleigh-Ritz projection and subspace rotation with the block resident on the device -------
+ * Replaces, for real (Gamma-point) data on a single-device context:
+ *   chefsi_subspace_project <- DP_Project_Hamiltonian  src/eigenSolver.c:939-1086 (Project_Hamiltonian :1477-1669):
+ *                              HY = H Y (c = 0), Mp = Y^T Y, Hp = Y^T HY; Hp, Mp: ncol x ncol, column-major, ld = ldp (host)
+ *   chefsi_subspace_rotate  <- DP_Subspace_Rotation    src/eigenSolver.c:1386-1443 (Subspace_Rotation :1854-1918):
+ *                              X = Y Q, Q: ncol x ncol (host, ld = ldq), X: host block, ld = ldx
+ * The three GEMMs run on the FP64 tensor cores (DMMA); only Hp, Mp, Q and the rotated block cross PCIe.
+ * chefsi_subspace_reserve allocates the two resident blocks for `ncol` columns (fails when they do not fit).
+ * chefsi_subspace_project takes Y from the device when the last filter call kept it (CHEFSI_FLAG_KEEP_Y, same host
+ * address and column count), otherwise it uploads the host block. chefsi_subspace_rotate needs a preceding project. */
+int chefsi_subspace_reserve(chefsi_ctx_t *ctx, int ncol);
+int chefsi_subspace_project(chefsi_ctx_t *ctx, const double *Y, size_t ldy, int ncol, double *Hp, double *Mp, size_t ldp);
+int chefsi_subspace_rotate(chefsi_ctx_t *ctx, const double *Q, size_t ldq, int ncol, double *X, size_t ldx);
 
 /* ---- device-resident entry points ---------------------------------------------------
  * Buffers are device pointers (256-byte aligned) holding ncol columns in the library's INTERNAL

@@ -51,6 +51,8 @@ class ChefsiContext:
     """One CUDA device's instance of the filter path (``chefsi_ctx_t``)."""
 
     FLAG_NO_X_COPYBACK = 1
+    FLAG_KEEP_Y = 2
+    FLAG_NO_Y_COPYBACK = 4
 
     def __init__(self, device=0):
         """``device``: a CUDA ordinal, or a list of ordinals for one context that owns several GPUs
@@ -113,10 +115,13 @@ class ChefsiContext:
         return int(self._lib.chefsi_device_ld(self._h))
 
     # -- reference-named host entry points ------------------------------------------------------
-    def ChebyshevFiltering(self, X, Y, m, a, b, a0, copy_back_x=True):
-        """X, Y: real arrays (ncol, ld).  X is overwritten with p_{m-1}(H)X0, Y with p_m(H)X0."""
+    def ChebyshevFiltering(self, X, Y, m, a, b, a0, copy_back_x=True, keep_y=False, copy_back_y=True):
+        """X, Y: real arrays (ncol, ld).  X is overwritten with p_{m-1}(H)X0, Y with p_m(H)X0.
+        keep_y: leave Y on the device for DP_Project_Hamiltonian / DP_Subspace_Rotation (after subspace_reserve)."""
         ncol, ldi = X.shape
         flags = 0 if copy_back_x else self.FLAG_NO_X_COPYBACK
+        if keep_y:
+            flags |= self.FLAG_KEEP_Y | (0 if copy_back_y else self.FLAG_NO_Y_COPYBACK)
         fn = self._lib.chefsi_chebyshev_filter_kpt if _is_complex(X) else self._lib.chefsi_chebyshev_filter
         self._check(fn(self._h, _addr(X), ldi, _addr(Y), Y.shape[1], ncol, int(m), float(a), float(b), float(a0), flags))
 
@@ -128,6 +133,21 @@ class ChefsiContext:
         self._check(fn(self._h, ncol, float(c), _addr(x), ldi, _addr(Hx), Hx.shape[1]))
 
     Hamiltonian_vectors_mult_kpt = Hamiltonian_vectors_mult
+
+    # -- Rayleigh-Ritz steps on the resident block (src/eigenSolver.c:939-1086, 1386-1443) ------------------------
+    def subspace_reserve(self, ncol):
+        self._check(self._lib.chefsi_subspace_reserve(self._h, int(ncol)))
+
+    def DP_Project_Hamiltonian(self, Y, Hp, Mp):
+        """Hp = Y^T H Y, Mp = Y^T Y (column-major ncol x ncol; symmetric, so the numpy view is the same matrix)."""
+        ncol, ldy = Y.shape
+        self._check(self._lib.chefsi_subspace_project(self._h, _addr(Y), ldy, ncol, _addr(Hp), _addr(Mp), Hp.shape[1]))
+
+    def DP_Subspace_Rotation(self, Q, X):
+        """X = Y Q with the resident Y; Q given as the reference stores it: column-major ncol x ncol, i.e. the numpy
+        array Q[n, m] holds element (m, n)."""
+        ncol = Q.shape[0]
+        self._check(self._lib.chefsi_subspace_rotate(self._h, _addr(Q), Q.shape[1], ncol, _addr(X), X.shape[1]))
 
     def Lap_vec_mult(self, c, x, Lapx, a=1.0):
         """Lapx = (a Lap + c) x (src/lapVecRoutines.c:37: a = 1; no potential, no projectors)."""

@@ -116,6 +116,8 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     cudaFree(ctx->d_alpha[1]);
     cudaFree(ctx->d_alpha_sum);
     for (int i = 0; i < 3; i++) if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
+    cudaFree(ctx->d_res_Y); cudaFree(ctx->d_res_W); cudaFree(ctx->d_gemm_ws);
+    for (int i = 0; i < 3; i++) cudaFree(ctx->d_small[i]);
     for (int i = 0; i < 12; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     cudaFree(ctx->d_sync);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -232,6 +234,7 @@ extern "C" int chefsi_set_grid(chefsi_ctx_t *ctx, const chefsi_grid_t *g)
     CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_veff = false;
     ctx->have_grid = true;
+    ctx->res_ncol = 0;
     /* projector tables refer to grid indices: drop them */
     chefsi_free_nloc(ctx->nl);
     return 0;
@@ -704,6 +707,10 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
     const int chunk = chunk_columns(ctx, ncol, esz);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
+    /* KEEP_Y: the result also goes into the resident block of the subspace routines (subspace.cu) */
+    const bool keep_y = (flags & CHEFSI_FLAG_KEEP_Y) && !is_complex && ctx->d_res_Y && (size_t)ncol * ctx->ld * esz <= ctx->res_bytes;
+    const bool skip_y = keep_y && (flags & CHEFSI_FLAG_NO_Y_COPYBACK);
+    ctx->res_ncol = 0;
     if (chunk == ncol && want_staging(ctx, X, Y, (size_t)ncol * ctx->Nd * esz)) {
         /* one small chunk in pageable memory: pinned staging, one stream, one synchronisation */
         const size_t row = ctx->Nd * esz, pitch = ctx->ld * esz;
@@ -711,12 +718,14 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
         if (staged_h2d(ctx, 0, ctx->d_buf[0], pitch, X, ldi * esz, row, ncol)) return drain_streams(ctx, 1);
         int ys = 1, xs = 0;
         if (filter_device(ctx, ctx->d_buf, ncol, m, a, b, a0, is_complex, &ys, &xs)) return drain_streams(ctx, 1);
-        if (staged_d2h_begin(ctx, 1, ctx->d_buf[ys], pitch, row, ncol)) return drain_streams(ctx, 1);
+        if (keep_y) CHEFSI_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_res_Y, ctx->d_buf[ys], (size_t)ncol * pitch, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (!skip_y && staged_d2h_begin(ctx, 1, ctx->d_buf[ys], pitch, row, ncol)) return drain_streams(ctx, 1);
         if (!(flags & CHEFSI_FLAG_NO_X_COPYBACK) && staged_d2h_begin(ctx, 2, ctx->d_buf[xs], pitch, row, ncol)) return drain_streams(ctx, 1);
         CHEFSI_CUDA_DRAIN(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
         CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
-        staged_d2h_finish(ctx, 1, Y, ldo * esz, row, ncol);
+        if (!skip_y) staged_d2h_finish(ctx, 1, Y, ldo * esz, row, ncol);
         if (!(flags & CHEFSI_FLAG_NO_X_COPYBACK)) staged_d2h_finish(ctx, 2, X, ldi * esz, row, ncol);
+        if (keep_y) { ctx->res_ncol = ncol; ctx->res_host = Y; }
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.last_filter_ms = ms; else cudaGetLastError();
         return 0;
@@ -759,10 +768,14 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
         CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[s], 0));
         int ys = 1, xs = 0;
         if (filter_device(ctx, trio, nc, m, a, b, a0, is_complex, &ys, &xs)) return drain_streams(ctx, 1);
+        if (keep_y)
+            CHEFSI_CUDA_DRAIN(ctx, cudaMemcpyAsync((char *)ctx->d_res_Y + (size_t)c0 * pitch, trio[ys], (size_t)nc * pitch,
+                                                   cudaMemcpyDeviceToDevice, ctx->stream));
         CHEFSI_CUDA_DRAIN(ctx, cudaEventRecord(ev_out[s], ctx->stream));
         CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev_out[s], 0));
-        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync((char *)Y + (size_t)c0 * ldo * esz, ldo * esz, trio[ys], pitch, row, nc,
-                                                 cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (!skip_y)
+            CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync((char *)Y + (size_t)c0 * ldo * esz, ldo * esz, trio[ys], pitch, row, nc,
+                                                     cudaMemcpyDeviceToHost, ctx->d2h_stream));
         if (copy_x)
             CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync((char *)X + (size_t)c0 * ldi * esz, ldi * esz, trio[xs], pitch, row, nc,
                                                      cudaMemcpyDeviceToHost, ctx->d2h_stream));
@@ -774,6 +787,7 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) ctx->stats.last_filter_ms = ms; else cudaGetLastError();
+    if (keep_y) { ctx->res_ncol = ncol; ctx->res_host = Y; }
     return 0;
 }
 
@@ -828,6 +842,99 @@ extern "C" int chefsi_hamiltonian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double c
                                            size_t ldo)
 {
     return ctx ? hmult_host(ctx, ncol, c, x, ldi, Hx, ldo, true) : 1;
+}
+
+/* ---- Rayleigh-Ritz projection / subspace rotation on the resident block (kernels: subspace.cu) ------------------- */
+static int ensure_small(chefsi_ctx *ctx, int ncol)
+{
+    const size_t need = (size_t)ncol * ncol * sizeof(double);
+    if (need <= ctx->small_bytes) return 0;
+    for (int i = 0; i < 3; i++) { cudaFree(ctx->d_small[i]); ctx->d_small[i] = nullptr; }
+    ctx->small_bytes = 0;
+    for (int i = 0; i < 3; i++) CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_small[i], need));
+    ctx->small_bytes = need;
+    return 0;
+}
+
+extern "C" int chefsi_subspace_reserve(chefsi_ctx_t *ctx, int ncol)
+{
+    if (!ctx) return 1;
+    if (ctx->multi) return chefsi_fail(ctx, "subspace routines take a single-device context");
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (ncol <= 0) return chefsi_fail(ctx, "subspace_reserve: ncol must be positive");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t need = (size_t)ncol * ctx->ld * sizeof(double);
+    if (need > ctx->res_bytes) {
+        cudaFree(ctx->d_res_Y); cudaFree(ctx->d_res_W);
+        ctx->d_res_Y = ctx->d_res_W = nullptr;
+        ctx->res_bytes = 0;
+        ctx->res_ncol = 0;
+        if (cudaMalloc(&ctx->d_res_Y, need) != cudaSuccess || cudaMalloc(&ctx->d_res_W, need) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(ctx->d_res_Y); cudaFree(ctx->d_res_W);
+            ctx->d_res_Y = ctx->d_res_W = nullptr;
+            return chefsi_fail(ctx, "subspace_reserve: two blocks of %d columns (%zu bytes each) do not fit on the device", ncol, need);
+        }
+        ctx->res_bytes = need;
+    }
+    return ensure_small(ctx, ncol);
+}
+
+extern "C" int chefsi_subspace_project(chefsi_ctx_t *ctx, const double *Y, size_t ldy, int ncol, double *Hp, double *Mp, size_t ldp)
+{
+    if (!ctx || !Y || !Hp || !Mp) return 1;
+    if (ncol <= 0 || ldp < (size_t)ncol || ldy < ctx->Nd) return chefsi_fail(ctx, "subspace_project: bad dimensions");
+    if (chefsi_subspace_reserve(ctx, ncol)) return 1;
+    const size_t row = ctx->Nd * sizeof(double), pitch = ctx->ld * sizeof(double);
+    if (!(ctx->res_ncol == ncol && ctx->res_host == (const void *)Y)) {
+        /* Y is not resident: upload it (pinned or pageable, the driver stages the latter) */
+        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(ctx->d_res_Y, pitch, Y, ldy * sizeof(double), row, ncol, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->res_ncol = ncol;
+        ctx->res_host = Y;
+    }
+    Profiler prof(ctx);
+    /* H Y with c = 0 (eigenSolver.c:960-967), in groups of columns the projector kernels' alpha buffers are sized for */
+    const int grp = 256;
+    for (int c0 = 0; c0 < ncol; c0 += grp) {
+        const int nc = ncol - c0 < grp ? ncol - c0 : grp;
+        if (apply_step(ctx, prof, (const char *)ctx->d_res_Y + (size_t)c0 * pitch, nullptr, (char *)ctx->d_res_W + (size_t)c0 * pitch, nc, 0.0,
+                       1.0, 0.0, false, false, false))
+            return drain_streams(ctx, 1);
+    }
+    double *dHp = (double *)ctx->d_small[0], *dMp = (double *)ctx->d_small[1];
+    int n = launch_gemm_tn(ctx, (const double *)ctx->d_res_Y, ctx->ld, (const double *)ctx->d_res_Y, ctx->ld, ncol, ncol, ctx->Nd, 1.0, dMp, ncol);
+    if (n < 0) return drain_streams(ctx, 1);
+    ctx->stats.kernel_launches += n;
+    n = launch_gemm_tn(ctx, (const double *)ctx->d_res_Y, ctx->ld, (const double *)ctx->d_res_W, ctx->ld, ncol, ncol, ctx->Nd, 1.0, dHp, ncol);
+    if (n < 0) return drain_streams(ctx, 1);
+    ctx->stats.kernel_launches += n;
+    const size_t w = (size_t)ncol * sizeof(double);
+    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(Mp, ldp * sizeof(double), dMp, w, w, ncol, cudaMemcpyDeviceToHost, ctx->stream));
+    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(Hp, ldp * sizeof(double), dHp, w, w, ncol, cudaMemcpyDeviceToHost, ctx->stream));
+    CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
+    prof.finish();
+    return 0;
+}
+
+extern "C" int chefsi_subspace_rotate(chefsi_ctx_t *ctx, const double *Q, size_t ldq, int ncol, double *X, size_t ldx)
+{
+    if (!ctx || !Q || !X) return 1;
+    if (ctx->multi) return chefsi_fail(ctx, "subspace routines take a single-device context");
+    if (ctx->res_ncol != ncol || !ctx->d_res_Y) return chefsi_fail(ctx, "subspace_rotate: no resident block of %d columns (call chefsi_subspace_project first)", ncol);
+    if (ldq < (size_t)ncol || ldx < ctx->Nd) return chefsi_fail(ctx, "subspace_rotate: bad dimensions");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ensure_small(ctx, ncol)) return 1;
+    const size_t w = (size_t)ncol * sizeof(double);
+    double *dQ = (double *)ctx->d_small[2];
+    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(dQ, w, Q, ldq * sizeof(double), w, ncol, cudaMemcpyHostToDevice, ctx->stream));
+    const int n = launch_gemm_nn(ctx, (const double *)ctx->d_res_Y, ctx->ld, dQ, ncol, ctx->Nd, ncol, ncol, (double *)ctx->d_res_W, ctx->ld);
+    if (n < 0) return drain_streams(ctx, 1);
+    ctx->stats.kernel_launches += n;
+    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(X, ldx * sizeof(double), ctx->d_res_W, ctx->ld * sizeof(double), ctx->Nd * sizeof(double), ncol,
+                                             cudaMemcpyDeviceToHost, ctx->stream));
+    CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->res_ncol = 0; /* the block has been consumed */
+    return 0;
 }
 
 /* ---- (a Lap + c) x: the operator of the Poisson residual ------------------------------------------------------

@@ -112,6 +112,15 @@ struct chefsi_ctx {
     /* small blocks in pageable host memory (the SCF test systems; single columns of Lanczos / the Poisson residual) go
        through these pinned staging buffers: one memcpy + one truly asynchronous copy instead of the driver's
        pageable path */
+    /* subspace.cu: the filtered block kept on the device between ChebyshevFiltering, the projection and the rotation */
+    void *d_res_Y = nullptr, *d_res_W = nullptr;   /* Y and a work block (H Y, then Y Q), ncol x ld each */
+    size_t res_bytes = 0;
+    int res_ncol = 0;                              /* columns of the resident Y (0: none) */
+    const void *res_host = nullptr;                /* host address the resident Y stands for */
+    void *d_gemm_ws = nullptr;                     /* split-K partial tiles */
+    size_t gemm_ws_bytes = 0;
+    void *d_small[3] = {nullptr, nullptr, nullptr}; /* Hp, Mp, Q (Ns x Ns) */
+    size_t small_bytes = 0;
     void *h_pin[3] = {nullptr, nullptr, nullptr};
     size_t h_pin_bytes = 0;
     int fast_small = 1;
@@ -179,6 +188,12 @@ int multi_synchronize(chefsi_ctx *lead);
 void multi_set_profiling(chefsi_ctx *lead, int on);
 void multi_bcast_stats(const chefsi_ctx *lead, unsigned long long *calls, unsigned long long *bytes);
 void chefsi_free_nloc(NlocDev &d);
+
+/* subspace.cu */
+int launch_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B, size_t ldb, int M, int N, size_t K, double scale,
+                   double *C, size_t ldc);
+int launch_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q, size_t ldq, size_t K, int M, int N, double *C,
+                   size_t ldc);
 
 /* util.cu */
 int launch_fill_random(chefsi_ctx *ctx, void *buf, int ncol, long long first_col, unsigned long long seed,

@@ -52,6 +52,10 @@ void Hamiltonian_vectors_mult_kpt_ref(const SPARC_OBJ *pSPARC, int DMnd, int *DM
                                       double c, double _Complex *x, const int ldi, double _Complex *Hx, const int ldo,
                                       int spin, int kpt, MPI_Comm comm);
 
+#ifdef USE_DP_SUBEIG
+void DP_Project_Hamiltonian_ref(SPARC_OBJ *pSPARC, int *DMVertices, double *Y, int ldi, double *HY, int ldo, double *Hp, double *Mp, int spn_i);
+void DP_Subspace_Rotation_ref(SPARC_OBJ *pSPARC, double *Psi_rot);
+#endif
 void Lap_vec_mult_ref(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c, double *x,
                       const int ldi, double *Lapx, const int ldo, MPI_Comm comm);
 
@@ -67,8 +71,10 @@ static struct {
     /* host registration of the caller's orbital arrays (pinned for full-rate async copies) */
     struct { void *base; size_t bytes; } pinned[64];
     int npinned;
-    unsigned long long n_filter, n_hmult, n_forward, n_lap;
-    double t_lap;
+    unsigned long long n_filter, n_hmult, n_forward, n_lap, n_project, n_rotate;
+    double t_lap, t_project, t_rotate;
+    int subspace_pending;    /* the last DP_Project_Hamiltonian ran on the device: DP_Subspace_Rotation finds its block there */
+    int multi;               /* the context owns several devices */
     double t_filter;
     double t_init, t_sync, t_hmult;  /* seconds in context creation, table/Veff synchronisation, H-apply calls */
     unsigned long long n_filter_fwd; /* ChebyshevFiltering calls forwarded to the reference, and their seconds */
@@ -97,6 +103,9 @@ static void shim_report(void)
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] %llu Lap_vec_mult calls (Poisson residual, Kerker mixing, Lanczos of the Laplacian) %.3f s\n",
                 G.n_lap, G.t_lap);
+    if (G.verbose)
+        fprintf(stderr, "[chefsi_b200 shim] %llu DP_Project_Hamiltonian calls %.3f s, %llu DP_Subspace_Rotation calls %.3f s on the device\n",
+                G.n_project, G.t_project, G.n_rotate, G.t_rotate);
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] context creation %.3f s, Hamiltonian_vectors_mult calls %.3f s, grid/projector/Veff "
                         "synchronisation %.3f s (included in the call times)\n", G.t_init, G.t_hmult, G.t_sync);
@@ -151,6 +160,7 @@ static void shim_init(void)
         }
         G.t_init += MPI_Wtime() - t_init0;
         int nd = 0, nccl = 0;
+        G.multi = 1;
         chefsi_multi_info(G.ctx, &nd, &nccl, NULL, NULL);
         if (G.verbose) fprintf(stderr, "[chefsi_b200 shim] %s on %d devices (%s), replication over %s\n", chefsi_version(), nd, devs, nccl ? "NCCL" : "cudaMemcpyPeer");
         return;
@@ -485,6 +495,24 @@ static void shim_dump_outputs(FILE *f, const SPARC_OBJ *S, int is_kpt, const voi
     if (getenv("CHEFSI_B200_DUMP_EXIT")) exit(0);
 }
 
+/* Rayleigh-Ritz steps on the device: real data, one rank, the generalized (not the standard)
+ * eigenproblem, a single-device context.  The same predicate guards ChebyshevFiltering's decision to leave Y on the
+ * device and the two replaced routines, so they always agree. */
+static int shim_subspace_ok(const SPARC_OBJ *S, int ncol)
+{
+#ifdef USE_DP_SUBEIG
+    if (getenv("CHEFSI_B200_NO_SUBSPACE") || G.multi) return 0;
+    DP_CheFSI_t dp = (DP_CheFSI_t)S->DP_CheFSI;
+    if (!dp || dp->nproc_row != 1 || dp->nproc_kpt != 1) return 0;
+    if (S->StandardEigenFlag || S->CyclixFlag) return 0;
+    if (dp->Ns_dp != ncol || dp->Ns_bp != ncol || dp->Nd_dp != S->Nd) return 0;
+    return 1;
+#else
+    (void)S; (void)ncol;
+    return 0;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 void ChebyshevFiltering(SPARC_OBJ *pSPARC, int *DMVertices, double *X, int ldi, double *Y, int ldo, int ncol, int m,
                         double a, double b, double a0, int k, int spn_i, MPI_Comm comm, double *time_info)
@@ -522,7 +550,11 @@ void ChebyshevFiltering(SPARC_OBJ *pSPARC, int *DMVertices, double *X, int ldi, 
     /* X is in/out in the reference (ends as p_{m-1}(H) X0, :787-794), but its only caller, CheFSI (eigenSolver.c:325),
        consumes Y alone and then reuses X as scratch (:347-365): the copy-back of the clobbered X is off by default
        (half of the call's D2H bytes); CHEFSI_B200_X_COPYBACK=1 restores the reference's exact in/out behaviour */
-    const int flags = getenv("CHEFSI_B200_X_COPYBACK") ? 0 : CHEFSI_FLAG_NO_X_COPYBACK;
+    int flags = getenv("CHEFSI_B200_X_COPYBACK") ? 0 : CHEFSI_FLAG_NO_X_COPYBACK;
+    /* when the projection and the rotation that follow (eigenSolver.c:349,420) run on the device too, Y stays there and
+       is not copied to the host at all */
+    if (shim_subspace_ok(pSPARC, ncol) && chefsi_subspace_reserve(G.ctx, ncol) == 0)
+        flags |= CHEFSI_FLAG_KEEP_Y | CHEFSI_FLAG_NO_Y_COPYBACK;
     if (chefsi_chebyshev_filter(G.ctx, X, (size_t)ldi, Y, (size_t)ldo, ncol, m, a, b, a0, flags) != 0)
         shim_fatal("chefsi_chebyshev_filter");
     *time_info = MPI_Wtime() - t1;
@@ -655,3 +687,47 @@ void Lap_vec_mult(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices
     G.n_lap++;
     G.t_lap += MPI_Wtime() - t1;
 }
+
+#ifdef USE_DP_SUBEIG
+/* Hp = Y^T H Y, Mp = Y^T Y -- src/eigenSolver.c:939-1086.  At one rank the reference copies Y and HY into its "domain
+ * parallel" buffers (BP2DP is the identity), calls cblas_dgemm twice and leaves the results in DP_CheFSI->Hp_local /
+ * Mp_local, where DP_Solve_Generalized_EigenProblem (:1262, unchanged reference code) picks them up. */
+void DP_Project_Hamiltonian(SPARC_OBJ *pSPARC, int *DMVertices, double *Y, int ldi, double *HY, int ldo, double *Hp, double *Mp, int spn_i)
+{
+    DP_CheFSI_t dp = (DP_CheFSI_t)pSPARC->DP_CheFSI;
+    if (dp == NULL) return; /* eigenSolver.c:942 */
+    const int DMnd = (1 - DMVertices[0] + DMVertices[1]) * (1 - DMVertices[2] + DMVertices[3]) * (1 - DMVertices[4] + DMVertices[5]);
+    G.subspace_pending = 0;
+    if (!G.ctx || !shim_supported(pSPARC, DMnd, DMVertices, pSPARC->dmcomm, pSPARC->nlocProj) || !shim_subspace_ok(pSPARC, dp->Ns_dp)) {
+        DP_Project_Hamiltonian_ref(pSPARC, DMVertices, Y, ldi, HY, ldo, Hp, Mp, spn_i);
+        return;
+    }
+    const double t1 = MPI_Wtime();
+    shim_sync_grid(pSPARC);
+    shim_sync_projectors(pSPARC, pSPARC->Atom_Influence_nloc, pSPARC->nlocProj, 0);
+    const int sg = pSPARC->spin_start_indx + spn_i;
+    shim_sync_veff(pSPARC->Veff_loc_dmcomm + (size_t)sg * pSPARC->Nd_d_dmcomm, (size_t)pSPARC->Nd);
+    if (chefsi_subspace_project(G.ctx, Y, (size_t)ldi, dp->Ns_dp, dp->Hp_local, dp->Mp_local, (size_t)dp->Ns_dp) != 0)
+        shim_fatal("chefsi_subspace_project");
+    G.subspace_pending = 1;
+    G.n_project++;
+    G.t_project += MPI_Wtime() - t1;
+}
+
+/* Psi_rot = Y Q -- src/eigenSolver.c:1386-1443; Q = DP_CheFSI->eig_vecs as left by DP_Solve_Generalized_EigenProblem */
+void DP_Subspace_Rotation(SPARC_OBJ *pSPARC, double *Psi_rot)
+{
+    DP_CheFSI_t dp = (DP_CheFSI_t)pSPARC->DP_CheFSI;
+    if (dp == NULL) return;
+    if (!G.subspace_pending) {
+        DP_Subspace_Rotation_ref(pSPARC, Psi_rot);
+        return;
+    }
+    const double t1 = MPI_Wtime();
+    if (chefsi_subspace_rotate(G.ctx, dp->eig_vecs, (size_t)dp->Ns_dp, dp->Ns_dp, Psi_rot, (size_t)dp->Ndsp_bp) != 0)
+        shim_fatal("chefsi_subspace_rotate");
+    G.subspace_pending = 0;
+    G.n_rotate++;
+    G.t_rotate += MPI_Wtime() - t1;
+}
+#endif
