@@ -156,6 +156,13 @@ int chefsi_subspace_reserve(chefsi_ctx_t *ctx, int ncol);
 int chefsi_subspace_project(chefsi_ctx_t *ctx, const double *Y, size_t ldy, int ncol, double *Hp, double *Mp, size_t ldp);
 int chefsi_subspace_rotate(chefsi_ctx_t *ctx, const double *Q, size_t ldq, int ncol, double *X, size_t ldx);
 
+/* Extreme eigenvalues of H = -1/2 Lap + Veff + Vnl by the Lanczos iteration with every vector resident on the device
+ * (SURVEY.md 8f-2): the body of Lanczos (src/eigenSolver.c:1920-2129) at one rank.  x0: start vector (host, Nd doubles);
+ * stops when |eigmin - previous| <= tol_min and |eigmax - previous| <= tol_max, or after maxit steps.  Real data,
+ * single-device context.  Fails (the caller falls back to the reference routine) if x0 is an eigenvector of H. */
+int chefsi_lanczos(chefsi_ctx_t *ctx, const double *x0, double tol_min, double tol_max, int maxit, double *eigmin,
+                   double *eigmax, int *iterations);
+
 /* ---- device-resident entry points ---------------------------------------------------
  * Buffers are device pointers (256-byte aligned) holding ncol columns in the library's INTERNAL
  * layout: chefsi_device_ld(ctx) elements (doubles, or complex pairs for the _kpt variants) per

@@ -134,6 +134,14 @@ class ChefsiContext:
 
     Hamiltonian_vectors_mult_kpt = Hamiltonian_vectors_mult
 
+    def Lanczos(self, x0, tol_min, tol_max, maxit=1000):
+        """(eigmin, eigmax, iterations) of H by Lanczos from x0 (src/eigenSolver.c:1920), vectors resident on the device."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1)
+        lo, hi, it = C.c_double(0), C.c_double(0), C.c_int(0)
+        self._check(self._lib.chefsi_lanczos(self._h, _addr(x0), float(tol_min), float(tol_max), int(maxit),
+                                             C.byref(lo), C.byref(hi), C.byref(it)))
+        return lo.value, hi.value, it.value
+
     # -- Rayleigh-Ritz steps on the resident block (src/eigenSolver.c:939-1086, 1386-1443) ------------------------
     def subspace_reserve(self, ncol):
         self._check(self._lib.chefsi_subspace_reserve(self._h, int(ncol)))

@@ -116,7 +116,7 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     cudaFree(ctx->d_alpha[1]);
     cudaFree(ctx->d_alpha_sum);
     for (int i = 0; i < 3; i++) if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
-    cudaFree(ctx->d_res_Y); cudaFree(ctx->d_res_W); cudaFree(ctx->d_gemm_ws);
+    cudaFree(ctx->d_res_Y); cudaFree(ctx->d_res_W); cudaFree(ctx->d_gemm_ws); cudaFree(ctx->d_lanczos);
     for (int i = 0; i < 3; i++) cudaFree(ctx->d_small[i]);
     for (int i = 0; i < 12; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     cudaFree(ctx->d_sync);
@@ -542,6 +542,9 @@ static int hmult_device(chefsi_ctx *ctx, int ncol, double c, const void *x, void
     prof.finish();
     return rc;
 }
+/* one H apply (c = 0) of a single resident real column: the operator of lanczos.cu */
+int apply_h_device(chefsi_ctx *ctx, const void *x, void *Hx) { return hmult_device(ctx, 1, 0.0, x, Hx, false); }
+
 extern "C" int chefsi_hamiltonian_mult_device(chefsi_ctx_t *ctx, int ncol, double c, const double *x, double *Hx)
 {
     return ctx ? hmult_device(ctx, ncol, c, x, Hx, false) : 1;

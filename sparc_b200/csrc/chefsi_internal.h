@@ -117,6 +117,8 @@ struct chefsi_ctx {
     size_t res_bytes = 0;
     int res_ncol = 0;                              /* columns of the resident Y (0: none) */
     const void *res_host = nullptr;                /* host address the resident Y stands for */
+    void *d_lanczos = nullptr;                     /* lanczos.cu: three vectors + scalars */
+    size_t lanczos_bytes = 0;
     void *d_gemm_ws = nullptr;                     /* split-K partial tiles */
     size_t gemm_ws_bytes = 0;
     void *d_small[3] = {nullptr, nullptr, nullptr}; /* Hp, Mp, Q (Ns x Ns) */

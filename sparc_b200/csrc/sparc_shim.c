@@ -56,6 +56,9 @@ void Hamiltonian_vectors_mult_kpt_ref(const SPARC_OBJ *pSPARC, int DMnd, int *DM
 void DP_Project_Hamiltonian_ref(SPARC_OBJ *pSPARC, int *DMVertices, double *Y, int ldi, double *HY, int ldo, double *Hp, double *Mp, int spn_i);
 void DP_Subspace_Rotation_ref(SPARC_OBJ *pSPARC, double *Psi_rot);
 #endif
+void Lanczos_ref(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc,
+                 NLOC_PROJ_OBJ *nlocProj, double *eigmin, double *eigmax, double *x0, double TOL_min, double TOL_max, int MAXIT,
+                 int k, int spn_i, MPI_Comm comm, MPI_Request *req_veff_loc);
 void Lap_vec_mult_ref(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c, double *x,
                       const int ldi, double *Lapx, const int ldo, MPI_Comm comm);
 
@@ -71,8 +74,8 @@ static struct {
     /* host registration of the caller's orbital arrays (pinned for full-rate async copies) */
     struct { void *base; size_t bytes; } pinned[64];
     int npinned;
-    unsigned long long n_filter, n_hmult, n_forward, n_lap, n_project, n_rotate;
-    double t_lap, t_project, t_rotate;
+    unsigned long long n_filter, n_hmult, n_forward, n_lap, n_project, n_rotate, n_lanczos, n_lanczos_iter;
+    double t_lap, t_project, t_rotate, t_lanczos;
     int subspace_pending;    /* the last DP_Project_Hamiltonian ran on the device: DP_Subspace_Rotation finds its block there */
     int multi;               /* the context owns several devices */
     double t_filter;
@@ -106,6 +109,9 @@ static void shim_report(void)
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] %llu DP_Project_Hamiltonian calls %.3f s, %llu DP_Subspace_Rotation calls %.3f s on the device\n",
                 G.n_project, G.t_project, G.n_rotate, G.t_rotate);
+    if (G.verbose)
+        fprintf(stderr, "[chefsi_b200 shim] %llu Lanczos calls (%llu iterations) %.3f s with the vectors resident on the device\n",
+                G.n_lanczos, G.n_lanczos_iter, G.t_lanczos);
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] context creation %.3f s, Hamiltonian_vectors_mult calls %.3f s, grid/projector/Veff "
                         "synchronisation %.3f s (included in the call times)\n", G.t_init, G.t_hmult, G.t_sync);
@@ -731,3 +737,37 @@ void DP_Subspace_Rotation(SPARC_OBJ *pSPARC, double *Psi_rot)
     G.t_rotate += MPI_Wtime() - t1;
 }
 #endif
+
+/* Extreme eigenvalues of H for the Chebyshev bounds -- src/eigenSolver.c:1920-2129.  One rank, real data,
+ * single-device context: the whole iteration runs on the device (chefsi_lanczos); anything else, and the degenerate
+ * start vector the reference re-randomises (:2020-2033), goes to the reference routine, whose single-column
+ * Hamiltonian_vectors_mult calls still land on the device. */
+void Lanczos(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc,
+             NLOC_PROJ_OBJ *nlocProj, double *eigmin, double *eigmax, double *x0, double TOL_min, double TOL_max, int MAXIT,
+             int k, int spn_i, MPI_Comm comm, MPI_Request *req_veff_loc)
+{
+    int ok = (comm != MPI_COMM_NULL) && !G.multi && !getenv("CHEFSI_B200_NO_LANCZOS") && pSPARC->kptcomm_inter == MPI_COMM_NULL;
+    int DMnd = 0;
+    if (ok) {
+        DMnd = (1 - DMVertices[0] + DMVertices[1]) * (1 - DMVertices[2] + DMVertices[3]) * (1 - DMVertices[4] + DMVertices[5]);
+        ok = shim_supported(pSPARC, DMnd, DMVertices, comm, nlocProj);
+    }
+    if (ok) {
+        shim_init();
+        const double t1 = MPI_Wtime();
+        MPI_Wait(req_veff_loc, MPI_STATUS_IGNORE); /* eigenSolver.c:1998: Veff may still be in flight */
+        shim_sync_grid(pSPARC);
+        shim_sync_projectors(pSPARC, Atom_Influence_nloc, nlocProj, 0);
+        shim_sync_veff(Veff_loc, (size_t)DMnd);
+        int iters = 0;
+        if (chefsi_lanczos(G.ctx, x0, TOL_min, TOL_max, MAXIT, eigmin, eigmax, &iters) == 0) {
+            G.n_lanczos++;
+            G.n_lanczos_iter += (unsigned long long)iters;
+            G.t_lanczos += MPI_Wtime() - t1;
+            return;
+        }
+        if (G.verbose) fprintf(stderr, "[chefsi_b200 shim] Lanczos: %s -- this call runs the reference iteration\n", chefsi_last_error(G.ctx));
+    }
+    Lanczos_ref(pSPARC, DMVertices, Veff_loc, Atom_Influence_nloc, nlocProj, eigmin, eigmax, x0, TOL_min, TOL_max, MAXIT, k, spn_i,
+                comm, req_veff_loc);
+}

@@ -48,7 +48,7 @@ def run_case(name, tmp_path, env_extra=None, timeout=1500):
     return _energy(out), _energy(os.path.join(cwd, name + ".refout")), r.stderr, out
 
 
-@pytest.mark.parametrize("name", ["Si8", "BaTiO3", "Si8_kpt", "Au_fcc211"])
+@pytest.mark.parametrize("name", ["Si8", "BaTiO3", "Si8_kpt", "Au_fcc211", "O2_spin_coarse"])
 def test_scf_energy_matches_reference(name, tmp_path):
     e, e_ref, log, out = run_case(name, tmp_path)
     m = re.search(r"(\d+) ChebyshevFiltering calls .*?(\d+) Hamiltonian_vectors_mult calls, (\d+) calls forwarded", log)
@@ -57,6 +57,10 @@ def test_scf_energy_matches_reference(name, tmp_path):
     print(f"{name}: E = {e:.10f} Ha/atom, refout {e_ref:.10f}, diff {e - e_ref:+.2e}; "
           f"{n_filter} filter calls, {n_hmult} H applies on the GPU, {n_fwd} forwarded")
     assert n_filter > 0 and n_fwd == 0, "the CUDA path did not serve the filter calls"
+    if name == "O2_spin_coarse":
+        # collinear spin: two filter calls per CheFSI pass (X = Xorb + spn_i * DMnd, ld = 2 DMnd, eigenSolver.c:325-328);
+        # .refout = the unmodified reference at np = 1 (integration/cases_extra/README.md)
+        assert n_filter % 2 == 0
     assert abs(e - e_ref) <= TOL_HA_PER_ATOM
 
 

@@ -77,3 +77,40 @@ def test_filter_keeps_y_resident(ctx, port):
     Xr = np.empty_like(x)
     ctx.DP_Subspace_Rotation(Q, Xr)
     assert rel_fro(Xr, Q @ Yw) < TOL
+
+
+@pytest.mark.parametrize("cell_typ,BC", [(0, (0, 0, 0)), (17, (0, 0, 0)), (0, (1, 1, 1))])
+def test_lanczos_extreme_eigenvalues(ctx, port, cell_typ, BC):
+    """chefsi_lanczos (Lanczos, eigenSolver.c:1920-2129) against the same iteration done on the host with the oracle's
+    H apply and numpy's symmetric tridiagonal eigenvalues (the reference calls LAPACKE_dsterf): same stopping step,
+    eigenvalues equal to rounding."""
+    g, veff, proj, x = small_case(cell_typ, BC, ncol=1)
+    _setup(ctx, g, veff, proj)
+    tol = 1e-2
+    lo, hi, it = ctx.Lanczos(x[0], tol, tol, maxit=300)
+    H = lambda v: port.hamiltonian_mult(g, proj, veff, 0.0, v[None, :].copy())[0]
+    vjm1 = x[0] / np.linalg.norm(x[0])
+    vj = H(vjm1)
+    a = [vjm1 @ vj]
+    vj = vj - a[0] * vjm1
+    b = [np.linalg.norm(vj)]
+    vj = vj / b[0]
+    emin_pre = emax_pre = 0.0
+    j = 0
+    while True:
+        vjp1 = H(vj)
+        a.append(vj @ vjp1)
+        vjp1 = vjp1 - (a[j + 1] * vj + b[j] * vjm1)
+        vjm1 = vj
+        b.append(np.linalg.norm(vjp1))
+        vj = vjp1 / b[j + 1]
+        T = np.diag(a[:j + 2]) + np.diag(b[:j + 1], 1) + np.diag(b[:j + 1], -1)
+        ev = np.linalg.eigvalsh(T)
+        emin, emax = ev[0], ev[-1]
+        done = abs(emin - emin_pre) <= tol and abs(emax - emax_pre) <= tol
+        emin_pre, emax_pre = emin, emax
+        j += 1
+        if done or j >= 300:
+            break
+    assert it == j
+    assert abs(lo - emin) < 1e-9 * max(1.0, abs(emax)) and abs(hi - emax) < 1e-9 * max(1.0, abs(emax))
