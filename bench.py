@@ -439,6 +439,13 @@ def run_ours(args):
     # ---- e2e: the same metric through the host-buffer C-ABI call the SPARC shim makes (chefsi_chebyshev_filter with
     # pinned HOST buffers; H2D of X and D2H of Y inside the timed region; X copy-back off = the shim's default) ----
     e2e_cols = max(1, min(args.e2e_cols, ncol_local))      # PER RANK
+    try:  # never pin more than a quarter of the host's available memory over all ranks (2 pinned blocks per rank)
+        import psutil
+        avail = psutil.virtual_memory().available
+        cap = int(0.25 * avail / max(world, 1) / (2 * g.Nd * 8 * words))
+        e2e_cols = max(8, min(e2e_cols, cap))
+    except Exception:
+        pass
     hdt = torch.complex128 if cplx else torch.float64
     saved_aff = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     numa = bind_to_gpu_numa_node(local_rank)

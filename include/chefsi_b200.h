@@ -93,8 +93,8 @@ typedef struct chefsi_ctx chefsi_ctx_t;
 /* flags for the filter entry points */
 #define CHEFSI_FLAG_NO_X_COPYBACK 1 /* host entry points: do not copy the clobbered X back   */
                                     /* (the caller reuses X as scratch, eigenSolver.c:364)   */
-#define CHEFSI_FLAG_KEEP_Y 2        /* keep Y = p_m(H) X0 on the device for chefsi_subspace_project / _rotate (real data,  */
-                                    /* single-device context; needs a successful chefsi_subspace_reserve)                  */
+#define CHEFSI_FLAG_KEEP_Y 2        /* keep Y = p_m(H) X0 on the device for chefsi_subspace_project / _rotate            */
+                                    /* (single-device context; needs a successful chefsi_subspace_reserve[_kpt])             */
 #define CHEFSI_FLAG_NO_Y_COPYBACK 4 /* with KEEP_Y: do not copy Y to the host at all (the caller's next steps are           */
                                     /* chefsi_subspace_project and chefsi_subspace_rotate, which read the device copy)      */
 
@@ -155,6 +155,11 @@ int chefsi_laplacian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double a, double c, c
 int chefsi_subspace_reserve(chefsi_ctx_t *ctx, int ncol);
 int chefsi_subspace_project(chefsi_ctx_t *ctx, const double *Y, size_t ldy, int ncol, double *Hp, double *Mp, size_t ldp);
 int chefsi_subspace_rotate(chefsi_ctx_t *ctx, const double *Q, size_t ldq, int ncol, double *X, size_t ldx);
+/* k-point (complex, interleaved re/im) variants: Hp = Y^H H Y, Mp = Y^H Y (DP_Project_Hamiltonian_kpt,
+ * src/eigenSolverKpt.c:676-790: zgemm ConjTrans), X = Y Q (DP_Subspace_Rotation_kpt, :947-1010); set the k-point first */
+int chefsi_subspace_reserve_kpt(chefsi_ctx_t *ctx, int ncol);
+int chefsi_subspace_project_kpt(chefsi_ctx_t *ctx, const void *Y, size_t ldy, int ncol, void *Hp, void *Mp, size_t ldp);
+int chefsi_subspace_rotate_kpt(chefsi_ctx_t *ctx, const void *Q, size_t ldq, int ncol, void *X, size_t ldx);
 
 /* Extreme eigenvalues of H = -1/2 Lap + Veff + Vnl by the Lanczos iteration with every vector resident on the device
  * (SURVEY.md 8f-2): the body of Lanczos (src/eigenSolver.c:1920-2129) at one rank.  x0: start vector (host, Nd doubles);
@@ -162,6 +167,15 @@ int chefsi_subspace_rotate(chefsi_ctx_t *ctx, const double *Q, size_t ldq, int n
  * single-device context.  Fails (the caller falls back to the reference routine) if x0 is an eigenvector of H. */
 int chefsi_lanczos(chefsi_ctx_t *ctx, const double *x0, double tol_min, double tol_max, int maxit, double *eigmin,
                    double *eigmax, int *iterations);
+
+/* Alternating Anderson-Richardson solve of -(Lap + c) x = b with the Jacobi preconditioner, every vector resident on the
+ * device: AAR (src/linearSolver.c:38-146) with res_fun = poisson_residual (src/lapVecRoutines.c:61) and
+ * precond_fun = Jacobi_preconditioner (src/electrostatics.c:1682) -- the Poisson solve of every SCF iteration
+ * (electrostatics.c:1658) and the Kerker preconditioner (mixing.c:501).  x: start vector in, solution out (host, Nd);
+ * b: right-hand side (host); omega, beta, m (<= 16), p, tol (relative to ||b||), max_iter as in the reference.
+ * Real data, single-device context. */
+int chefsi_poisson_aar(chefsi_ctx_t *ctx, double c, double *x, const double *b, double omega, double beta, int m, int p,
+                       double tol, int max_iter, int *iterations, double *res_norm);
 
 /* ---- device-resident entry points ---------------------------------------------------
  * Buffers are device pointers (256-byte aligned) holding ncol columns in the library's INTERNAL

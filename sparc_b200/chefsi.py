@@ -134,6 +134,14 @@ class ChefsiContext:
 
     Hamiltonian_vectors_mult_kpt = Hamiltonian_vectors_mult
 
+    def AAR(self, c, x, b, omega=0.6, beta=0.6, m=7, p=6, tol=1e-8, max_iter=1000):
+        """Solve -(Lap + c) x = b in place (src/linearSolver.c:38 with poisson_residual + Jacobi_preconditioner);
+        returns (iterations, ||r||)."""
+        it, rn = C.c_int(0), C.c_double(0)
+        self._check(self._lib.chefsi_poisson_aar(self._h, float(c), _addr(x), _addr(b), float(omega), float(beta), int(m), int(p),
+                                                 float(tol), int(max_iter), C.byref(it), C.byref(rn)))
+        return it.value, rn.value
+
     def Lanczos(self, x0, tol_min, tol_max, maxit=1000):
         """(eigmin, eigmax, iterations) of H by Lanczos from x0 (src/eigenSolver.c:1920), vectors resident on the device."""
         x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1)
@@ -143,19 +151,26 @@ class ChefsiContext:
         return lo.value, hi.value, it.value
 
     # -- Rayleigh-Ritz steps on the resident block (src/eigenSolver.c:939-1086, 1386-1443) ------------------------
-    def subspace_reserve(self, ncol):
-        self._check(self._lib.chefsi_subspace_reserve(self._h, int(ncol)))
+    def subspace_reserve(self, ncol, is_complex=False):
+        fn = self._lib.chefsi_subspace_reserve_kpt if is_complex else self._lib.chefsi_subspace_reserve
+        self._check(fn(self._h, int(ncol)))
 
     def DP_Project_Hamiltonian(self, Y, Hp, Mp):
-        """Hp = Y^T H Y, Mp = Y^T Y (column-major ncol x ncol; symmetric, so the numpy view is the same matrix)."""
+        """Hp = Y^H H Y, Mp = Y^H Y, column-major ncol x ncol: the numpy arrays hold Hp[n, m] = element (m, n)."""
         ncol, ldy = Y.shape
-        self._check(self._lib.chefsi_subspace_project(self._h, _addr(Y), ldy, ncol, _addr(Hp), _addr(Mp), Hp.shape[1]))
+        fn = self._lib.chefsi_subspace_project_kpt if _is_complex(Y) else self._lib.chefsi_subspace_project
+        self._check(fn(self._h, _addr(Y), ldy, ncol, _addr(Hp), _addr(Mp), Hp.shape[1]))
+
+    DP_Project_Hamiltonian_kpt = DP_Project_Hamiltonian
 
     def DP_Subspace_Rotation(self, Q, X):
         """X = Y Q with the resident Y; Q given as the reference stores it: column-major ncol x ncol, i.e. the numpy
         array Q[n, m] holds element (m, n)."""
         ncol = Q.shape[0]
-        self._check(self._lib.chefsi_subspace_rotate(self._h, _addr(Q), Q.shape[1], ncol, _addr(X), X.shape[1]))
+        fn = self._lib.chefsi_subspace_rotate_kpt if _is_complex(Q) else self._lib.chefsi_subspace_rotate
+        self._check(fn(self._h, _addr(Q), Q.shape[1], ncol, _addr(X), X.shape[1]))
+
+    DP_Subspace_Rotation_kpt = DP_Subspace_Rotation
 
     def Lap_vec_mult(self, c, x, Lapx, a=1.0):
         """Lapx = (a Lap + c) x (src/lapVecRoutines.c:37: a = 1; no potential, no projectors)."""

@@ -116,7 +116,7 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     cudaFree(ctx->d_alpha[1]);
     cudaFree(ctx->d_alpha_sum);
     for (int i = 0; i < 3; i++) if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
-    cudaFree(ctx->d_res_Y); cudaFree(ctx->d_res_W); cudaFree(ctx->d_gemm_ws); cudaFree(ctx->d_lanczos);
+    cudaFree(ctx->d_res_Y); cudaFree(ctx->d_res_W); cudaFree(ctx->d_res_T); cudaFree(ctx->d_gemm_ws); cudaFree(ctx->d_lanczos); cudaFree(ctx->d_aar);
     for (int i = 0; i < 3; i++) cudaFree(ctx->d_small[i]);
     for (int i = 0; i < 12; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     cudaFree(ctx->d_sync);
@@ -542,6 +542,16 @@ static int hmult_device(chefsi_ctx *ctx, int ncol, double c, const void *x, void
     prof.finish();
     return rc;
 }
+/* r = b + (Lap + c) x for one resident real column: the residual of aar.cu (poisson_residual, lapVecRoutines.c:61-79).
+   The stencil kernels evaluate s1 ((-1/2 Lap + c') x) - s2 xprev: s1 = -2, c' = c / s1, xprev = b, s2 = -1. */
+int lap_residual_device(chefsi_ctx *ctx, double c, const void *x, const void *b, void *r)
+{
+    Profiler prof(ctx);
+    const int rc = apply_step(ctx, prof, x, b, r, 1, c / -2.0, -2.0, -1.0, false, false, false, /*with_nl=*/false, /*with_veff=*/false);
+    prof.finish();
+    return rc;
+}
+
 /* one H apply (c = 0) of a single resident real column: the operator of lanczos.cu */
 int apply_h_device(chefsi_ctx *ctx, const void *x, void *Hx) { return hmult_device(ctx, 1, 0.0, x, Hx, false); }
 
@@ -711,9 +721,10 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     const int chunk = chunk_columns(ctx, ncol, esz);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
     /* KEEP_Y: the result also goes into the resident block of the subspace routines (subspace.cu) */
-    const bool keep_y = (flags & CHEFSI_FLAG_KEEP_Y) && !is_complex && ctx->d_res_Y && (size_t)ncol * ctx->ld * esz <= ctx->res_bytes;
+    const bool keep_y = (flags & CHEFSI_FLAG_KEEP_Y) && ctx->d_res_Y && (size_t)ncol * ctx->ld * esz <= ctx->res_bytes;
     const bool skip_y = keep_y && (flags & CHEFSI_FLAG_NO_Y_COPYBACK);
     ctx->res_ncol = 0;
+    ctx->res_unwritten_host = skip_y ? Y : nullptr;
     if (chunk == ncol && want_staging(ctx, X, Y, (size_t)ncol * ctx->Nd * esz)) {
         /* one small chunk in pageable memory: pinned staging, one stream, one synchronisation */
         const size_t row = ctx->Nd * esz, pitch = ctx->ld * esz;
@@ -728,7 +739,7 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
         CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
         if (!skip_y) staged_d2h_finish(ctx, 1, Y, ldo * esz, row, ncol);
         if (!(flags & CHEFSI_FLAG_NO_X_COPYBACK)) staged_d2h_finish(ctx, 2, X, ldi * esz, row, ncol);
-        if (keep_y) { ctx->res_ncol = ncol; ctx->res_host = Y; }
+        if (keep_y) { ctx->res_ncol = ncol; ctx->res_host = Y; ctx->res_complex = is_complex; }
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.last_filter_ms = ms; else cudaGetLastError();
         return 0;
@@ -790,7 +801,7 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) ctx->stats.last_filter_ms = ms; else cudaGetLastError();
-    if (keep_y) { ctx->res_ncol = ncol; ctx->res_host = Y; }
+    if (keep_y) { ctx->res_ncol = ncol; ctx->res_host = Y; ctx->res_complex = is_complex; }
     return 0;
 }
 
@@ -848,25 +859,13 @@ extern "C" int chefsi_hamiltonian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double c
 }
 
 /* ---- Rayleigh-Ritz projection / subspace rotation on the resident block (kernels: subspace.cu) ------------------- */
-static int ensure_small(chefsi_ctx *ctx, int ncol)
+static int subspace_reserve(chefsi_ctx *ctx, int ncol, bool is_complex)
 {
-    const size_t need = (size_t)ncol * ncol * sizeof(double);
-    if (need <= ctx->small_bytes) return 0;
-    for (int i = 0; i < 3; i++) { cudaFree(ctx->d_small[i]); ctx->d_small[i] = nullptr; }
-    ctx->small_bytes = 0;
-    for (int i = 0; i < 3; i++) CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_small[i], need));
-    ctx->small_bytes = need;
-    return 0;
-}
-
-extern "C" int chefsi_subspace_reserve(chefsi_ctx_t *ctx, int ncol)
-{
-    if (!ctx) return 1;
     if (ctx->multi) return chefsi_fail(ctx, "subspace routines take a single-device context");
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ncol <= 0) return chefsi_fail(ctx, "subspace_reserve: ncol must be positive");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t need = (size_t)ncol * ctx->ld * sizeof(double);
+    const size_t need = (size_t)ncol * ctx->ld * sizeof(double) * (is_complex ? 2 : 1);
     if (need > ctx->res_bytes) {
         cudaFree(ctx->d_res_Y); cudaFree(ctx->d_res_W);
         ctx->d_res_Y = ctx->d_res_W = nullptr;
@@ -880,64 +879,132 @@ extern "C" int chefsi_subspace_reserve(chefsi_ctx_t *ctx, int ncol)
         }
         ctx->res_bytes = need;
     }
-    return ensure_small(ctx, ncol);
+    if (is_complex && need > ctx->res_t_bytes) { /* third block: -i H Y, then i Y */
+        cudaFree(ctx->d_res_T);
+        ctx->d_res_T = nullptr;
+        ctx->res_t_bytes = 0;
+        if (cudaMalloc(&ctx->d_res_T, need) != cudaSuccess) {
+            cudaGetLastError();
+            return chefsi_fail(ctx, "subspace_reserve: the third block of %d complex columns does not fit on the device", ncol);
+        }
+        ctx->res_t_bytes = need;
+    }
+    /* Hp, Mp, Q: ncol x ncol (complex: twice that; Q split into real and imaginary parts) */
+    const size_t sm = (size_t)ncol * ncol * sizeof(double) * (is_complex ? 2 : 1);
+    if (sm > ctx->small_bytes) {
+        for (int i = 0; i < 3; i++) { cudaFree(ctx->d_small[i]); ctx->d_small[i] = nullptr; }
+        ctx->small_bytes = 0;
+        for (int i = 0; i < 3; i++) CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_small[i], sm));
+        ctx->small_bytes = sm;
+    }
+    return 0;
+}
+
+extern "C" int chefsi_subspace_reserve(chefsi_ctx_t *ctx, int ncol) { return ctx ? subspace_reserve(ctx, ncol, false) : 1; }
+extern "C" int chefsi_subspace_reserve_kpt(chefsi_ctx_t *ctx, int ncol) { return ctx ? subspace_reserve(ctx, ncol, true) : 1; }
+
+/* Hp = Y^H (H Y), Mp = Y^H Y.  Complex columns are handled as real columns of twice the length (subspace.cu). */
+static int subspace_project(chefsi_ctx *ctx, const void *Y, size_t ldy, int ncol, void *Hp, void *Mp, size_t ldp, bool is_complex)
+{
+    if (ncol <= 0 || ldp < (size_t)ncol || ldy < ctx->Nd) return chefsi_fail(ctx, "subspace_project: bad dimensions");
+    if (subspace_reserve(ctx, ncol, is_complex)) return 1;
+    const int words = is_complex ? 2 : 1;
+    const size_t esz = sizeof(double) * words, row = ctx->Nd * esz, pitch = ctx->ld * esz;
+    if (!(ctx->res_ncol == ncol && ctx->res_host == Y && ctx->res_complex == (int)is_complex)) {
+        if (ctx->res_unwritten_host == Y)
+            return chefsi_fail(ctx, "subspace_project: this Y was filtered with NO_Y_COPYBACK (its host copy was never written) and the "
+                                    "device copy does not match the call (%d columns, %s)", ncol, is_complex ? "complex" : "real");
+        /* Y is not resident: upload it (pinned or pageable, the driver stages the latter) */
+        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(ctx->d_res_Y, pitch, Y, ldy * esz, row, ncol, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->res_ncol = ncol;
+        ctx->res_host = Y;
+        ctx->res_complex = is_complex;
+    }
+    Profiler prof(ctx);
+    /* H Y with c = 0 (eigenSolver.c:960-967, eigenSolverKpt.c:699-704), in groups of columns */
+    const int grp = 256;
+    for (int c0 = 0; c0 < ncol; c0 += grp) {
+        const int nc = ncol - c0 < grp ? ncol - c0 : grp;
+        if (apply_step(ctx, prof, (const char *)ctx->d_res_Y + (size_t)c0 * pitch, nullptr, (char *)ctx->d_res_W + (size_t)c0 * pitch, nc, 0.0,
+                       1.0, 0.0, is_complex, false, false))
+            return drain_streams(ctx, 1);
+    }
+    double *dHp = (double *)ctx->d_small[0], *dMp = (double *)ctx->d_small[1];
+    const double *Yv = (const double *)ctx->d_res_Y, *Wv = (const double *)ctx->d_res_W;
+    const size_t K = ctx->Nd * words, ldv = ctx->ld * words; /* real view of the columns */
+    int n = launch_gemm_tn(ctx, Yv, ldv, Yv, ldv, ncol, ncol, K, 1.0, dMp, ncol, words);
+    if (n >= 0) { ctx->stats.kernel_launches += n; n = launch_gemm_tn(ctx, Yv, ldv, Wv, ldv, ncol, ncol, K, 1.0, dHp, ncol, words); }
+    if (n >= 0 && is_complex) {
+        /* imaginary parts: Im(A^H B) = A_view^T (-i B)_view */
+        ctx->stats.kernel_launches += n;
+        const double *Tv = (const double *)ctx->d_res_T;
+        n = launch_rot90(ctx, ctx->d_res_Y, ctx->d_res_T, ctx->Nd, ctx->ld, ncol, -1.0);
+        if (n >= 0) n = launch_gemm_tn(ctx, Yv, ldv, Tv, ldv, ncol, ncol, K, 1.0, dMp + 1, ncol, 2);
+        if (n >= 0) n = launch_rot90(ctx, ctx->d_res_W, ctx->d_res_T, ctx->Nd, ctx->ld, ncol, -1.0);
+        if (n >= 0) n = launch_gemm_tn(ctx, Yv, ldv, Tv, ldv, ncol, ncol, K, 1.0, dHp + 1, ncol, 2);
+        if (n >= 0) ctx->stats.kernel_launches += 6;
+    }
+    if (n < 0) return drain_streams(ctx, 1);
+    const size_t w = (size_t)ncol * esz;
+    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(Mp, ldp * esz, dMp, w, w, ncol, cudaMemcpyDeviceToHost, ctx->stream));
+    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(Hp, ldp * esz, dHp, w, w, ncol, cudaMemcpyDeviceToHost, ctx->stream));
+    CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
+    prof.finish();
+    return 0;
 }
 
 extern "C" int chefsi_subspace_project(chefsi_ctx_t *ctx, const double *Y, size_t ldy, int ncol, double *Hp, double *Mp, size_t ldp)
 {
     if (!ctx || !Y || !Hp || !Mp) return 1;
-    if (ncol <= 0 || ldp < (size_t)ncol || ldy < ctx->Nd) return chefsi_fail(ctx, "subspace_project: bad dimensions");
-    if (chefsi_subspace_reserve(ctx, ncol)) return 1;
-    const size_t row = ctx->Nd * sizeof(double), pitch = ctx->ld * sizeof(double);
-    if (!(ctx->res_ncol == ncol && ctx->res_host == (const void *)Y)) {
-        /* Y is not resident: upload it (pinned or pageable, the driver stages the latter) */
-        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(ctx->d_res_Y, pitch, Y, ldy * sizeof(double), row, ncol, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->res_ncol = ncol;
-        ctx->res_host = Y;
+    return subspace_project(ctx, Y, ldy, ncol, Hp, Mp, ldp, false);
+}
+extern "C" int chefsi_subspace_project_kpt(chefsi_ctx_t *ctx, const void *Y, size_t ldy, int ncol, void *Hp, void *Mp, size_t ldp)
+{
+    if (!ctx || !Y || !Hp || !Mp) return 1;
+    return subspace_project(ctx, Y, ldy, ncol, Hp, Mp, ldp, true);
+}
+
+static int subspace_rotate(chefsi_ctx *ctx, const void *Q, size_t ldq, int ncol, void *X, size_t ldx, bool is_complex)
+{
+    if (ctx->multi) return chefsi_fail(ctx, "subspace routines take a single-device context");
+    if (ctx->res_ncol != ncol || !ctx->d_res_Y || ctx->res_complex != (int)is_complex)
+        return chefsi_fail(ctx, "subspace_rotate: no resident block of %d columns (call chefsi_subspace_project first)", ncol);
+    if (ldq < (size_t)ncol || ldx < ctx->Nd) return chefsi_fail(ctx, "subspace_rotate: bad dimensions");
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int words = is_complex ? 2 : 1;
+    const size_t esz = sizeof(double) * words, w = (size_t)ncol * esz;
+    double *dQ = (double *)ctx->d_small[2];
+    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(dQ, w, Q, ldq * esz, w, ncol, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t K = ctx->Nd * words, ldv = ctx->ld * words;
+    int n;
+    if (!is_complex) {
+        n = launch_gemm_nn(ctx, (const double *)ctx->d_res_Y, ldv, dQ, ncol, K, ncol, ncol, (double *)ctx->d_res_W, ldv, 0);
+    } else {
+        /* (Y Q)_view = Y_view Q_r + (i Y)_view Q_i */
+        double *Qr = (double *)ctx->d_small[0], *Qi = (double *)ctx->d_small[1];
+        n = launch_split_complex(ctx, dQ, ncol, ncol, ncol, Qr, Qi);
+        if (n >= 0) n = launch_rot90(ctx, ctx->d_res_Y, ctx->d_res_T, ctx->Nd, ctx->ld, ncol, 1.0);
+        if (n >= 0) n = launch_gemm_nn(ctx, (const double *)ctx->d_res_Y, ldv, Qr, ncol, K, ncol, ncol, (double *)ctx->d_res_W, ldv, 0);
+        if (n >= 0) n = launch_gemm_nn(ctx, (const double *)ctx->d_res_T, ldv, Qi, ncol, K, ncol, ncol, (double *)ctx->d_res_W, ldv, 1);
+        if (n >= 0) n = 4;
     }
-    Profiler prof(ctx);
-    /* H Y with c = 0 (eigenSolver.c:960-967), in groups of columns the projector kernels' alpha buffers are sized for */
-    const int grp = 256;
-    for (int c0 = 0; c0 < ncol; c0 += grp) {
-        const int nc = ncol - c0 < grp ? ncol - c0 : grp;
-        if (apply_step(ctx, prof, (const char *)ctx->d_res_Y + (size_t)c0 * pitch, nullptr, (char *)ctx->d_res_W + (size_t)c0 * pitch, nc, 0.0,
-                       1.0, 0.0, false, false, false))
-            return drain_streams(ctx, 1);
-    }
-    double *dHp = (double *)ctx->d_small[0], *dMp = (double *)ctx->d_small[1];
-    int n = launch_gemm_tn(ctx, (const double *)ctx->d_res_Y, ctx->ld, (const double *)ctx->d_res_Y, ctx->ld, ncol, ncol, ctx->Nd, 1.0, dMp, ncol);
     if (n < 0) return drain_streams(ctx, 1);
     ctx->stats.kernel_launches += n;
-    n = launch_gemm_tn(ctx, (const double *)ctx->d_res_Y, ctx->ld, (const double *)ctx->d_res_W, ctx->ld, ncol, ncol, ctx->Nd, 1.0, dHp, ncol);
-    if (n < 0) return drain_streams(ctx, 1);
-    ctx->stats.kernel_launches += n;
-    const size_t w = (size_t)ncol * sizeof(double);
-    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(Mp, ldp * sizeof(double), dMp, w, w, ncol, cudaMemcpyDeviceToHost, ctx->stream));
-    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(Hp, ldp * sizeof(double), dHp, w, w, ncol, cudaMemcpyDeviceToHost, ctx->stream));
+    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(X, ldx * esz, ctx->d_res_W, ctx->ld * esz, ctx->Nd * esz, ncol, cudaMemcpyDeviceToHost, ctx->stream));
     CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
-    prof.finish();
+    ctx->res_ncol = 0; /* the block has been consumed */
     return 0;
 }
 
 extern "C" int chefsi_subspace_rotate(chefsi_ctx_t *ctx, const double *Q, size_t ldq, int ncol, double *X, size_t ldx)
 {
     if (!ctx || !Q || !X) return 1;
-    if (ctx->multi) return chefsi_fail(ctx, "subspace routines take a single-device context");
-    if (ctx->res_ncol != ncol || !ctx->d_res_Y) return chefsi_fail(ctx, "subspace_rotate: no resident block of %d columns (call chefsi_subspace_project first)", ncol);
-    if (ldq < (size_t)ncol || ldx < ctx->Nd) return chefsi_fail(ctx, "subspace_rotate: bad dimensions");
-    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (ensure_small(ctx, ncol)) return 1;
-    const size_t w = (size_t)ncol * sizeof(double);
-    double *dQ = (double *)ctx->d_small[2];
-    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(dQ, w, Q, ldq * sizeof(double), w, ncol, cudaMemcpyHostToDevice, ctx->stream));
-    const int n = launch_gemm_nn(ctx, (const double *)ctx->d_res_Y, ctx->ld, dQ, ncol, ctx->Nd, ncol, ncol, (double *)ctx->d_res_W, ctx->ld);
-    if (n < 0) return drain_streams(ctx, 1);
-    ctx->stats.kernel_launches += n;
-    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(X, ldx * sizeof(double), ctx->d_res_W, ctx->ld * sizeof(double), ctx->Nd * sizeof(double), ncol,
-                                             cudaMemcpyDeviceToHost, ctx->stream));
-    CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->res_ncol = 0; /* the block has been consumed */
-    return 0;
+    return subspace_rotate(ctx, Q, ldq, ncol, X, ldx, false);
+}
+extern "C" int chefsi_subspace_rotate_kpt(chefsi_ctx_t *ctx, const void *Q, size_t ldq, int ncol, void *X, size_t ldx)
+{
+    if (!ctx || !Q || !X) return 1;
+    return subspace_rotate(ctx, Q, ldq, ncol, X, ldx, true);
 }
 
 /* ---- (a Lap + c) x: the operator of the Poisson residual ------------------------------------------------------

@@ -114,9 +114,14 @@ struct chefsi_ctx {
        pageable path */
     /* subspace.cu: the filtered block kept on the device between ChebyshevFiltering, the projection and the rotation */
     void *d_res_Y = nullptr, *d_res_W = nullptr;   /* Y and a work block (H Y, then Y Q), ncol x ld each */
-    size_t res_bytes = 0;
+    void *d_res_T = nullptr;                       /* complex data only: -i H Y, then i Y */
+    size_t res_bytes = 0, res_t_bytes = 0;
+    int res_complex = 0;                           /* the resident Y is complex */
     int res_ncol = 0;                              /* columns of the resident Y (0: none) */
     const void *res_host = nullptr;                /* host address the resident Y stands for */
+    const void *res_unwritten_host = nullptr;      /* host block whose copy-back was skipped (NO_Y_COPYBACK): its contents are stale */
+    void *d_aar = nullptr;                         /* aar.cu: x, b, r, x_old, f, f_old, the two histories, scalars */
+    size_t aar_bytes = 0;
     void *d_lanczos = nullptr;                     /* lanczos.cu: three vectors + scalars */
     size_t lanczos_bytes = 0;
     void *d_gemm_ws = nullptr;                     /* split-K partial tiles */
@@ -193,9 +198,11 @@ void chefsi_free_nloc(NlocDev &d);
 
 /* subspace.cu */
 int launch_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B, size_t ldb, int M, int N, size_t K, double scale,
-                   double *C, size_t ldc);
+                   double *C, size_t ldc, int cstride);
 int launch_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q, size_t ldq, size_t K, int M, int N, double *C,
-                   size_t ldc);
+                   size_t ldc, int accumulate);
+int launch_rot90(chefsi_ctx *ctx, const void *in, void *out, size_t n, size_t ld, int ncol, double s);
+int launch_split_complex(chefsi_ctx *ctx, const void *Q, size_t ldq, int M, int N, double *Qr, double *Qi);
 
 /* util.cu */
 int launch_fill_random(chefsi_ctx *ctx, void *buf, int ncol, long long first_col, unsigned long long seed,

@@ -55,10 +55,18 @@ void Hamiltonian_vectors_mult_kpt_ref(const SPARC_OBJ *pSPARC, int DMnd, int *DM
 #ifdef USE_DP_SUBEIG
 void DP_Project_Hamiltonian_ref(SPARC_OBJ *pSPARC, int *DMVertices, double *Y, int ldi, double *HY, int ldo, double *Hp, double *Mp, int spn_i);
 void DP_Subspace_Rotation_ref(SPARC_OBJ *pSPARC, double *Psi_rot);
+void DP_Project_Hamiltonian_kpt_ref(SPARC_OBJ *pSPARC, int *DMVertices, double _Complex *Y, int ldi, double _Complex *HY, int ldo,
+                                    double _Complex *Hp, double _Complex *Mp, int spn_i, int kpt);
+void DP_Subspace_Rotation_kpt_ref(SPARC_OBJ *pSPARC, double _Complex *Psi_rot);
 #endif
 void Lanczos_ref(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc,
                  NLOC_PROJ_OBJ *nlocProj, double *eigmin, double *eigmax, double *x0, double TOL_min, double TOL_max, int MAXIT,
                  int k, int spn_i, MPI_Comm comm, MPI_Request *req_veff_loc);
+void AAR_ref(SPARC_OBJ *pSPARC, void (*res_fun)(SPARC_OBJ *, int, double, double *, double *, double *, MPI_Comm, double *),
+             void (*precond_fun)(SPARC_OBJ *, int, double, double *, double *, MPI_Comm), double c, int N, double *x, double *b,
+             double omega, double beta, int m, int p, double tol, int max_iter, MPI_Comm comm);
+void poisson_residual(SPARC_OBJ *pSPARC, int N, double c, double *x, double *b, double *r, MPI_Comm comm, double *time_info);
+void Jacobi_preconditioner(SPARC_OBJ *pSPARC, int N, double c, double *r, double *f, MPI_Comm comm);
 void Lap_vec_mult_ref(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c, double *x,
                       const int ldi, double *Lapx, const int ldo, MPI_Comm comm);
 
@@ -74,8 +82,8 @@ static struct {
     /* host registration of the caller's orbital arrays (pinned for full-rate async copies) */
     struct { void *base; size_t bytes; } pinned[64];
     int npinned;
-    unsigned long long n_filter, n_hmult, n_forward, n_lap, n_project, n_rotate, n_lanczos, n_lanczos_iter;
-    double t_lap, t_project, t_rotate, t_lanczos;
+    unsigned long long n_filter, n_hmult, n_forward, n_lap, n_project, n_rotate, n_lanczos, n_lanczos_iter, n_aar, n_aar_iter;
+    double t_lap, t_project, t_rotate, t_lanczos, t_aar;
     int subspace_pending;    /* the last DP_Project_Hamiltonian ran on the device: DP_Subspace_Rotation finds its block there */
     int multi;               /* the context owns several devices */
     double t_filter;
@@ -83,6 +91,14 @@ static struct {
     unsigned long long n_filter_fwd; /* ChebyshevFiltering calls forwarded to the reference, and their seconds */
     double t_filter_fwd;
 } G;
+
+/* the context will own several devices (CHEFSI_B200_DEVICES="0,1,..."): known before the context exists, because the
+ * single-device-only routines (Lanczos, AAR, the subspace steps) decide on it before their first call creates it */
+static int shim_is_multi(void)
+{
+    const char *devs = getenv("CHEFSI_B200_DEVICES");
+    return devs && strchr(devs, ',') != NULL;
+}
 
 static void shim_fatal(const char *what)
 {
@@ -112,6 +128,9 @@ static void shim_report(void)
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] %llu Lanczos calls (%llu iterations) %.3f s with the vectors resident on the device\n",
                 G.n_lanczos, G.n_lanczos_iter, G.t_lanczos);
+    if (G.verbose)
+        fprintf(stderr, "[chefsi_b200 shim] %llu AAR solves (Poisson, Kerker; %llu iterations) %.3f s with the vectors resident on the device\n",
+                G.n_aar, G.n_aar_iter, G.t_aar);
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] context creation %.3f s, Hamiltonian_vectors_mult calls %.3f s, grid/projector/Veff "
                         "synchronisation %.3f s (included in the call times)\n", G.t_init, G.t_hmult, G.t_sync);
@@ -507,10 +526,25 @@ static void shim_dump_outputs(FILE *f, const SPARC_OBJ *S, int is_kpt, const voi
 static int shim_subspace_ok(const SPARC_OBJ *S, int ncol)
 {
 #ifdef USE_DP_SUBEIG
-    if (getenv("CHEFSI_B200_NO_SUBSPACE") || G.multi) return 0;
+    if (getenv("CHEFSI_B200_NO_SUBSPACE") || shim_is_multi()) return 0;
     DP_CheFSI_t dp = (DP_CheFSI_t)S->DP_CheFSI;
     if (!dp || dp->nproc_row != 1 || dp->nproc_kpt != 1) return 0;
     if (S->StandardEigenFlag || S->CyclixFlag) return 0;
+    if (dp->Ns_dp != ncol || dp->Ns_bp != ncol || dp->Nd_dp != S->Nd) return 0;
+    return 1;
+#else
+    (void)S; (void)ncol;
+    return 0;
+#endif
+}
+
+static int shim_subspace_ok_kpt(const SPARC_OBJ *S, int ncol)
+{
+#ifdef USE_DP_SUBEIG
+    if (getenv("CHEFSI_B200_NO_SUBSPACE") || shim_is_multi()) return 0;
+    DP_CheFSI_kpt_t dp = (DP_CheFSI_kpt_t)S->DP_CheFSI_kpt;
+    if (!dp || dp->nproc_row != 1 || dp->nproc_kpt != 1) return 0;
+    if (S->CyclixFlag) return 0;
     if (dp->Ns_dp != ncol || dp->Ns_bp != ncol || dp->Nd_dp != S->Nd) return 0;
     return 1;
 #else
@@ -609,7 +643,9 @@ void ChebyshevFiltering_kpt(SPARC_OBJ *pSPARC, int *DMVertices, double _Complex 
         shim_pin(X - (size_t)spn_i * DMnd, sizeof(double _Complex) * (size_t)ldi * ncol);
         shim_pin(Y - (size_t)spn_i * DMnd, sizeof(double _Complex) * (size_t)ldo * ncol);
     }
-    const int flags = getenv("CHEFSI_B200_X_COPYBACK") ? 0 : CHEFSI_FLAG_NO_X_COPYBACK; /* sole caller eigenSolverKpt.c:246 reuses X as scratch */
+    int flags = getenv("CHEFSI_B200_X_COPYBACK") ? 0 : CHEFSI_FLAG_NO_X_COPYBACK; /* sole caller eigenSolverKpt.c:246 reuses X as scratch */
+    if (shim_subspace_ok_kpt(pSPARC, ncol) && chefsi_subspace_reserve_kpt(G.ctx, ncol) == 0)
+        flags |= CHEFSI_FLAG_KEEP_Y | CHEFSI_FLAG_NO_Y_COPYBACK; /* projection and rotation follow on the device (eigenSolverKpt.c:262,330) */
     if (chefsi_chebyshev_filter_kpt(G.ctx, X, (size_t)ldi, Y, (size_t)ldo, ncol, m, a, b, a0, flags) != 0)
         shim_fatal("chefsi_chebyshev_filter_kpt");
     *time_info = MPI_Wtime() - t1;
@@ -725,13 +761,56 @@ void DP_Subspace_Rotation(SPARC_OBJ *pSPARC, double *Psi_rot)
 {
     DP_CheFSI_t dp = (DP_CheFSI_t)pSPARC->DP_CheFSI;
     if (dp == NULL) return;
-    if (!G.subspace_pending) {
+    if (G.subspace_pending != 1) {
         DP_Subspace_Rotation_ref(pSPARC, Psi_rot);
         return;
     }
     const double t1 = MPI_Wtime();
     if (chefsi_subspace_rotate(G.ctx, dp->eig_vecs, (size_t)dp->Ns_dp, dp->Ns_dp, Psi_rot, (size_t)dp->Ndsp_bp) != 0)
         shim_fatal("chefsi_subspace_rotate");
+    G.subspace_pending = 0;
+    G.n_rotate++;
+    G.t_rotate += MPI_Wtime() - t1;
+}
+#endif
+
+#ifdef USE_DP_SUBEIG
+/* k-point variants: Hp = Y^H H Y, Mp = Y^H Y (src/eigenSolverKpt.c:676-790), Psi_rot = Y Q (:947-1010) */
+void DP_Project_Hamiltonian_kpt(SPARC_OBJ *pSPARC, int *DMVertices, double _Complex *Y, int ldi, double _Complex *HY, int ldo,
+                                double _Complex *Hp, double _Complex *Mp, int spn_i, int kpt)
+{
+    DP_CheFSI_kpt_t dp = (DP_CheFSI_kpt_t)pSPARC->DP_CheFSI_kpt;
+    if (dp == NULL) return;
+    const int DMnd = (1 - DMVertices[0] + DMVertices[1]) * (1 - DMVertices[2] + DMVertices[3]) * (1 - DMVertices[4] + DMVertices[5]);
+    G.subspace_pending = 0;
+    if (!G.ctx || !shim_supported(pSPARC, DMnd, DMVertices, pSPARC->dmcomm, pSPARC->nlocProj) || !shim_subspace_ok_kpt(pSPARC, dp->Ns_dp)) {
+        DP_Project_Hamiltonian_kpt_ref(pSPARC, DMVertices, Y, ldi, HY, ldo, Hp, Mp, spn_i, kpt);
+        return;
+    }
+    const double t1 = MPI_Wtime();
+    shim_sync_grid(pSPARC);
+    shim_sync_projectors(pSPARC, pSPARC->Atom_Influence_nloc, pSPARC->nlocProj, 1);
+    const int sg = pSPARC->spin_start_indx + spn_i;
+    shim_sync_veff(pSPARC->Veff_loc_dmcomm + (size_t)sg * pSPARC->Nd_d_dmcomm, (size_t)pSPARC->Nd);
+    if (chefsi_set_kpoint(G.ctx, pSPARC->k1_loc[kpt], pSPARC->k2_loc[kpt], pSPARC->k3_loc[kpt]) != 0) shim_fatal("chefsi_set_kpoint");
+    if (chefsi_subspace_project_kpt(G.ctx, Y, (size_t)ldi, dp->Ns_dp, dp->Hp_local, dp->Mp_local, (size_t)dp->Ns_dp) != 0)
+        shim_fatal("chefsi_subspace_project_kpt");
+    G.subspace_pending = 2;
+    G.n_project++;
+    G.t_project += MPI_Wtime() - t1;
+}
+
+void DP_Subspace_Rotation_kpt(SPARC_OBJ *pSPARC, double _Complex *Psi_rot)
+{
+    DP_CheFSI_kpt_t dp = (DP_CheFSI_kpt_t)pSPARC->DP_CheFSI_kpt;
+    if (dp == NULL) return;
+    if (G.subspace_pending != 2) {
+        DP_Subspace_Rotation_kpt_ref(pSPARC, Psi_rot);
+        return;
+    }
+    const double t1 = MPI_Wtime();
+    if (chefsi_subspace_rotate_kpt(G.ctx, dp->eig_vecs, (size_t)dp->Ns_dp, dp->Ns_dp, Psi_rot, (size_t)dp->Ndsp_bp) != 0)
+        shim_fatal("chefsi_subspace_rotate_kpt");
     G.subspace_pending = 0;
     G.n_rotate++;
     G.t_rotate += MPI_Wtime() - t1;
@@ -746,7 +825,7 @@ void Lanczos(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NL
              NLOC_PROJ_OBJ *nlocProj, double *eigmin, double *eigmax, double *x0, double TOL_min, double TOL_max, int MAXIT,
              int k, int spn_i, MPI_Comm comm, MPI_Request *req_veff_loc)
 {
-    int ok = (comm != MPI_COMM_NULL) && !G.multi && !getenv("CHEFSI_B200_NO_LANCZOS") && pSPARC->kptcomm_inter == MPI_COMM_NULL;
+    int ok = (comm != MPI_COMM_NULL) && !shim_is_multi() && !getenv("CHEFSI_B200_NO_LANCZOS") && pSPARC->kptcomm_inter == MPI_COMM_NULL;
     int DMnd = 0;
     if (ok) {
         DMnd = (1 - DMVertices[0] + DMVertices[1]) * (1 - DMVertices[2] + DMVertices[3]) * (1 - DMVertices[4] + DMVertices[5]);
@@ -770,4 +849,38 @@ void Lanczos(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NL
     }
     Lanczos_ref(pSPARC, DMVertices, Veff_loc, Atom_Influence_nloc, nlocProj, eigmin, eigmax, x0, TOL_min, TOL_max, MAXIT, k, spn_i,
                 comm, req_veff_loc);
+}
+
+/* Alternating Anderson-Richardson solve -- src/linearSolver.c:38-146.  SPARC calls it with one operator
+ * pair only: poisson_residual + Jacobi_preconditioner (the Poisson solve, electrostatics.c:1658, and the Kerker
+ * preconditioner, mixing.c:501).  That pair on an unsplit domain runs on the device with x and b resident
+ * (chefsi_poisson_aar); any other pair, communicator or cell goes to the reference routine. */
+void AAR(SPARC_OBJ *pSPARC, void (*res_fun)(SPARC_OBJ *, int, double, double *, double *, double *, MPI_Comm, double *),
+         void (*precond_fun)(SPARC_OBJ *, int, double, double *, double *, MPI_Comm), double c, int N, double *x, double *b,
+         double omega, double beta, int m, int p, double tol, int max_iter, MPI_Comm comm)
+{
+    if (comm == MPI_COMM_NULL) return; /* linearSolver.c:48 */
+    int ok = res_fun == poisson_residual && precond_fun == Jacobi_preconditioner && !shim_is_multi() && m >= 1 && m <= 16 &&
+             !getenv("CHEFSI_B200_DISABLE") && !getenv("CHEFSI_B200_NO_AAR") && !getenv("CHEFSI_B200_NO_LAP");
+    if (ok) {
+        int nproc = 1;
+        MPI_Comm_size(comm, &nproc);
+        const int FDn = pSPARC->order / 2;
+        ok = nproc == 1 && N == pSPARC->Nd && !pSPARC->CyclixFlag && (pSPARC->cell_typ == 0 || (pSPARC->cell_typ >= 11 && pSPARC->cell_typ <= 17)) &&
+             FDn <= CHEFSI_MAX_FDN && !((pSPARC->BCx == 0 && pSPARC->Nx < FDn) || (pSPARC->BCy == 0 && pSPARC->Ny < FDn) || (pSPARC->BCz == 0 && pSPARC->Nz < FDn)) &&
+             pSPARC->DMVertices[0] == 0 && pSPARC->DMVertices[1] == pSPARC->Nx - 1 && pSPARC->DMVertices[2] == 0 &&
+             pSPARC->DMVertices[3] == pSPARC->Ny - 1 && pSPARC->DMVertices[4] == 0 && pSPARC->DMVertices[5] == pSPARC->Nz - 1;
+    }
+    if (!ok) {
+        AAR_ref(pSPARC, res_fun, precond_fun, c, N, x, b, omega, beta, m, p, tol, max_iter, comm);
+        return;
+    }
+    shim_init();
+    const double t1 = MPI_Wtime();
+    shim_sync_grid(pSPARC);
+    int iters = 0;
+    if (chefsi_poisson_aar(G.ctx, c, x, b, omega, beta, m, p, tol, max_iter, &iters, NULL) != 0) shim_fatal("chefsi_poisson_aar");
+    G.n_aar++;
+    G.n_aar_iter += (unsigned long long)iters;
+    G.t_aar += MPI_Wtime() - t1;
 }

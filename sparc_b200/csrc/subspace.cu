@@ -16,6 +16,9 @@
  *            K cut into slabs over CTAs (split-K: tall-skinny operands would otherwise fill only a few SMs); every
  *            slab writes its partial tile, a second kernel adds the slabs in a fixed order (deterministic).
  *   gemm_nn  C(K x N) = A Q,  A: K x M, Q: M x N.  CTA tile 128 rows x 64 columns, loop over M.
+ * Complex (k-point) data: a complex column is a real column of twice the length (re, im interleaved), so
+ *   Re(A^H B) = A_view^T B_view,  Im(A^H B) = A_view^T (-i B)_view,   (A Q)_view = A_view Q_r + (i A)_view Q_i
+ * -- two real DMMA products each, plus one rotation pass (rot90_kernel) that forms -i B or i A.
  * Both stage 32-deep operand chunks with 16-byte cp.async into a 3-stage shared-memory ring; fragments are read
  * with bank-conflict-free pitches (pitch = 4 mod 16 doubles).
  */
@@ -131,7 +134,7 @@ gemm_tn_kernel(const double *__restrict__ A, size_t lda, const double *__restric
 
 /* C[m + n ldc] = scale * sum over slabs (fixed order) of the partial tiles */
 __global__ void gemm_tn_reduce_kernel(const double *__restrict__ part, int nslab, int ntiles, int tiles_m, int M, int N, double scale,
-                                      double *__restrict__ C, size_t ldc)
+                                      double *__restrict__ C, size_t ldc, int cstride)
 {
     const size_t total = (size_t)ntiles * 4096;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -140,7 +143,7 @@ __global__ void gemm_tn_reduce_kernel(const double *__restrict__ part, int nslab
         if (m >= M || n >= N) continue;
         double s = 0.0;
         for (int sl = 0; sl < nslab; sl++) s += part[(size_t)sl * total + e];
-        C[(size_t)n * ldc + m] = scale * s;
+        C[((size_t)n * ldc + m) * cstride] = scale * s;
     }
 }
 
@@ -150,7 +153,7 @@ constexpr int RPITCH = RT + 4;   /* 132 = 4 mod 16 */
 /* grid: (row tiles, column tiles of 64); block 256 = 8 warps as 4 (rows) x 2 (cols): warp tile 32 rows x 32 columns */
 __global__ void __launch_bounds__(256)
 gemm_nn_kernel(const double *__restrict__ A, size_t lda, const double *__restrict__ Qm, size_t ldq, size_t K, int M, int N,
-               double *__restrict__ C, size_t ldc)
+               double *__restrict__ C, size_t ldc, int accumulate)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sA = reinterpret_cast<double *>(smem_raw);   /* [NSTG][KC (m)][RPITCH]: column m of A, rows contiguous */
@@ -228,10 +231,32 @@ gemm_nn_kernel(const double *__restrict__ A, size_t lda, const double *__restric
             const size_t r = r0 + wr + i * 8 + (lane >> 2);
             const int cc = n0 + wn + j * 8 + 2 * (lane & 3);
             if (r < K) {
-                if (cc < N) C[(size_t)cc * ldc + r] = acc[i][j][0];
-                if (cc + 1 < N) C[(size_t)(cc + 1) * ldc + r] = acc[i][j][1];
+                if (cc < N) C[(size_t)cc * ldc + r] = acc[i][j][0] + (accumulate ? C[(size_t)cc * ldc + r] : 0.0);
+                if (cc + 1 < N) C[(size_t)(cc + 1) * ldc + r] = acc[i][j][1] + (accumulate ? C[(size_t)(cc + 1) * ldc + r] : 0.0);
             }
         }
+}
+
+/* out = s * i * in on interleaved complex columns: (re, im) -> s * (-im, re).  s = +1: i z, s = -1: -i z */
+__global__ void rot90_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, size_t n, size_t ld, double s)
+{
+    const double2 *ci = in + (size_t)blockIdx.y * ld;
+    double2 *co = out + (size_t)blockIdx.y * ld;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double2 z = ci[i];
+        co[i] = make_double2(-s * z.y, s * z.x);
+    }
+}
+
+/* Q (complex, M x N, interleaved, ld ldq) -> Qr, Qi (real M x N, ld M) */
+__global__ void split_complex_kernel(const double2 *__restrict__ Q, size_t ldq, int M, int N, double *__restrict__ Qr, double *__restrict__ Qi)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)M * N; e += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(e % M), n = (int)(e / M);
+        const double2 z = Q[(size_t)n * ldq + m];
+        Qr[e] = z.x;
+        Qi[e] = z.y;
+    }
 }
 
 int ensure_bytes(chefsi_ctx *ctx, void **p, size_t *have, size_t need)
@@ -250,7 +275,7 @@ int ensure_bytes(chefsi_ctx *ctx, void **p, size_t *have, size_t need)
 
 /* C(M x N, ld ldc, device) = scale * A^T B with A: K x M (lda), B: K x N (ldb), all device, column-major */
 int launch_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B, size_t ldb, int M, int N, size_t K, double scale,
-                   double *C, size_t ldc)
+                   double *C, size_t ldc, int cstride)
 {
     const int tiles_m = (M + 63) / 64, tiles_n = (N + 63) / 64, ntiles = tiles_m * tiles_n;
     /* slabs: enough CTAs to fill the GPU twice, at least 8 chunks per slab */
@@ -268,7 +293,7 @@ int launch_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B
     gemm_tn_kernel<<<dim3((unsigned)ntiles, (unsigned)nslab), 256, smem, ctx->stream>>>(A, lda, B, ldb, M, N, K, kslab, tiles_m,
                                                                                           (double *)ctx->d_gemm_ws);
     gemm_tn_reduce_kernel<<<std::min(4 * ctx->num_sms, (ntiles * 4096 + 255) / 256), 256, 0, ctx->stream>>>(
-        (const double *)ctx->d_gemm_ws, (int)nslab, ntiles, tiles_m, M, N, scale, C, ldc);
+        (const double *)ctx->d_gemm_ws, (int)nslab, ntiles, tiles_m, M, N, scale, C, ldc, cstride);
     e = cudaGetLastError();
     if (e != cudaSuccess) { chefsi_fail(ctx, "gemm_tn launch: %s", cudaGetErrorString(e)); return -1; }
     return 2;
@@ -276,15 +301,33 @@ int launch_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B
 
 /* C(K x N, ldc) = A Q with A: K x M (lda), Q: M x N (ldq); C must not alias A */
 int launch_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q, size_t ldq, size_t K, int M, int N, double *C,
-                   size_t ldc)
+                   size_t ldc, int accumulate)
 {
     const size_t smem = ((size_t)NSTG * KC * RPITCH + (size_t)NSTG * 64 * PITCH) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(gemm_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(gemm_nn): %s", cudaGetErrorString(e)); return -1; }
     const size_t rt = (K + RT - 1) / RT;
     if (rt > 0x7fffffffULL) { chefsi_fail(ctx, "gemm_nn: too many row tiles"); return -1; }
-    gemm_nn_kernel<<<dim3((unsigned)rt, (unsigned)((N + 63) / 64)), 256, smem, ctx->stream>>>(A, lda, Q, ldq, K, M, N, C, ldc);
+    gemm_nn_kernel<<<dim3((unsigned)rt, (unsigned)((N + 63) / 64)), 256, smem, ctx->stream>>>(A, lda, Q, ldq, K, M, N, C, ldc, accumulate);
     e = cudaGetLastError();
     if (e != cudaSuccess) { chefsi_fail(ctx, "gemm_nn launch: %s", cudaGetErrorString(e)); return -1; }
+    return 1;
+}
+
+/* out = s * i * in for ncol interleaved complex columns of n elements (column stride ld complex elements) */
+int launch_rot90(chefsi_ctx *ctx, const void *in, void *out, size_t n, size_t ld, int ncol, double s)
+{
+    if (ncol <= 0) return 0;
+    rot90_kernel<<<dim3(64, (unsigned)ncol), 256, 0, ctx->stream>>>((const double2 *)in, (double2 *)out, n, ld, s);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { chefsi_fail(ctx, "rot90 launch: %s", cudaGetErrorString(e)); return -1; }
+    return 1;
+}
+
+int launch_split_complex(chefsi_ctx *ctx, const void *Q, size_t ldq, int M, int N, double *Qr, double *Qi)
+{
+    split_complex_kernel<<<64, 256, 0, ctx->stream>>>((const double2 *)Q, ldq, M, N, Qr, Qi);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { chefsi_fail(ctx, "split launch: %s", cudaGetErrorString(e)); return -1; }
     return 1;
 }

@@ -27,17 +27,21 @@ def _setup(ctx, g, veff, proj):
     ctx.set_kpoint((0, 0, 0))
 
 
-def _check(ctx, port, g, veff, proj, y, resident_from_filter=None):
+def _check(ctx, port, g, veff, proj, y, kvec=(0, 0, 0)):
     ncol = y.shape[0]
-    Hp, Mp = np.zeros((ncol, ncol + 3)), np.zeros((ncol, ncol + 3))   # ld > ncol
+    Hp, Mp = np.zeros((ncol, ncol + 3), dtype=y.dtype), np.zeros((ncol, ncol + 3), dtype=y.dtype)   # ld > ncol
     ctx.DP_Project_Hamiltonian(y, Hp, Mp)
-    hy = port.hamiltonian_mult(g, proj, veff, 0.0, y)
-    assert rel_fro(Mp[:, :ncol], y @ y.T) < TOL
-    assert rel_fro(Hp[:, :ncol], hy @ y.T) < TOL                      # element (m, n) = y_m . (H y_n), stored column-major
+    hy = port.hamiltonian_mult(g, proj, veff, 0.0, y, kvec=kvec)
+    # element (m, n) = conj(y_m) . (H y_n), stored column-major: numpy Hp[n, m]
+    assert rel_fro(Mp[:, :ncol], y @ y.conj().T) < TOL
+    assert rel_fro(Hp[:, :ncol], hy @ y.conj().T) < TOL
     assert (Hp[:, ncol:] == 0).all() and (Mp[:, ncol:] == 0).all()
     rng = np.random.default_rng(5)
-    Q = np.ascontiguousarray(rng.standard_normal((ncol, ncol)))        # Q[n, m] = element (m, n) of the column-major matrix
-    X = np.full((ncol, g.Nd + 5), 3.0)
+    Q = rng.standard_normal((ncol, ncol))                              # Q[n, m] = element (m, n) of the column-major matrix
+    if np.iscomplexobj(y):
+        Q = Q + 1j * rng.standard_normal((ncol, ncol))
+    Q = np.ascontiguousarray(Q)
+    X = np.full((ncol, g.Nd + 5), 3.0, dtype=y.dtype)
     ctx.DP_Subspace_Rotation(Q, X)
     assert rel_fro(X[:, :g.Nd], Q @ y) < TOL
     assert (X[:, g.Nd:] == 3.0).all()
@@ -50,6 +54,24 @@ def test_project_and_rotate_small(ctx, port, cell_typ, ncol):
     _check(ctx, port, g, veff, proj, y)
 
 
+@pytest.mark.parametrize("cell_typ,ncol", [(0, 9), (17, 12)])
+def test_project_and_rotate_kpt(ctx, port, cell_typ, ncol):
+    """Complex (k-point) variants: Hp = Y^H H Y, Mp = Y^H Y (zgemm ConjTrans, eigenSolverKpt.c:749-770), X = Y Q."""
+    from tests.cases import KVEC
+    g, veff, proj, y = small_case(cell_typ, ncol=ncol, complex_=True)
+    _setup(ctx, g, veff, proj)
+    ctx.set_kpoint(KVEC)
+    _check(ctx, port, g, veff, proj, y, kvec=KVEC)
+
+
+def test_project_and_rotate_kpt_streaming_kernel(ctx, port):
+    from tests.cases import KVEC
+    g, veff, proj, y = overlap_case("stream", ncol=70, complex_=True)
+    _setup(ctx, g, veff, proj)
+    ctx.set_kpoint(KVEC)
+    _check(ctx, port, g, veff, proj, y, kvec=KVEC)
+
+
 def test_project_and_rotate_streaming_kernel_many_columns(ctx, port):
     """More columns than one 64 x 64 GEMM tile, streaming stencil kernel, overlapping spheres, several K slabs."""
     g, veff, proj, y = overlap_case("stream", ncol=70)
@@ -57,23 +79,29 @@ def test_project_and_rotate_streaming_kernel_many_columns(ctx, port):
     _check(ctx, port, g, veff, proj, y)
 
 
-def test_filter_keeps_y_resident(ctx, port):
+@pytest.mark.parametrize("complex_", [False, True])
+def test_filter_keeps_y_resident(ctx, port, complex_):
     """ChebyshevFiltering with KEEP_Y and no Y copy-back, then projection and rotation from the device copy: the
-    sequence CheFSI runs (eigenSolver.c:325-420); Y never visits the host."""
-    g, veff, proj, x = small_case(17, ncol=12)
+    sequence CheFSI[_kpt] runs (eigenSolver.c:325-420, eigenSolverKpt.c:246-313); Y never visits the host."""
+    from tests.cases import KVEC
+    g, veff, proj, x = small_case(17, ncol=12, complex_=complex_)
     _setup(ctx, g, veff, proj)
+    kvec = KVEC if complex_ else (0, 0, 0)
+    ctx.set_kpoint(kvec)
     a, b, a0 = 0.5, 40.0, -0.6
-    ctx.subspace_reserve(12)
+    ctx.subspace_reserve(12, is_complex=complex_)
     X = x.copy()
     Y = np.full_like(x, np.nan)
     ctx.ChebyshevFiltering(X, Y, 7, a, b, a0, copy_back_x=False, keep_y=True, copy_back_y=False)
     assert np.isnan(Y).all()                                           # untouched on the host
-    _, Yw = port.chebyshev_filter(g, proj, veff, x, 7, a, b, a0)
-    Hp, Mp = np.zeros((12, 12)), np.zeros((12, 12))
+    _, Yw = port.chebyshev_filter(g, proj, veff, x, 7, a, b, a0, kvec=kvec)
+    Hp, Mp = np.zeros((12, 12), dtype=x.dtype), np.zeros((12, 12), dtype=x.dtype)
     ctx.DP_Project_Hamiltonian(Y, Hp, Mp)                              # same host address: the device copy is used
-    assert rel_fro(Mp, Yw @ Yw.T) < TOL
-    assert rel_fro(Hp, port.hamiltonian_mult(g, proj, veff, 0.0, Yw) @ Yw.T) < TOL
-    Q = np.ascontiguousarray(np.random.default_rng(1).standard_normal((12, 12)))
+    assert rel_fro(Mp, Yw @ Yw.conj().T) < TOL
+    assert rel_fro(Hp, port.hamiltonian_mult(g, proj, veff, 0.0, Yw, kvec=kvec) @ Yw.conj().T) < TOL
+    rng = np.random.default_rng(1)
+    Q = rng.standard_normal((12, 12)) + (1j * rng.standard_normal((12, 12)) if complex_ else 0.0)
+    Q = np.ascontiguousarray(Q.astype(x.dtype))
     Xr = np.empty_like(x)
     ctx.DP_Subspace_Rotation(Q, Xr)
     assert rel_fro(Xr, Q @ Yw) < TOL
@@ -114,3 +142,55 @@ def test_lanczos_extreme_eigenvalues(ctx, port, cell_typ, BC):
             break
     assert it == j
     assert abs(lo - emin) < 1e-9 * max(1.0, abs(emax)) and abs(hi - emax) < 1e-9 * max(1.0, abs(emax))
+
+
+def _aar_host(port, g, c, x, b, omega, beta, m, p, tol, max_iter):
+    """AAR (linearSolver.c:38-146) with poisson_residual + Jacobi_preconditioner replayed on the host: the oracle's
+    Laplacian, numpy's lstsq (minimum-norm, like LAPACKE_dgelsd) for the Anderson coefficients."""
+    lap = lambda v: port.lap_plus_diag(g, 1.0, 0.0, c, None, v[None, :].copy())[0]
+    N = x.size
+    m_inv = g.coefs["D2_x"][0] + g.coefs["D2_y"][0] + g.coefs["D2_z"][0] + c
+    m_inv = -1.0 / (1.0 if abs(m_inv) < 1e-14 else m_inv)
+    x = x.copy()
+    x_old, f_old = x.copy(), np.zeros(N)
+    X, F = np.zeros((m, N)), np.zeros((m, N))
+    r = b + lap(x)
+    tol = tol * np.linalg.norm(b)
+    r_2norm, it = tol + 1.0, 0
+    while r_2norm > tol and it < max_iter:
+        f = m_inv * r
+        if it > 0:
+            h = (it - 1) % m
+            X[h], F[h] = x - x_old, f - f_old
+        x_old, f_old = x.copy(), f.copy()
+        if (it + 1) % p == 0 and it > 0:
+            G = np.linalg.lstsq(F @ F.T, F @ f, rcond=None)[0]
+            x = x_old - G @ X + beta * (f - G @ F)
+            r = b + lap(x)
+            r_2norm = np.linalg.norm(r)
+        else:
+            x = x_old + omega * f
+            r = b + lap(x)
+        it += 1
+    return x, it, r_2norm
+
+
+@pytest.mark.parametrize("cell_typ,BC,c", [(0, (1, 1, 1), 0.0), (17, (0, 0, 0), -0.35), (0, (0, 1, 0), -0.2)])
+def test_aar_poisson_solve(ctx, port, cell_typ, BC, c):
+    """chefsi_poisson_aar against a host replay of the reference's AAR (same operator pair, parameters and stopping
+    rule): same iteration count, solution equal to solver tolerance, and the residual of the returned x really is small."""
+    g, veff, proj, _ = small_case(cell_typ, BC, ncol=1)
+    _setup(ctx, g, veff, proj)
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(g.Nd)
+    if c == 0.0 and BC == (0, 0, 0):
+        b -= b.mean()
+    x0 = np.zeros(g.Nd)
+    x = x0.copy()
+    it, rn = ctx.AAR(c, x, b, tol=1e-8, max_iter=600)
+    xh, ith, rnh = _aar_host(port, g, c, x0, b, 0.6, 0.6, 7, 6, 1e-8, 600)
+    assert abs(it - ith) <= 6 and it < 600   # the norm is tested every p = 6 steps; rounding may move the stop by one test
+    assert np.linalg.norm(x - xh) <= 1e-5 * np.linalg.norm(xh)
+    r = b + port.lap_plus_diag(g, 1.0, 0.0, c, None, x[None, :].copy())[0]
+    assert np.linalg.norm(r) <= 1.0001e-8 * np.linalg.norm(b)
+    assert abs(rn - np.linalg.norm(r)) <= 1e-6 * np.linalg.norm(r)
