@@ -89,6 +89,7 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
     if (getenv("CHEFSI_B200_GRIDSYNC")) ctx->stream_gridsync = atoi(getenv("CHEFSI_B200_GRIDSYNC"));
     if (getenv("CHEFSI_B200_ALPHA_REDUCE_MIN")) ctx->alpha_reduce_min = atoi(getenv("CHEFSI_B200_ALPHA_REDUCE_MIN"));
     if (getenv("CHEFSI_B200_FAST_SMALL")) ctx->fast_small = atoi(getenv("CHEFSI_B200_FAST_SMALL"));
+    if (getenv("CHEFSI_B200_SMALL_BRICK")) ctx->small_brick = atoi(getenv("CHEFSI_B200_SMALL_BRICK"));
     if (getenv("CHEFSI_B200_TMA_L2PROMO")) ctx->tma_l2promo = atoi(getenv("CHEFSI_B200_TMA_L2PROMO")) & 3;
     *out = ctx;
     return 0;
@@ -457,6 +458,17 @@ static int apply_step(chefsi_ctx *ctx, Profiler &prof, const void *x, const void
         if (stream_mixed_supported(ctx, is_complex)) {
             n = launch_stencil_stream_mixed(ctx, a); /* -2: tables without the structure the kernel folds */
             ctx->stats.last_path = 3;
+        }
+        /* a launch with fewer z-marching CTAs than SMs (single columns of Lanczos / the AAR iteration on the SCF test
+           systems: 4-15 CTAs that walk the whole z extent) is latency-bound; the 3-D brick kernel cuts z as well
+           (Au_fcc211: 125 bricks per column) */
+        if (n == -2 && ctx->small_brick && ctx->force_general < 2) {
+            const int tx = is_complex ? 16 : 32, ty = is_complex ? 16 : 8;
+            const long long ctas = (long long)ncol * ((ctx->grid.Nx + tx - 1) / tx) * ((ctx->grid.Ny + ty - 1) / ty);
+            if (ctas * 2 < ctx->num_sms) {
+                n = launch_stencil_general(ctx, a, is_complex);
+                ctx->stats.last_path = 0;
+            }
         }
         if (n == -2 && stencil_zmarch_supported(ctx)) {
             n = launch_stencil_zmarch(ctx, a, is_complex); /* -2: this case does not fit (shared memory) */

@@ -46,16 +46,7 @@ namespace {
 using namespace tma_ring;
 
 constexpr int R = 6;        /* FD radius */
-#ifndef MIXED_STAGES
-#define MIXED_STAGES 4
-#endif
-#ifndef MIXED_ARRIVE_ALL
-#define MIXED_ARRIVE_ALL 0   /* 1: every merge thread arrives on `full` itself (no bar.sync + single arrive) */
-#endif
-#ifndef MIXED_ROLL
-#define MIXED_ROLL 0   /* 1: rolling loads of the halo columns' y window (fewer live registers) */
-#endif
-constexpr int kStages = MIXED_STAGES;  /* shared memory ring depth */
+constexpr int kStages = 4;  /* shared memory ring depth (5 measured 2 % slower: profiles/r2_exp_mixed_kernel_variants.log) */
 constexpr int HT = 8;       /* top halo rows held in the tile (6 used; 8 keep box starts 128-byte aligned) */
 constexpr int SW = 10;      /* width of the periodic-x strips */
 constexpr int Q = 2 * R + 1; /* depth of the z queue */
@@ -198,17 +189,6 @@ __device__ __forceinline__ void consume_plane(const MixDesc &d, const StepArgs &
                     const int hx = (xp < 3) ? xp : xp + 6;
                     const double *hp = ytile + (r0 + HT) * Cfg::YP + 2 * hx;
                     double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-#if MIXED_ROLL
-                    double2 hu_prev = *reinterpret_cast<const double2 *>(hp), hd_prev = *reinterpret_cast<const double2 *>(hp + Cfg::YP);
-#pragma unroll
-                    for (int k = 1; k <= R; k++) {
-                        const double2 hu_k = *reinterpret_cast<const double2 *>(hp - k * Cfg::YP);
-                        const double2 hd_k = *reinterpret_cast<const double2 *>(hp + (1 + k) * Cfg::YP);
-                        e0 = fma(d.bxy[k], hd_prev.x - hu_k.x, e0); e1 = fma(d.bxy[k], hd_prev.y - hu_k.y, e1);
-                        e2 = fma(d.bxy[k], hd_k.x - hu_prev.x, e2); e3 = fma(d.bxy[k], hd_k.y - hu_prev.y, e3);
-                        hu_prev = hu_k; hd_prev = hd_k;
-                    }
-#else
                     double2 hu[R + 1], hd[R + 1];
 #pragma unroll
                     for (int k = 0; k <= R; k++) {
@@ -220,7 +200,6 @@ __device__ __forceinline__ void consume_plane(const MixDesc &d, const StepArgs &
                         e0 = fma(d.bxy[k], hd[k - 1].x - hu[k].x, e0); e1 = fma(d.bxy[k], hd[k - 1].y - hu[k].y, e1);
                         e2 = fma(d.bxy[k], hd[k].x - hu[k - 1].x, e2); e3 = fma(d.bxy[k], hd[k].y - hu[k - 1].y, e3);
                     }
-#endif
                     *reinterpret_cast<double2 *>(drow + 2 * hx) = make_double2(e0, e1);
                     *reinterpret_cast<double2 *>(drow + Cfg::DP + 2 * hx) = make_double2(e2, e3);
                 }
@@ -308,7 +287,7 @@ stream_mixed_kernel(const __grid_constant__ MixMaps maps, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
-            mbar_init(&full[s], MIXED_ARRIVE_ALL ? 96 : 1);
+            mbar_init(&full[s], 1);
             mbar_init(&landed[s], 1);
             mbar_init(&empty[s], Cfg::CONSUMER_WARPS);
         }
@@ -423,12 +402,8 @@ stream_mixed_kernel(const __grid_constant__ MixMaps maps, const __grid_constant_
                                         *reinterpret_cast<const double2 *>(sr + row * SW + 2 * j);
                             }
                     }
-#if MIXED_ARRIVE_ALL
-                    mbar_arrive(&full[s]);
-#else
                     asm volatile("bar.sync 2, 96;" ::: "memory");
                     if (ft == 0) mbar_arrive(&full[s]);
-#endif
                     itf++;
                 }
             }
