@@ -131,7 +131,7 @@ struct chefsi_ctx {
     void *h_pin[3] = {nullptr, nullptr, nullptr};
     size_t h_pin_bytes = 0;
     int fast_small = 1;
-    int small_brick = 0;                           /* launches with very few z-marching CTAs take the 3-D brick kernel */
+    int small_brick = 1;                           /* launches with very few z-marching CTAs take the 3-D brick kernel */
     void *d_alpha[2] = {nullptr, nullptr}; /* per-image alpha partials: [cur] belongs to the current input */
     int alpha_sum_external = 0;            /* 1: d_alpha_sum was produced by chefsi_nloc_project_device: expand must not rebuild it */
     int alpha_reduce_min = 8;              /* atoms with more alpha partials than this get them summed by alpha_reduce_kernel */

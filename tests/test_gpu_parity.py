@@ -24,6 +24,21 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(scope="module")
+def ctx_zmarch():
+    """Context that keeps launches with few CTAs on the z-march kernel (by default single columns and other tiny
+    launches take the 3-D brick kernel, which also cuts z: CHEFSI_B200_SMALL_BRICK)."""
+    import os
+    from sparc_b200.chefsi import ChefsiContext
+    os.environ["CHEFSI_B200_SMALL_BRICK"] = "0"
+    try:
+        c = ChefsiContext(0)
+    finally:
+        del os.environ["CHEFSI_B200_SMALL_BRICK"]
+    yield c
+    c.close()
+
+
 def _setup(ctx, g, veff, proj, kvec=None):
     ctx.set_grid(g)
     ctx.set_veff(veff)
@@ -71,18 +86,21 @@ def test_real_sparc_filter_calls(ctx, name):
 @pytest.mark.parametrize("cell_typ", [0, 11, 12, 13, 14, 15, 16, 17])
 @pytest.mark.parametrize("BC", [(0, 0, 0), (0, 1, 0), (1, 1, 1)])
 @pytest.mark.parametrize("complex_", [False, True])
-def test_hamiltonian_all_cell_types(ctx, port, cell_typ, BC, complex_):
+def test_hamiltonian_all_cell_types(ctx_zmarch, port, cell_typ, BC, complex_):
+    ctx = ctx_zmarch
     g, veff, proj, x = small_case(cell_typ, BC, complex_=complex_)
     _setup(ctx, g, veff, proj, KVEC)
     Hx = np.empty_like(x)
     ctx.Hamiltonian_vectors_mult(-0.3, x, Hx)
+    assert ctx.stats()["last_path"] == (0 if (cell_typ == 15 and complex_) else 2)
     want = port.hamiltonian_mult(g, proj, veff, -0.3, x, kvec=KVEC)
     assert rel_fro(Hx, want) < TOL
 
 
 @pytest.mark.parametrize("cell_typ", [0, 14, 17])
 @pytest.mark.parametrize("complex_", [False, True])
-def test_chebyshev_filter_small(ctx, port, cell_typ, complex_):
+def test_chebyshev_filter_small(ctx_zmarch, port, cell_typ, complex_):
+    ctx = ctx_zmarch
     g, veff, proj, x = small_case(cell_typ, complex_=complex_, ncol=5)
     _setup(ctx, g, veff, proj, KVEC)
     a, b, a0 = BOUNDS
@@ -129,13 +147,14 @@ def test_no_projectors_no_veff_lanczos_style_call(ctx, port):
     assert rel_fro(Hx, port.hamiltonian_mult(g, None, veff, 0.0, x)) < TOL
 
 
-@pytest.mark.parametrize("cell_typ,N,BC,path", [(0, (14, 13, 15), (0, 0, 0), 2), (17, (14, 13, 15), (0, 1, 0), 2),
+@pytest.mark.parametrize("cell_typ,N,BC,path", [(0, (14, 13, 15), (0, 0, 0), 0), (17, (14, 13, 15), (0, 1, 0), 0),
                                                 (0, (32, 32, 16), (0, 0, 0), 1), (0, (40, 39, 12), (1, 1, 1), 1),
                                                 (17, (32, 32, 14), (0, 0, 0), 3), (14, (64, 40, 13), (0, 0, 1), 3)])
 def test_lap_vec_mult(ctx, port, cell_typ, N, BC, path):
     """Lap_vec_mult (lapVecRoutines.c:37-58): (Lap + c) x without potential and projectors -- the operator of the
-    Poisson residual / Kerker preconditioner -- on every stencil kernel, single column and a small block,
-    with a potential and projectors set on the context (they must not be applied)."""
+    Poisson residual / Kerker preconditioner -- on the kernels the default dispatch picks (tiny launches: the 3-D
+    brick kernel; streaming grids: K1 / K2m), single column and a small block, with a potential and projectors set on
+    the context (they must not be applied)."""
     g = P.make_grid(N, tuple(0.45 * n for n in N), BC=BC, latvec=P.LATVEC_BY_CELL_TYP[cell_typ])
     veff = P.synthetic_veff(g)
     proj = P.make_projectors(g, np.array([[0.3, 0.5, 0.6]]), rc=[2.0], nproj=[5])
@@ -173,7 +192,7 @@ def test_overlapping_spheres(ctx, port, name, complex_):
     ctx.Hamiltonian_vectors_mult(-0.3, x, Hx)
     st = ctx.stats()
     assert st["last_nloc_atomic"] == 1
-    assert st["last_path"] == (1 if name.startswith("stream") else 2)
+    assert st["last_path"] == (1 if name.startswith("stream") else 0)   # 5 columns on a 14 x 13 x 15 grid: a tiny launch -> brick kernel
     if name in ("general_small", "general_typ17", "stream"):
         assert st["last_alpha_reduced"] == 1   # 9 alpha partials on one atom
     assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, -0.3, x, kvec=kvec)) < TOL
@@ -350,10 +369,12 @@ def test_stream_zmarch_and_brick_kernels_agree(ctx):
     assert ctx.stats()["last_path"] == 1
     for level, path, tol in ((1, 2, 1e-12), (2, 0, 1e-12)):
         os.environ["CHEFSI_B200_FORCE_GENERAL"] = str(level)
+        os.environ["CHEFSI_B200_SMALL_BRICK"] = "0"
         try:
             c2 = ChefsiContext(0)
         finally:
             del os.environ["CHEFSI_B200_FORCE_GENERAL"]
+            del os.environ["CHEFSI_B200_SMALL_BRICK"]
         _setup(c2, g, veff, None)
         X2, Y2 = x.copy(), np.empty_like(x)
         c2.ChebyshevFiltering(X2, Y2, 10, a, b, a0)
@@ -391,9 +412,10 @@ def test_brick_kernel_all_cell_types(ctx_brick, port, cell_typ, complex_):
 @pytest.mark.parametrize("cell_typ", [0, 12, 15, 17])
 @pytest.mark.parametrize("complex_", [False, True])
 @pytest.mark.parametrize("N", [(45, 21, 19), (70, 35, 14)])
-def test_zmarch_kernel_multi_tile(ctx, port, cell_typ, complex_, N):
+def test_zmarch_kernel_multi_tile(ctx_zmarch, port, cell_typ, complex_, N):
     """z-march kernel on grids with several (ragged) tiles per plane, all three kinds of mixed-derivative
     components (x-, y- and z-extended), real and complex."""
+    ctx = ctx_zmarch
     g, veff, proj, x = small_case(cell_typ, (0, 0, 0), N=N, L=tuple(0.5 * n for n in N), complex_=complex_)
     _setup(ctx, g, veff, proj, KVEC)
     Hx = np.empty_like(x)
