@@ -188,3 +188,19 @@ class Reference:
         fn(self.h, _ptr(X), C.c_int(ld), _ptr(Y), C.c_int(ld), C.c_int(ncol), C.c_int(m), C.c_double(a),
            C.c_double(b), C.c_double(a0))
         return X, Y
+
+    def lanczos(self, x0, tol_min, tol_max, maxit=1000):
+        """The reference's own Lanczos (src/eigenSolver.c:1920) on this problem: (eigmin, eigmax)."""
+        x0 = np.array(x0, dtype=np.float64, copy=True, order="C").reshape(-1)
+        lo, hi = C.c_double(0), C.c_double(0)
+        self.lib.ref_lanczos(self.h, _ptr(x0), C.c_double(tol_min), C.c_double(tol_max), C.c_int(maxit),
+                             C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    def aar(self, c, x, b, omega=0.6, beta=0.6, m=7, p=6, tol=1e-8, max_iter=1000):
+        """The reference's own AAR (src/linearSolver.c:38) with poisson_residual + Jacobi_preconditioner: returns x."""
+        x = np.array(x, dtype=np.float64, copy=True, order="C").reshape(-1)
+        b = np.array(b, dtype=np.float64, copy=True, order="C").reshape(-1)
+        self.lib.ref_aar(self.h, C.c_double(c), _ptr(x), _ptr(b), C.c_double(omega), C.c_double(beta), C.c_int(m),
+                         C.c_int(p), C.c_double(tol), C.c_int(max_iter))
+        return x

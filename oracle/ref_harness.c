@@ -30,6 +30,7 @@
 #include "lapVecRoutines.h"
 #include "lapVecRoutinesKpt.h"
 #include "nlocVecRoutines.h"
+#include "linearSolver.h"
 
 #include "chefsi_oracle.h"
 
@@ -88,6 +89,8 @@ void *ref_problem_create(const chefsi_grid_t *g, const chefsi_nloc_t *nl, const 
     S->spin_start_indx = 0;
     S->bandcomm_index = 0;
     S->kptcomm_topo = MPI_COMM_NULL;       /* != the communicator passed below */
+    S->kptcomm_inter = MPI_COMM_NULL;      /* Lanczos: no ranks outside the Cartesian topology (eigenSolver.c:2105) */
+    S->comm_dist_graph_phi = MPI_COMM_SELF;
     S->comm_dist_graph_psi = MPI_COMM_SELF;
     S->kptcomm_topo_dist_graph = MPI_COMM_SELF;
 
@@ -95,6 +98,7 @@ void *ref_problem_create(const chefsi_grid_t *g, const chefsi_nloc_t *nl, const 
     P->DMVertices[0] = 0; P->DMVertices[1] = g->Nx - 1;
     P->DMVertices[2] = 0; P->DMVertices[3] = g->Ny - 1;
     P->DMVertices[4] = 0; P->DMVertices[5] = g->Nz - 1;
+    for (int i = 0; i < 6; i++) S->DMVertices[i] = P->DMVertices[i]; /* phi domain = the whole grid (poisson_residual) */
     P->veff = (double *)calloc(S->Nd, sizeof(double));
     if (veff) memcpy(P->veff, veff, sizeof(double) * S->Nd);
     S->Veff_loc_dmcomm = P->veff;
@@ -253,4 +257,24 @@ double ref_chebyshev_filter_kpt(void *h, double _Complex *X, int ldi, double _Co
     ChebyshevFiltering_kpt(&P->S, P->DMVertices, X, ldi, Y, ldo, ncol, m, a, b, a0, 0, 0,
                            MPI_COMM_SELF, &t);
     return t;
+}
+
+/* ---- the rows around the filter: the reference's own Lanczos and AAR on the same flat problem ---- */
+void Jacobi_preconditioner(SPARC_OBJ *pSPARC, int N, double c, double *r, double *f, MPI_Comm comm); /* electrostatics.c:1682 */
+
+/* Lanczos (src/eigenSolver.c:1920-2129) from the start vector x0 */
+void ref_lanczos(void *h, double *x0, double tol_min, double tol_max, int maxit, double *eigmin, double *eigmax)
+{
+    ref_problem_t *P = (ref_problem_t *)h;
+    MPI_Request req = MPI_REQUEST_NULL;
+    Lanczos(&P->S, P->DMVertices, P->veff, P->S.Atom_Influence_nloc, P->S.nlocProj, eigmin, eigmax, x0, tol_min, tol_max, maxit,
+            0, 0, MPI_COMM_SELF, &req);
+}
+
+/* AAR (src/linearSolver.c:38-146) with the operator pair SPARC uses: poisson_residual (lapVecRoutines.c:61) and
+ * Jacobi_preconditioner; x is the start vector on entry and the solution on return */
+void ref_aar(void *h, double c, double *x, double *b, double omega, double beta, int m, int p, double tol, int max_iter)
+{
+    ref_problem_t *P = (ref_problem_t *)h;
+    AAR(&P->S, poisson_residual, Jacobi_preconditioner, c, P->Nd, x, b, omega, beta, m, p, tol, max_iter, MPI_COMM_SELF);
 }

@@ -1,0 +1,41 @@
+"""Pins the numpy restatements of the rows around the filter (oracle/next_rows.py: Lanczos, AAR) to the reference's
+OWN compiled routines (oracle/_ref: ref_lanczos -> Lanczos eigenSolver.c:1920, ref_aar -> AAR linearSolver.c:38 with
+poisson_residual + Jacobi_preconditioner) on the same inputs.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import next_rows
+from tests.cases import small_case
+
+
+@pytest.fixture(scope="module")
+def ref_cls(have_reference):
+    if not have_reference:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from oracle.bindings import Reference
+    return Reference
+
+
+@pytest.mark.parametrize("cell_typ,BC", [(0, (0, 0, 0)), (17, (0, 0, 0)), (0, (1, 1, 1))])
+def test_lanczos_restatement_vs_reference(port, ref_cls, cell_typ, BC):
+    g, veff, proj, x = small_case(cell_typ, BC, ncol=1)
+    ref = ref_cls(g, proj, veff)
+    tol = 1e-2
+    lo_r, hi_r = ref.lanczos(x[0], tol, tol, 300)
+    lo, hi, it = next_rows.lanczos(port, g, proj, veff, x[0], tol, tol, 300)
+    assert it < 300
+    assert abs(lo - lo_r) < 1e-9 * max(1.0, abs(hi_r)) and abs(hi - hi_r) < 1e-9 * max(1.0, abs(hi_r))
+
+
+@pytest.mark.parametrize("cell_typ,BC,c", [(0, (1, 1, 1), 0.0), (17, (0, 0, 0), -0.35), (0, (0, 1, 0), -0.2)])
+def test_aar_restatement_vs_reference(port, ref_cls, cell_typ, BC, c):
+    g, veff, proj, _ = small_case(cell_typ, BC, ncol=1)
+    ref = ref_cls(g, proj, veff)
+    b = np.random.default_rng(3).standard_normal(g.Nd)
+    x0 = np.zeros(g.Nd)
+    x_r = ref.aar(c, x0, b, tol=1e-8, max_iter=600)
+    x, it, rn = next_rows.aar(port, g, c, x0, b, tol=1e-8, max_iter=600)
+    assert it < 600
+    assert np.linalg.norm(x - x_r) <= 1e-6 * np.linalg.norm(x_r)
+    r = b + port.lap_plus_diag(g, 1.0, 0.0, c, None, x_r[None, :].copy())[0]
+    assert np.linalg.norm(r) <= 1.0001e-8 * np.linalg.norm(b)     # the reference's solution meets its own tolerance

@@ -5,6 +5,7 @@ for the same three GEMMs; only the summation order differs)."""
 import numpy as np
 import pytest
 
+from oracle import next_rows  # checker only
 from sparc_b200 import problem as P
 from tests.cases import overlap_case, rel_fro, small_case
 
@@ -31,10 +32,9 @@ def _check(ctx, port, g, veff, proj, y, kvec=(0, 0, 0)):
     ncol = y.shape[0]
     Hp, Mp = np.zeros((ncol, ncol + 3), dtype=y.dtype), np.zeros((ncol, ncol + 3), dtype=y.dtype)   # ld > ncol
     ctx.DP_Project_Hamiltonian(y, Hp, Mp)
-    hy = port.hamiltonian_mult(g, proj, veff, 0.0, y, kvec=kvec)
-    # element (m, n) = conj(y_m) . (H y_n), stored column-major: numpy Hp[n, m]
-    assert rel_fro(Mp[:, :ncol], y @ y.conj().T) < TOL
-    assert rel_fro(Hp[:, :ncol], hy @ y.conj().T) < TOL
+    Hp_w, Mp_w = next_rows.project(port, g, proj, veff, y, kvec=kvec)   # element (m, n) = conj(y_m) . (H y_n) at numpy [n, m]
+    assert rel_fro(Mp[:, :ncol], Mp_w) < TOL
+    assert rel_fro(Hp[:, :ncol], Hp_w) < TOL
     assert (Hp[:, ncol:] == 0).all() and (Mp[:, ncol:] == 0).all()
     rng = np.random.default_rng(5)
     Q = rng.standard_normal((ncol, ncol))                              # Q[n, m] = element (m, n) of the column-major matrix
@@ -43,7 +43,7 @@ def _check(ctx, port, g, veff, proj, y, kvec=(0, 0, 0)):
     Q = np.ascontiguousarray(Q)
     X = np.full((ncol, g.Nd + 5), 3.0, dtype=y.dtype)
     ctx.DP_Subspace_Rotation(Q, X)
-    assert rel_fro(X[:, :g.Nd], Q @ y) < TOL
+    assert rel_fro(X[:, :g.Nd], next_rows.rotate(y, Q)) < TOL
     assert (X[:, g.Nd:] == 3.0).all()
 
 
@@ -109,76 +109,22 @@ def test_filter_keeps_y_resident(ctx, port, complex_):
 
 @pytest.mark.parametrize("cell_typ,BC", [(0, (0, 0, 0)), (17, (0, 0, 0)), (0, (1, 1, 1))])
 def test_lanczos_extreme_eigenvalues(ctx, port, cell_typ, BC):
-    """chefsi_lanczos (Lanczos, eigenSolver.c:1920-2129) against the same iteration done on the host with the oracle's
-    H apply and numpy's symmetric tridiagonal eigenvalues (the reference calls LAPACKE_dsterf): same stopping step,
-    eigenvalues equal to rounding."""
+    """chefsi_lanczos (Lanczos, eigenSolver.c:1920-2129) against the oracle's restatement (oracle/next_rows.py, pinned to
+    the reference's own Lanczos by tests/test_next_rows_oracle.py): same stopping step, eigenvalues equal to rounding."""
     g, veff, proj, x = small_case(cell_typ, BC, ncol=1)
     _setup(ctx, g, veff, proj)
     tol = 1e-2
     lo, hi, it = ctx.Lanczos(x[0], tol, tol, maxit=300)
-    H = lambda v: port.hamiltonian_mult(g, proj, veff, 0.0, v[None, :].copy())[0]
-    vjm1 = x[0] / np.linalg.norm(x[0])
-    vj = H(vjm1)
-    a = [vjm1 @ vj]
-    vj = vj - a[0] * vjm1
-    b = [np.linalg.norm(vj)]
-    vj = vj / b[0]
-    emin_pre = emax_pre = 0.0
-    j = 0
-    while True:
-        vjp1 = H(vj)
-        a.append(vj @ vjp1)
-        vjp1 = vjp1 - (a[j + 1] * vj + b[j] * vjm1)
-        vjm1 = vj
-        b.append(np.linalg.norm(vjp1))
-        vj = vjp1 / b[j + 1]
-        T = np.diag(a[:j + 2]) + np.diag(b[:j + 1], 1) + np.diag(b[:j + 1], -1)
-        ev = np.linalg.eigvalsh(T)
-        emin, emax = ev[0], ev[-1]
-        done = abs(emin - emin_pre) <= tol and abs(emax - emax_pre) <= tol
-        emin_pre, emax_pre = emin, emax
-        j += 1
-        if done or j >= 300:
-            break
+    emin, emax, j = next_rows.lanczos(port, g, proj, veff, x[0], tol, tol, 300)
     assert it == j
     assert abs(lo - emin) < 1e-9 * max(1.0, abs(emax)) and abs(hi - emax) < 1e-9 * max(1.0, abs(emax))
 
 
-def _aar_host(port, g, c, x, b, omega, beta, m, p, tol, max_iter):
-    """AAR (linearSolver.c:38-146) with poisson_residual + Jacobi_preconditioner replayed on the host: the oracle's
-    Laplacian, numpy's lstsq (minimum-norm, like LAPACKE_dgelsd) for the Anderson coefficients."""
-    lap = lambda v: port.lap_plus_diag(g, 1.0, 0.0, c, None, v[None, :].copy())[0]
-    N = x.size
-    m_inv = g.coefs["D2_x"][0] + g.coefs["D2_y"][0] + g.coefs["D2_z"][0] + c
-    m_inv = -1.0 / (1.0 if abs(m_inv) < 1e-14 else m_inv)
-    x = x.copy()
-    x_old, f_old = x.copy(), np.zeros(N)
-    X, F = np.zeros((m, N)), np.zeros((m, N))
-    r = b + lap(x)
-    tol = tol * np.linalg.norm(b)
-    r_2norm, it = tol + 1.0, 0
-    while r_2norm > tol and it < max_iter:
-        f = m_inv * r
-        if it > 0:
-            h = (it - 1) % m
-            X[h], F[h] = x - x_old, f - f_old
-        x_old, f_old = x.copy(), f.copy()
-        if (it + 1) % p == 0 and it > 0:
-            G = np.linalg.lstsq(F @ F.T, F @ f, rcond=None)[0]
-            x = x_old - G @ X + beta * (f - G @ F)
-            r = b + lap(x)
-            r_2norm = np.linalg.norm(r)
-        else:
-            x = x_old + omega * f
-            r = b + lap(x)
-        it += 1
-    return x, it, r_2norm
-
-
 @pytest.mark.parametrize("cell_typ,BC,c", [(0, (1, 1, 1), 0.0), (17, (0, 0, 0), -0.35), (0, (0, 1, 0), -0.2)])
 def test_aar_poisson_solve(ctx, port, cell_typ, BC, c):
-    """chefsi_poisson_aar against a host replay of the reference's AAR (same operator pair, parameters and stopping
-    rule): same iteration count, solution equal to solver tolerance, and the residual of the returned x really is small."""
+    """chefsi_poisson_aar against the oracle's restatement of the reference's AAR (oracle/next_rows.py, pinned to the
+    reference's own AAR by tests/test_next_rows_oracle.py; same operator pair, parameters and stopping rule): same
+    iteration count up to one stopping test, solution equal to solver tolerance, residual of the returned x small."""
     g, veff, proj, _ = small_case(cell_typ, BC, ncol=1)
     _setup(ctx, g, veff, proj)
     rng = np.random.default_rng(3)
@@ -188,7 +134,7 @@ def test_aar_poisson_solve(ctx, port, cell_typ, BC, c):
     x0 = np.zeros(g.Nd)
     x = x0.copy()
     it, rn = ctx.AAR(c, x, b, tol=1e-8, max_iter=600)
-    xh, ith, rnh = _aar_host(port, g, c, x0, b, 0.6, 0.6, 7, 6, 1e-8, 600)
+    xh, ith, rnh = next_rows.aar(port, g, c, x0, b, 0.6, 0.6, 7, 6, 1e-8, 600)
     assert abs(it - ith) <= 6 and it < 600   # the norm is tested every p = 6 steps; rounding may move the stop by one test
     assert np.linalg.norm(x - xh) <= 1e-5 * np.linalg.norm(xh)
     r = b + port.lap_plus_diag(g, 1.0, 0.0, c, None, x[None, :].copy())[0]
