@@ -106,7 +106,9 @@ int chefsi_create(chefsi_ctx_t **ctx, int device);
  * NB = ceil(ncol / ndev) per device and run the devices concurrently; chefsi_set_veff / chefsi_set_projectors upload to
  * the first device and replicate with ncclBroadcast over NVLink (Transfer_Veff_loc's MPI_Bcast,
  * src/electronicGroundState.c:1313-1385); NCCL is loaded at run time, cudaMemcpyPeer is used when it is absent.
- * The device-resident entry points take single-device contexts only. */
+ * chefsi_subspace_project / _rotate on such a context split Hp / Mp / Y Q by column blocks and read the other devices'
+ * blocks through NVLink peer memory inside the GEMM kernels; chefsi_lanczos / chefsi_poisson_aar (single vectors) run on
+ * the first device.  The device-resident entry points take single-device contexts only. */
 int chefsi_create_multi(chefsi_ctx_t **ctx, const int *devices, int ndev);
 /* devices of the context (1 for a single-device context), whether the replication runs over NCCL, and the
  * number / bytes of broadcasts so far */
@@ -172,8 +174,7 @@ int chefsi_lanczos(chefsi_ctx_t *ctx, const double *x0, double tol_min, double t
  * device: AAR (src/linearSolver.c:38-146) with res_fun = poisson_residual (src/lapVecRoutines.c:61) and
  * precond_fun = Jacobi_preconditioner (src/electrostatics.c:1682) -- the Poisson solve of every SCF iteration
  * (electrostatics.c:1658) and the Kerker preconditioner (mixing.c:501).  x: start vector in, solution out (host, Nd);
- * b: right-hand side (host); omega, beta, m (<= 16), p, tol (relative to ||b||), max_iter as in the reference.
- * Real data, single-device context. */
+ * b: right-hand side (host); omega, beta, m (<= 16), p, tol (relative to ||b||), max_iter as in the reference.  Real data. */
 int chefsi_poisson_aar(chefsi_ctx_t *ctx, double c, double *x, const double *b, double omega, double beta, int m, int p,
                        double tol, int max_iter, int *iterations, double *res_norm);
 

@@ -15,6 +15,7 @@
  * The Laplacian is the filter's stencil kernel (its `- s2 * xprev` operand carries b: s2 = -1).
  */
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "chefsi_internal.h"
@@ -159,7 +160,12 @@ extern "C" int chefsi_poisson_aar(chefsi_ctx_t *ctx, double c, double *x, const 
                                   double tol, int max_iter, int *iterations, double *res_norm)
 {
     if (!ctx || !x || !b) return 1;
-    if (ctx->multi) return chefsi_fail(ctx, "chefsi_poisson_aar takes a single-device context");
+    if (ctx->multi) { /* a single right-hand side does not split over devices: the first one solves it */
+        chefsi_ctx *k = multi_first(ctx);
+        const int rc = chefsi_poisson_aar(k, c, x, b, omega, beta, m, p, tol, max_iter, iterations, res_norm);
+        if (rc) { strncpy(ctx->err, k->err, sizeof(ctx->err) - 1); ctx->err[sizeof(ctx->err) - 1] = 0; }
+        return rc;
+    }
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (m < 1 || m > kMaxM || p < 1) return chefsi_fail(ctx, "aar: history length must be 1..%d, p >= 1", kMaxM);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -873,7 +873,7 @@ extern "C" int chefsi_hamiltonian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double c
 /* ---- Rayleigh-Ritz projection / subspace rotation on the resident block (kernels: subspace.cu) ------------------- */
 static int subspace_reserve(chefsi_ctx *ctx, int ncol, bool is_complex)
 {
-    if (ctx->multi) return chefsi_fail(ctx, "subspace routines take a single-device context");
+    if (ctx->multi) return multi_subspace_reserve(ctx, ncol, is_complex);
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (ncol <= 0) return chefsi_fail(ctx, "subspace_reserve: ncol must be positive");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -918,6 +918,7 @@ extern "C" int chefsi_subspace_reserve_kpt(chefsi_ctx_t *ctx, int ncol) { return
 /* Hp = Y^H (H Y), Mp = Y^H Y.  Complex columns are handled as real columns of twice the length (subspace.cu). */
 static int subspace_project(chefsi_ctx *ctx, const void *Y, size_t ldy, int ncol, void *Hp, void *Mp, size_t ldp, bool is_complex)
 {
+    if (ctx->multi) return multi_subspace_project(ctx, Y, ldy, ncol, Hp, Mp, ldp, is_complex);
     if (ncol <= 0 || ldp < (size_t)ncol || ldy < ctx->Nd) return chefsi_fail(ctx, "subspace_project: bad dimensions");
     if (subspace_reserve(ctx, ncol, is_complex)) return 1;
     const int words = is_complex ? 2 : 1;
@@ -978,7 +979,7 @@ extern "C" int chefsi_subspace_project_kpt(chefsi_ctx_t *ctx, const void *Y, siz
 
 static int subspace_rotate(chefsi_ctx *ctx, const void *Q, size_t ldq, int ncol, void *X, size_t ldx, bool is_complex)
 {
-    if (ctx->multi) return chefsi_fail(ctx, "subspace routines take a single-device context");
+    if (ctx->multi) return multi_subspace_rotate(ctx, Q, ldq, ncol, X, ldx, is_complex);
     if (ctx->res_ncol != ncol || !ctx->d_res_Y || ctx->res_complex != (int)is_complex)
         return chefsi_fail(ctx, "subspace_rotate: no resident block of %d columns (call chefsi_subspace_project first)", ncol);
     if (ldq < (size_t)ncol || ldx < ctx->Nd) return chefsi_fail(ctx, "subspace_rotate: bad dimensions");

@@ -181,6 +181,7 @@ int launch_alpha_reduce(chefsi_ctx *ctx, int ncol, bool is_complex);
 int nloc_ensure_alpha(chefsi_ctx *ctx, int ncol, bool is_complex); /* (re)allocate the alpha buffers for ncol columns */
 
 /* multi.cu: the leader context's side of every entry point it supports */
+chefsi_ctx *multi_first(chefsi_ctx *lead);
 int multi_size(const chefsi_ctx *lead);
 int multi_uses_nccl(const chefsi_ctx *lead);
 void multi_destroy(chefsi_ctx *lead);
@@ -194,6 +195,9 @@ int multi_hmult_host(chefsi_ctx *lead, int ncol, double c, const void *x, size_t
 int multi_lapmult_host(chefsi_ctx *lead, int ncol, double a, double c, const void *x, size_t ldi, void *y, size_t ldo, bool is_complex);
 int multi_synchronize(chefsi_ctx *lead);
 void multi_set_profiling(chefsi_ctx *lead, int on);
+int multi_subspace_reserve(chefsi_ctx *lead, int ncol, bool is_complex);
+int multi_subspace_project(chefsi_ctx *lead, const void *Y, size_t ldy, int ncol, void *Hp, void *Mp, size_t ldp, bool is_complex);
+int multi_subspace_rotate(chefsi_ctx *lead, const void *Q, size_t ldq, int ncol, void *X, size_t ldx, bool is_complex);
 void multi_bcast_stats(const chefsi_ctx *lead, unsigned long long *calls, unsigned long long *bytes);
 void chefsi_free_nloc(NlocDev &d);
 

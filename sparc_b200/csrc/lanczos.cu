@@ -11,6 +11,7 @@
  * kernel, and one 16-byte copy of (a, b) for the host-side convergence test.
  */
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "chefsi_internal.h"
@@ -133,7 +134,12 @@ extern "C" int chefsi_lanczos(chefsi_ctx_t *ctx, const double *x0, double tol_mi
                               double *eigmax, int *iterations)
 {
     if (!ctx || !x0 || !eigmin || !eigmax) return 1;
-    if (ctx->multi) return chefsi_fail(ctx, "chefsi_lanczos takes a single-device context");
+    if (ctx->multi) { /* a single vector does not split over devices: the first one iterates */
+        chefsi_ctx *k = multi_first(ctx);
+        const int rc = chefsi_lanczos(k, x0, tol_min, tol_max, maxit, eigmin, eigmax, iterations);
+        if (rc) { strncpy(ctx->err, k->err, sizeof(ctx->err) - 1); ctx->err[sizeof(ctx->err) - 1] = 0; }
+        return rc;
+    }
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (maxit < 1) return chefsi_fail(ctx, "lanczos: maxit must be positive");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));

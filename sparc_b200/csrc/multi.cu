@@ -37,6 +37,10 @@ typedef const char *(*PFN_ncclGetErrorString)(ncclResult_t);
 
 struct MultiState {
     std::vector<chefsi_ctx *> kids;
+    /* subspace steps: per device the column block of Hp / Mp / Q it owns (ncol x nc_r, column-major, ld = ncol) */
+    std::vector<void *> d_hp, d_mp, d_q, d_qr, d_qi;
+    size_t blk_bytes = 0;
+    int sub_ncol = 0, sub_complex = 0;      /* the blocks currently resident on the kids */
     void *nccl_lib = nullptr;
     std::vector<ncclComm_t> comms;
     PFN_ncclCommDestroy commDestroy = nullptr;
@@ -151,6 +155,9 @@ extern "C" int chefsi_create_multi(chefsi_ctx_t **out, const int *devices, int n
     return 0;
 }
 
+/* single-column solvers (Lanczos, AAR) do not split: they run on the first device, which holds every replicated table */
+chefsi_ctx *multi_first(chefsi_ctx *lead) { return lead->multi ? lead->multi->kids[0] : lead; }
+
 int multi_size(const chefsi_ctx *lead) { return lead->multi ? (int)lead->multi->kids.size() : 1; }
 int multi_uses_nccl(const chefsi_ctx *lead) { return lead->multi && lead->multi->use_nccl; }
 
@@ -159,6 +166,10 @@ void multi_destroy(chefsi_ctx *lead)
     MultiState *ms = lead->multi;
     for (size_t i = 0; i < ms->comms.size(); i++)
         if (ms->comms[i]) ms->commDestroy(ms->comms[i]);
+    for (size_t r = 0; r < ms->kids.size(); r++) {
+        cudaSetDevice(ms->kids[r]->device);
+        if (r < ms->d_hp.size()) { cudaFree(ms->d_hp[r]); cudaFree(ms->d_mp[r]); cudaFree(ms->d_q[r]); cudaFree(ms->d_qr[r]); cudaFree(ms->d_qi[r]); }
+    }
     for (chefsi_ctx *k : ms->kids) chefsi_destroy(k);
     if (ms->nccl_lib) dlclose(ms->nccl_lib);
     delete ms;
@@ -336,4 +347,207 @@ void multi_bcast_stats(const chefsi_ctx *lead, unsigned long long *calls, unsign
 {
     *calls = lead->multi ? lead->multi->bcast_calls : 0;
     *bytes = lead->multi ? lead->multi->bcast_bytes : 0;
+}
+
+/* ---- Rayleigh-Ritz steps over several devices (SURVEY.md 8e "exchange step after", 8f-1) --------------------------------
+ * The filtered block is split by columns: device r holds Y_r (and H Y_r).  Mp = Y^H Y and Hp = Y^H H Y need every pair of
+ * column blocks, X = Y Q every block for every output block.  The reference re-distributes the block with MPI_Alltoallv
+ * (BP2DP, src/parallelization.c:2535) before its dgemm; here nothing is re-distributed: device I computes the column
+ * block I of Hp / Mp and of X, and its GEMM kernels READ the other devices' Y_J straight through NVLink peer memory
+ * (the A operand of gemm_tn / gemm_nn is a peer pointer; cp.async pulls the tiles while the DMMAs of the previous chunk
+ * run), i.e. the all-gather is fused into the product.  Only the Ns x Ns matrices and the rotated block cross PCIe. */
+static void kid_range(int ncol, int n, int r, int *c0, int *nc)
+{
+    const int nb = (ncol + n - 1) / n;
+    const int a = r * nb < ncol ? r * nb : ncol, b = (r + 1) * nb < ncol ? (r + 1) * nb : ncol;
+    *c0 = a;
+    *nc = b - a;
+}
+
+template <class F>
+static int multi_parallel(chefsi_ctx *lead, F fn)
+{
+    MultiState *ms = lead->multi;
+    const int n = (int)ms->kids.size();
+    std::vector<int> rcs(n, 0);
+    std::vector<std::thread> th;
+    for (int r = 1; r < n; r++) th.emplace_back([&, r] { rcs[r] = fn(r); });
+    rcs[0] = fn(0);
+    for (std::thread &t : th) t.join();
+    for (int r = 0; r < n; r++)
+        if (rcs[r]) return multi_fail_from(lead, ms->kids[r], rcs[r]);
+    return 0;
+}
+
+int multi_subspace_reserve(chefsi_ctx *lead, int ncol, bool is_complex)
+{
+    MultiState *ms = lead->multi;
+    const int n = (int)ms->kids.size();
+    const int nb = (ncol + n - 1) / n;
+    const size_t need = (size_t)ncol * nb * sizeof(double) * (is_complex ? 2 : 1);
+    for (int r = 0; r < n; r++) {
+        int c0, nc;
+        kid_range(ncol, n, r, &c0, &nc);
+        if (nc <= 0) continue;
+        const int rc = is_complex ? chefsi_subspace_reserve_kpt(ms->kids[r], nc) : chefsi_subspace_reserve(ms->kids[r], nc);
+        if (rc) return multi_fail_from(lead, ms->kids[r], rc);
+    }
+    if (need > ms->blk_bytes) {
+        ms->d_hp.resize(n, nullptr); ms->d_mp.resize(n, nullptr); ms->d_q.resize(n, nullptr); ms->d_qr.resize(n, nullptr); ms->d_qi.resize(n, nullptr);
+        for (int r = 0; r < n; r++) {
+            CHEFSI_CUDA(lead, cudaSetDevice(ms->kids[r]->device));
+            cudaFree(ms->d_hp[r]); cudaFree(ms->d_mp[r]); cudaFree(ms->d_q[r]); cudaFree(ms->d_qr[r]); cudaFree(ms->d_qi[r]);
+            ms->d_hp[r] = ms->d_mp[r] = ms->d_q[r] = ms->d_qr[r] = ms->d_qi[r] = nullptr;
+            CHEFSI_CUDA(lead, cudaMalloc(&ms->d_hp[r], need));
+            CHEFSI_CUDA(lead, cudaMalloc(&ms->d_mp[r], need));
+            CHEFSI_CUDA(lead, cudaMalloc(&ms->d_q[r], need));
+            CHEFSI_CUDA(lead, cudaMalloc(&ms->d_qr[r], need));
+            CHEFSI_CUDA(lead, cudaMalloc(&ms->d_qi[r], need));
+        }
+        ms->blk_bytes = need;
+    }
+    return 0;
+}
+
+int multi_subspace_project(chefsi_ctx *lead, const void *Y, size_t ldy, int ncol, void *Hp, void *Mp, size_t ldp, bool is_complex)
+{
+    MultiState *ms = lead->multi;
+    const int n = (int)ms->kids.size();
+    if (ncol <= 0 || ldp < (size_t)ncol || ldy < lead->Nd) return chefsi_fail(lead, "subspace_project: bad dimensions");
+    if (multi_subspace_reserve(lead, ncol, is_complex)) return 1;
+    const int words = is_complex ? 2 : 1;
+    const size_t esz = sizeof(double) * words, row = lead->Nd * esz;
+    /* phase 1 (per device): make Y_r resident if the filter did not leave it there, W_r = H Y_r, T_r = -i W_r .. done later */
+    int rc = multi_parallel(lead, [&](int r) {
+        chefsi_ctx *k = ms->kids[r];
+        int c0, nc;
+        kid_range(ncol, n, r, &c0, &nc);
+        if (nc <= 0) return 0;
+        const char *yslice = (const char *)Y + (size_t)c0 * ldy * esz;
+        if (cudaSetDevice(k->device) != cudaSuccess) return chefsi_fail(k, "cudaSetDevice failed");
+        if (!(k->res_ncol == nc && k->res_host == (const void *)yslice && k->res_complex == (int)is_complex)) {
+            if (k->res_unwritten_host == (const void *)yslice)
+                return chefsi_fail(k, "subspace_project: the host copy of this Y block was never written (NO_Y_COPYBACK) and the device copy is gone");
+            if (cudaMemcpy2DAsync(k->d_res_Y, k->ld * esz, yslice, ldy * esz, row, nc, cudaMemcpyHostToDevice, k->stream) != cudaSuccess)
+                return chefsi_fail(k, "subspace_project: upload of the Y block failed");
+            k->res_ncol = nc; k->res_host = yslice; k->res_complex = is_complex;
+        }
+        const int rc1 = is_complex ? chefsi_hamiltonian_mult_kpt_device(k, nc, 0.0, k->d_res_Y, k->d_res_W)
+                                   : chefsi_hamiltonian_mult_device(k, nc, 0.0, (const double *)k->d_res_Y, (double *)k->d_res_W);
+        if (rc1) return rc1;
+        return cudaStreamSynchronize(k->stream) == cudaSuccess ? 0 : chefsi_fail(k, "subspace_project: H Y failed");
+    });
+    if (rc) return rc;
+    /* phase 2 (per device I): column block I of Mp and Hp; the A operand Y_J is read through peer memory */
+    rc = multi_parallel(lead, [&](int I) {
+        chefsi_ctx *k = ms->kids[I];
+        int c0I, ncI;
+        kid_range(ncol, n, I, &c0I, &ncI);
+        if (ncI <= 0) return 0;
+        if (cudaSetDevice(k->device) != cudaSuccess) return chefsi_fail(k, "cudaSetDevice failed");
+        const size_t K = lead->Nd * words, ldv = k->ld * words;
+        double *dMp = (double *)ms->d_mp[I], *dHp = (double *)ms->d_hp[I];
+        const double *Yi = (const double *)k->d_res_Y, *Wi = (const double *)k->d_res_W;
+        for (int pass = 0; pass < (is_complex ? 2 : 1); pass++) {
+            const double *By = Yi, *Bw = Wi;
+            if (pass == 1) { /* imaginary parts: B -> -i B, formed locally */
+                if (launch_rot90(k, k->d_res_Y, k->d_res_T, lead->Nd, k->ld, ncI, -1.0) < 0) return 1;
+                By = (const double *)k->d_res_T;
+            }
+            for (int which = 0; which < 2; which++) { /* 0: Mp (B = Y_I), 1: Hp (B = H Y_I) */
+                if (pass == 1 && which == 1) {
+                    if (launch_rot90(k, k->d_res_W, k->d_res_T, lead->Nd, k->ld, ncI, -1.0) < 0) return 1;
+                    Bw = (const double *)k->d_res_T;
+                }
+                const double *B = which ? Bw : By;
+                double *Cblk = (which ? dHp : dMp) + pass; /* interleaved complex: imaginary parts at +1 */
+                for (int J = 0; J < n; J++) {
+                    int c0J, ncJ;
+                    kid_range(ncol, n, J, &c0J, &ncJ);
+                    if (ncJ <= 0) continue;
+                    const double *A = (const double *)ms->kids[J]->d_res_Y; /* peer pointer when J != I */
+                    const int nl = launch_gemm_tn(k, A, ms->kids[J]->ld * words, B, ldv, ncJ, ncI, K, 1.0, Cblk + (size_t)c0J * words, ncol, words);
+                    if (nl < 0) return 1;
+                    k->stats.kernel_launches += nl;
+                }
+                if (pass == 1 && which == 0 && cudaStreamSynchronize(k->stream) != cudaSuccess) return chefsi_fail(k, "subspace_project: GEMM failed"); /* d_res_T is reused */
+            }
+        }
+        const size_t w = (size_t)ncol * esz;
+        if (cudaMemcpy2DAsync((char *)Mp + (size_t)c0I * ldp * esz, ldp * esz, dMp, w, w, ncI, cudaMemcpyDeviceToHost, k->stream) != cudaSuccess ||
+            cudaMemcpy2DAsync((char *)Hp + (size_t)c0I * ldp * esz, ldp * esz, dHp, w, w, ncI, cudaMemcpyDeviceToHost, k->stream) != cudaSuccess ||
+            cudaStreamSynchronize(k->stream) != cudaSuccess)
+            return chefsi_fail(k, "subspace_project: copy of Hp / Mp failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    });
+    if (rc) return rc;
+    ms->sub_ncol = ncol;
+    ms->sub_complex = is_complex;
+    return 0;
+}
+
+int multi_subspace_rotate(chefsi_ctx *lead, const void *Q, size_t ldq, int ncol, void *X, size_t ldx, bool is_complex)
+{
+    MultiState *ms = lead->multi;
+    const int n = (int)ms->kids.size();
+    if (ms->sub_ncol != ncol || ms->sub_complex != (int)is_complex)
+        return chefsi_fail(lead, "subspace_rotate: no resident block of %d columns (call chefsi_subspace_project first)", ncol);
+    if (ldq < (size_t)ncol || ldx < lead->Nd) return chefsi_fail(lead, "subspace_rotate: bad dimensions");
+    const int words = is_complex ? 2 : 1;
+    const size_t esz = sizeof(double) * words;
+    /* phase 1: complex data needs i Y_J next to Y_J on every device before anybody multiplies */
+    if (is_complex) {
+        const int rc = multi_parallel(lead, [&](int r) {
+            chefsi_ctx *k = ms->kids[r];
+            int c0, nc;
+            kid_range(ncol, n, r, &c0, &nc);
+            if (nc <= 0) return 0;
+            if (cudaSetDevice(k->device) != cudaSuccess) return chefsi_fail(k, "cudaSetDevice failed");
+            if (launch_rot90(k, k->d_res_Y, k->d_res_T, lead->Nd, k->ld, nc, 1.0) < 0) return 1;
+            return cudaStreamSynchronize(k->stream) == cudaSuccess ? 0 : chefsi_fail(k, "subspace_rotate: rotation pass failed");
+        });
+        if (rc) return rc;
+    }
+    /* phase 2 (per device I): X_I = sum_J Y_J Q[J, I], Y_J read through peer memory, accumulated in W_I */
+    const int rc = multi_parallel(lead, [&](int I) {
+        chefsi_ctx *k = ms->kids[I];
+        int c0I, ncI;
+        kid_range(ncol, n, I, &c0I, &ncI);
+        if (ncI <= 0) return 0;
+        if (cudaSetDevice(k->device) != cudaSuccess) return chefsi_fail(k, "cudaSetDevice failed");
+        const size_t w = (size_t)ncol * esz;
+        double *dQ = (double *)ms->d_q[I];
+        if (cudaMemcpy2DAsync(dQ, w, (const char *)Q + (size_t)c0I * ldq * esz, ldq * esz, w, ncI, cudaMemcpyHostToDevice, k->stream) != cudaSuccess)
+            return chefsi_fail(k, "subspace_rotate: upload of Q failed");
+        const double *Qr = dQ, *Qi = nullptr;
+        if (is_complex) {
+            if (launch_split_complex(k, dQ, ncol, ncol, ncI, (double *)ms->d_qr[I], (double *)ms->d_qi[I]) < 0) return 1;
+            Qr = (const double *)ms->d_qr[I];
+            Qi = (const double *)ms->d_qi[I];
+        }
+        const size_t K = lead->Nd * words;
+        int first = 1;
+        for (int J = 0; J < n; J++) {
+            int c0J, ncJ;
+            kid_range(ncol, n, J, &c0J, &ncJ);
+            if (ncJ <= 0) continue;
+            chefsi_ctx *kj = ms->kids[J];
+            int nl = launch_gemm_nn(k, (const double *)kj->d_res_Y, kj->ld * words, Qr + c0J, ncol, K, ncJ, ncI, (double *)k->d_res_W, k->ld * words, first ? 0 : 1);
+            if (nl < 0) return 1;
+            if (is_complex) {
+                nl = launch_gemm_nn(k, (const double *)kj->d_res_T, kj->ld * words, Qi + c0J, ncol, K, ncJ, ncI, (double *)k->d_res_W, k->ld * words, 1);
+                if (nl < 0) return 1;
+            }
+            first = 0;
+            k->stats.kernel_launches += is_complex ? 2 : 1;
+        }
+        if (cudaMemcpy2DAsync((char *)X + (size_t)c0I * ldx * esz, ldx * esz, k->d_res_W, k->ld * esz, lead->Nd * esz, ncI, cudaMemcpyDeviceToHost, k->stream) != cudaSuccess ||
+            cudaStreamSynchronize(k->stream) != cudaSuccess)
+            return chefsi_fail(k, "subspace_rotate: GEMM / copy of the rotated block failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    });
+    if (rc) return rc;
+    for (chefsi_ctx *k : ms->kids) k->res_ncol = 0; /* consumed */
+    ms->sub_ncol = 0;
+    return 0;
 }

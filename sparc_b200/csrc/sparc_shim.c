@@ -92,14 +92,6 @@ static struct {
     double t_filter_fwd;
 } G;
 
-/* the context will own several devices (CHEFSI_B200_DEVICES="0,1,..."): known before the context exists, because the
- * single-device-only routines (Lanczos, AAR, the subspace steps) decide on it before their first call creates it */
-static int shim_is_multi(void)
-{
-    const char *devs = getenv("CHEFSI_B200_DEVICES");
-    return devs && strchr(devs, ',') != NULL;
-}
-
 static void shim_fatal(const char *what)
 {
     fprintf(stderr, "[chefsi_b200 shim] %s: %s\n", what, chefsi_last_error(G.ctx));
@@ -526,7 +518,7 @@ static void shim_dump_outputs(FILE *f, const SPARC_OBJ *S, int is_kpt, const voi
 static int shim_subspace_ok(const SPARC_OBJ *S, int ncol)
 {
 #ifdef USE_DP_SUBEIG
-    if (getenv("CHEFSI_B200_NO_SUBSPACE") || shim_is_multi()) return 0;
+    if (getenv("CHEFSI_B200_NO_SUBSPACE")) return 0; /* a multi-device context does these steps over peer memory (multi.cu) */
     DP_CheFSI_t dp = (DP_CheFSI_t)S->DP_CheFSI;
     if (!dp || dp->nproc_row != 1 || dp->nproc_kpt != 1) return 0;
     if (S->StandardEigenFlag || S->CyclixFlag) return 0;
@@ -541,7 +533,7 @@ static int shim_subspace_ok(const SPARC_OBJ *S, int ncol)
 static int shim_subspace_ok_kpt(const SPARC_OBJ *S, int ncol)
 {
 #ifdef USE_DP_SUBEIG
-    if (getenv("CHEFSI_B200_NO_SUBSPACE") || shim_is_multi()) return 0;
+    if (getenv("CHEFSI_B200_NO_SUBSPACE")) return 0; /* a multi-device context does these steps over peer memory (multi.cu) */
     DP_CheFSI_kpt_t dp = (DP_CheFSI_kpt_t)S->DP_CheFSI_kpt;
     if (!dp || dp->nproc_row != 1 || dp->nproc_kpt != 1) return 0;
     if (S->CyclixFlag) return 0;
@@ -825,7 +817,7 @@ void Lanczos(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NL
              NLOC_PROJ_OBJ *nlocProj, double *eigmin, double *eigmax, double *x0, double TOL_min, double TOL_max, int MAXIT,
              int k, int spn_i, MPI_Comm comm, MPI_Request *req_veff_loc)
 {
-    int ok = (comm != MPI_COMM_NULL) && !shim_is_multi() && !getenv("CHEFSI_B200_NO_LANCZOS") && pSPARC->kptcomm_inter == MPI_COMM_NULL;
+    int ok = (comm != MPI_COMM_NULL) && !getenv("CHEFSI_B200_NO_LANCZOS") && pSPARC->kptcomm_inter == MPI_COMM_NULL;
     int DMnd = 0;
     if (ok) {
         DMnd = (1 - DMVertices[0] + DMVertices[1]) * (1 - DMVertices[2] + DMVertices[3]) * (1 - DMVertices[4] + DMVertices[5]);
@@ -860,7 +852,7 @@ void AAR(SPARC_OBJ *pSPARC, void (*res_fun)(SPARC_OBJ *, int, double, double *, 
          double omega, double beta, int m, int p, double tol, int max_iter, MPI_Comm comm)
 {
     if (comm == MPI_COMM_NULL) return; /* linearSolver.c:48 */
-    int ok = res_fun == poisson_residual && precond_fun == Jacobi_preconditioner && !shim_is_multi() && m >= 1 && m <= 16 &&
+    int ok = res_fun == poisson_residual && precond_fun == Jacobi_preconditioner && m >= 1 && m <= 16 &&
              !getenv("CHEFSI_B200_DISABLE") && !getenv("CHEFSI_B200_NO_AAR") && !getenv("CHEFSI_B200_NO_LAP");
     if (ok) {
         int nproc = 1;
