@@ -190,10 +190,12 @@ class Reference:
         return X, Y
 
     def lanczos(self, x0, tol_min, tol_max, maxit=1000):
-        """The reference's own Lanczos (src/eigenSolver.c:1920) on this problem: (eigmin, eigmax)."""
-        x0 = np.array(x0, dtype=np.float64, copy=True, order="C").reshape(-1)
+        """The reference's own Lanczos (src/eigenSolver.c:1920; complex x0: Lanczos_kpt, src/eigenSolverKpt.c:1361)
+        on this problem: (eigmin, eigmax)."""
+        cplx = np.iscomplexobj(x0)
+        x0 = np.array(x0, dtype=np.complex128 if cplx else np.float64, copy=True, order="C").reshape(-1)
         lo, hi = C.c_double(0), C.c_double(0)
-        self.lib.ref_lanczos(self.h, _ptr(x0), C.c_double(tol_min), C.c_double(tol_max), C.c_int(maxit),
+        (self.lib.ref_lanczos_kpt if cplx else self.lib.ref_lanczos)(self.h, _ptr(x0), C.c_double(tol_min), C.c_double(tol_max), C.c_int(maxit),
                              C.byref(lo), C.byref(hi))
         return lo.value, hi.value
 

@@ -10,12 +10,16 @@ from __future__ import annotations
 import numpy as np
 
 
-def lanczos(port, grid, proj, veff, x0, tol_min, tol_max, maxit=1000):
-    """Extreme eigenvalues of H by Lanczos -- src/eigenSolver.c:1920-2129.  Returns (eigmin, eigmax, iterations)."""
-    H = lambda v: port.hamiltonian_mult(grid, proj, veff, 0.0, v[None, :].copy())[0]
+def lanczos(port, grid, proj, veff, x0, tol_min, tol_max, maxit=1000, kvec=None):
+    """Extreme eigenvalues of H by Lanczos -- src/eigenSolver.c:1920-2129 (line numbers below), and with kvec
+    Lanczos_kpt, src/eigenSolverKpt.c:1361-1566: the same loop on complex vectors whose dot product keeps only the
+    REAL part (VectorDotProduct_complex accumulates conj(a)*b into a double, src/tools.c:815-826) -- for a Hermitian
+    H the imaginary part is rounding noise anyway.  Returns (eigmin, eigmax, iterations)."""
+    H = lambda v: port.hamiltonian_mult(grid, proj, veff, 0.0, v[None, :].copy(), kvec=kvec)[0]
+    dot = (lambda u, v: u @ v) if kvec is None else (lambda u, v: float(np.real(np.vdot(u, v))))
     vjm1 = x0 / np.linalg.norm(x0)                      # :1986-1992
     vj = H(vjm1)                                        # :2003
-    a = [vjm1 @ vj]                                     # :2012
+    a = [dot(vjm1, vj)]                                 # :2012
     vj = vj - a[0] * vjm1                               # :2014-2015
     b = [np.linalg.norm(vj)]                            # :2017
     vj = vj / b[0]                                      # :2036-2038
@@ -23,7 +27,7 @@ def lanczos(port, grid, proj, veff, x0, tol_min, tol_max, maxit=1000):
     j = 0
     while True:
         vjp1 = H(vj)                                    # :2048
-        a.append(vj @ vjp1)                             # :2054
+        a.append(dot(vj, vjp1))                         # :2054
         vjp1 = vjp1 - (a[j + 1] * vj + b[j] * vjm1)     # :2056-2061
         vjm1 = vj
         b.append(np.linalg.norm(vjp1))                  # :2063

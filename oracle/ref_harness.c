@@ -271,6 +271,15 @@ void ref_lanczos(void *h, double *x0, double tol_min, double tol_max, int maxit,
             0, 0, MPI_COMM_SELF, &req);
 }
 
+/* Lanczos_kpt (src/eigenSolverKpt.c:1361-1566) from the complex start vector x0, at the problem's k-point */
+void ref_lanczos_kpt(void *h, double _Complex *x0, double tol_min, double tol_max, int maxit, double *eigmin, double *eigmax)
+{
+    ref_problem_t *P = (ref_problem_t *)h;
+    MPI_Request req = MPI_REQUEST_NULL;
+    Lanczos_kpt(&P->S, P->DMVertices, P->veff, P->S.Atom_Influence_nloc, P->S.nlocProj, eigmin, eigmax, x0, tol_min, tol_max,
+                maxit, 0, 0, MPI_COMM_SELF, &req);
+}
+
 /* AAR (src/linearSolver.c:38-146) with the operator pair SPARC uses: poisson_residual (lapVecRoutines.c:61) and
  * Jacobi_preconditioner; x is the start vector on entry and the solution on return */
 void ref_aar(void *h, double c, double *x, double *b, double omega, double beta, int m, int p, double tol, int max_iter)

@@ -564,8 +564,8 @@ int lap_residual_device(chefsi_ctx *ctx, double c, const void *x, const void *b,
     return rc;
 }
 
-/* one H apply (c = 0) of a single resident real column: the operator of lanczos.cu */
-int apply_h_device(chefsi_ctx *ctx, const void *x, void *Hx) { return hmult_device(ctx, 1, 0.0, x, Hx, false); }
+/* one H apply (c = 0) of a single resident column: the operator of lanczos.cu */
+int apply_h_device(chefsi_ctx *ctx, const void *x, void *Hx, bool is_complex) { return hmult_device(ctx, 1, 0.0, x, Hx, is_complex); }
 
 extern "C" int chefsi_hamiltonian_mult_device(chefsi_ctx_t *ctx, int ncol, double c, const double *x, double *Hx)
 {
@@ -772,7 +772,24 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
         /* only for long pipelines: a chunk of < 32 columns costs the projector kernel as much as 32 (it works on
            groups of 32 columns), so on a short block the ramp costs more than the copies it hides (measured at
            128 columns per rank: 8.1e9 flat vs 5.7e9 ramped at N = 2) */
-        if (ncol >= 6 * chunk && q >= 8 && getenv("CHEFSI_B200_FLAT_CHUNKS") == nullptr) {
+        const char *sched_env = getenv("CHEFSI_B200_CHUNK_SCHED"); /* experiments: explicit "c0,c1,..." (the last entry repeats) */
+        if (sched_env && *sched_env) {
+            std::vector<int> pat;
+            for (const char *p2 = sched_env; *p2;) {
+                const int v = atoi(p2);
+                if (v > 0) pat.push_back(v < chunk ? v : chunk);
+                while (*p2 && *p2 != ',') p2++;
+                if (*p2 == ',') p2++;
+            }
+            int rest = ncol;
+            for (size_t i = 0; rest > 0 && !pat.empty(); i++) {
+                const int c1 = pat[i < pat.size() ? i : pat.size() - 1];
+                sched.push_back(rest < c1 ? rest : c1);
+                rest -= sched.back();
+            }
+        }
+        if (!sched.empty()) {
+        } else if (ncol >= 6 * chunk && q >= 8 && getenv("CHEFSI_B200_FLAT_CHUNKS") == nullptr) {
             int rest = ncol - 2 * (q + h);
             sched.push_back(q); sched.push_back(h);
             while (rest > 0) { const int c1 = rest < chunk ? rest : chunk; sched.push_back(c1); rest -= c1; }

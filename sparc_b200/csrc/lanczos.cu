@@ -1,6 +1,12 @@
 /*
  * lanczos.cu -- Lanczos estimate of the extreme eigenvalues of H with every vector resident on the device
- * (SURVEY.md 8f-2), real data, single-device contexts.
+ * (SURVEY.md 8f-2), real (chefsi_lanczos) and complex / k-point (chefsi_lanczos_kpt) data.
+ *
+ * Lanczos_kpt (src/eigenSolverKpt.c:1361-1566) is the same loop on complex vectors, and its inner products are REAL:
+ * VectorDotProduct_complex accumulates conj(a_i) b_i into a double (src/tools.c:815-826, the imaginary part is dropped)
+ * and Vector2Norm_complex is the 2-norm.  Both are the real dot product / norm of the interleaved (re, im) view of
+ * length 2 Nd, and a, b are real, so the only complex step is the H apply: the kernels below run unchanged on the
+ * real view.
  *
  * Replaces the body of Lanczos (src/eigenSolver.c:1920-2129) at one rank: start from x0 / ||x0||, three-term
  * recurrence V_{j+1} = H V_j - a_{j+1} V_j - b_j V_{j-1}, a = <V_j, H V_j>, b = ||V_{j+1}||, and after every step the
@@ -128,22 +134,26 @@ void tridiag_extremes(const std::vector<double> &d, const std::vector<double> &e
 
 }  // namespace
 
-int apply_h_device(chefsi_ctx *ctx, const void *x, void *Hx); /* chefsi_api.cu: one H apply (c = 0) of a resident column */
+int apply_h_device(chefsi_ctx *ctx, const void *x, void *Hx, bool is_complex); /* chefsi_api.cu: one H apply (c = 0) of a resident column */
 
-extern "C" int chefsi_lanczos(chefsi_ctx_t *ctx, const double *x0, double tol_min, double tol_max, int maxit, double *eigmin,
-                              double *eigmax, int *iterations)
+namespace {
+
+/* words = 1: real column of Nd doubles; words = 2: complex column seen as 2 Nd doubles */
+int lanczos_impl(chefsi_ctx *ctx, const void *x0, int words, double tol_min, double tol_max, int maxit, double *eigmin, double *eigmax,
+                 int *iterations)
 {
     if (!ctx || !x0 || !eigmin || !eigmax) return 1;
     if (ctx->multi) { /* a single vector does not split over devices: the first one iterates */
         chefsi_ctx *k = multi_first(ctx);
-        const int rc = chefsi_lanczos(k, x0, tol_min, tol_max, maxit, eigmin, eigmax, iterations);
+        const int rc = lanczos_impl(k, x0, words, tol_min, tol_max, maxit, eigmin, eigmax, iterations);
         if (rc) { strncpy(ctx->err, k->err, sizeof(ctx->err) - 1); ctx->err[sizeof(ctx->err) - 1] = 0; }
         return rc;
     }
     if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
     if (maxit < 1) return chefsi_fail(ctx, "lanczos: maxit must be positive");
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t n = ctx->Nd, ldb = ctx->ld * sizeof(double);
+    const bool cplx = words == 2;
+    const size_t n = (size_t)ctx->Nd * words, ldb = (size_t)ctx->ld * words * sizeof(double);
     /* workspace: 3 vectors, scalars a[maxit+1], b[maxit+1], partials, ticket */
     const size_t scal = (size_t)2 * (maxit + 2) + kBlocks + 8;
     const size_t need = 3 * ldb + scal * sizeof(double);
@@ -173,7 +183,7 @@ extern "C" int chefsi_lanczos(chefsi_ctx_t *ctx, const double *x0, double tol_mi
     CHEFSI_CUDA(ctx, cudaMemcpyAsync(tmp, h_ab, sizeof(double), cudaMemcpyHostToDevice, st));
     scale_kernel<<<kBlocks, kThreads, 0, st>>>(Vjm1, Vjp1, tmp, n);
     /* V_j = H V_{j-1}; a0 = <V_{j-1}, V_j>; V_j -= a0 V_{j-1}; b0 = ||V_j||; V_j /= b0   (:2003-2040) */
-    if (apply_h_device(ctx, Vjm1, Vjp1)) return 1;
+    if (apply_h_device(ctx, Vjm1, Vjp1, cplx)) return 1;
     dot_kernel<<<kBlocks, kThreads, 0, st>>>(Vjm1, Vjp1, n, partials, ticket, da);
     update_kernel<<<kBlocks, kThreads, 0, st>>>(Vjp1, Vjm1, nullptr, da, 0.0, n, partials, ticket, db);
     scale_kernel<<<kBlocks, kThreads, 0, st>>>(Vj, Vjp1, db, n);
@@ -189,7 +199,7 @@ extern "C" int chefsi_lanczos(chefsi_ctx_t *ctx, const double *x0, double tol_mi
     double err_min = tol_min + 1.0, err_max = tol_max + 1.0;
     int j = 0;
     while ((err_min > tol_min || err_max > tol_max) && j < maxit) {
-        if (apply_h_device(ctx, Vj, Vjp1)) return 1;                                        /* V_{j+1} = H V_j          (:2048) */
+        if (apply_h_device(ctx, Vj, Vjp1, cplx)) return 1;                                   /* V_{j+1} = H V_j          (:2048) */
         dot_kernel<<<kBlocks, kThreads, 0, st>>>(Vj, Vjp1, n, partials, ticket, da + j + 1);  /* a[j+1] = <V_j, V_{j+1}>  (:2054) */
         update_kernel<<<kBlocks, kThreads, 0, st>>>(Vjp1, Vj, Vjm1, da + j + 1, b[j], n, partials, ticket, db + j + 1); /* (:2056-2063) */
         scale_kernel<<<kBlocks, kThreads, 0, st>>>(Vj, Vjp1, db + j + 1, n);                  /* V_j = V_{j+1} / b[j+1]   (:2068-2071) */
@@ -213,4 +223,18 @@ extern "C" int chefsi_lanczos(chefsi_ctx_t *ctx, const double *x0, double tol_mi
     *eigmax = emax;
     if (iterations) *iterations = j;
     return 0;
+}
+
+}  // namespace
+
+extern "C" int chefsi_lanczos(chefsi_ctx_t *ctx, const double *x0, double tol_min, double tol_max, int maxit, double *eigmin,
+                              double *eigmax, int *iterations)
+{
+    return lanczos_impl(ctx, x0, 1, tol_min, tol_max, maxit, eigmin, eigmax, iterations);
+}
+
+extern "C" int chefsi_lanczos_kpt(chefsi_ctx_t *ctx, const void *x0, double tol_min, double tol_max, int maxit, double *eigmin,
+                                  double *eigmax, int *iterations)
+{
+    return lanczos_impl(ctx, x0, 2, tol_min, tol_max, maxit, eigmin, eigmax, iterations);
 }

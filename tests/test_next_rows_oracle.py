@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import next_rows
-from tests.cases import small_case
+from tests.cases import KVEC, small_case
 
 
 @pytest.fixture(scope="module")
@@ -23,6 +23,19 @@ def test_lanczos_restatement_vs_reference(port, ref_cls, cell_typ, BC):
     tol = 1e-2
     lo_r, hi_r = ref.lanczos(x[0], tol, tol, 300)
     lo, hi, it = next_rows.lanczos(port, g, proj, veff, x[0], tol, tol, 300)
+    assert it < 300
+    assert abs(lo - lo_r) < 1e-9 * max(1.0, abs(hi_r)) and abs(hi - hi_r) < 1e-9 * max(1.0, abs(hi_r))
+
+
+@pytest.mark.parametrize("cell_typ,BC", [(0, (0, 0, 0)), (17, (0, 0, 0)), (0, (0, 0, 1))])
+def test_lanczos_kpt_restatement_vs_reference(port, ref_cls, cell_typ, BC):
+    """Lanczos_kpt (eigenSolverKpt.c:1361): complex vectors, real-part dot products (tools.c:815)."""
+    g, veff, proj, x = small_case(cell_typ, BC, ncol=1, complex_=True)
+    kvec = tuple(kk if bc == 0 else 0.0 for kk, bc in zip(KVEC, g.BC))
+    ref = ref_cls(g, proj, veff, kvec=kvec)
+    tol = 1e-2
+    lo_r, hi_r = ref.lanczos(x[0], tol, tol, 300)
+    lo, hi, it = next_rows.lanczos(port, g, proj, veff, x[0], tol, tol, 300, kvec=kvec)
     assert it < 300
     assert abs(lo - lo_r) < 1e-9 * max(1.0, abs(hi_r)) and abs(hi - hi_r) < 1e-9 * max(1.0, abs(hi_r))
 
