@@ -165,10 +165,15 @@ int chefsi_subspace_rotate_kpt(chefsi_ctx_t *ctx, const void *Q, size_t ldq, int
 
 /* Extreme eigenvalues of H = -1/2 Lap + Veff + Vnl by the Lanczos iteration with every vector resident on the device
  * (SURVEY.md 8f-2): the body of Lanczos (src/eigenSolver.c:1920-2129) at one rank.  x0: start vector (host, Nd doubles);
- * stops when |eigmin - previous| <= tol_min and |eigmax - previous| <= tol_max, or after maxit steps.  Real data,
- * single-device context.  Fails (the caller falls back to the reference routine) if x0 is an eigenvector of H. */
+ * stops when |eigmin - previous| <= tol_min and |eigmax - previous| <= tol_max, or after maxit steps.
+ * Fails (the caller falls back to the reference routine) if x0 is an eigenvector of H.
+ * chefsi_lanczos_kpt: the body of Lanczos_kpt (src/eigenSolverKpt.c:1361-1566) for the k-point set with
+ * chefsi_set_kpoint; x0: Nd complex numbers (interleaved re/im).  The reference's complex dot product keeps the real
+ * part only (VectorDotProduct_complex, src/tools.c:815-826), and so does this. */
 int chefsi_lanczos(chefsi_ctx_t *ctx, const double *x0, double tol_min, double tol_max, int maxit, double *eigmin,
                    double *eigmax, int *iterations);
+int chefsi_lanczos_kpt(chefsi_ctx_t *ctx, const void *x0, double tol_min, double tol_max, int maxit, double *eigmin,
+                       double *eigmax, int *iterations);
 
 /* Alternating Anderson-Richardson solve of -(Lap + c) x = b with the Jacobi preconditioner, every vector resident on the
  * device: AAR (src/linearSolver.c:38-146) with res_fun = poisson_residual (src/lapVecRoutines.c:61) and

@@ -18,7 +18,7 @@ EXPORTS = (
     "chefsi_set_grid", "chefsi_set_projectors", "chefsi_set_veff", "chefsi_set_kpoint",
     "chefsi_chebyshev_filter", "chefsi_chebyshev_filter_kpt",
     "chefsi_hamiltonian_mult", "chefsi_hamiltonian_mult_kpt", "chefsi_laplacian_mult", "chefsi_laplacian_mult_kpt",
-    "chefsi_lanczos", "chefsi_poisson_aar", "chefsi_subspace_reserve", "chefsi_subspace_reserve_kpt", "chefsi_subspace_project_kpt", "chefsi_subspace_rotate_kpt", "chefsi_subspace_project", "chefsi_subspace_rotate",
+    "chefsi_lanczos", "chefsi_lanczos_kpt", "chefsi_poisson_aar", "chefsi_subspace_reserve", "chefsi_subspace_reserve_kpt", "chefsi_subspace_project_kpt", "chefsi_subspace_rotate_kpt", "chefsi_subspace_project", "chefsi_subspace_rotate",
     "chefsi_device_ld",
     "chefsi_chebyshev_filter_device", "chefsi_chebyshev_filter_kpt_device",
     "chefsi_hamiltonian_mult_device", "chefsi_hamiltonian_mult_kpt_device",
@@ -82,6 +82,7 @@ def load_library() -> C.CDLL:
     for name in ("chefsi_laplacian_mult", "chefsi_laplacian_mult_kpt"):
         getattr(lib, name).argtypes = [vp, i, d, d, dp, sz, dp, sz]
     lib.chefsi_lanczos.argtypes = [vp, dp, d, d, i, C.POINTER(C.c_double), C.POINTER(C.c_double), ip]
+    lib.chefsi_lanczos_kpt.argtypes = [vp, vp, d, d, i, C.POINTER(C.c_double), C.POINTER(C.c_double), ip]
     lib.chefsi_poisson_aar.argtypes = [vp, d, dp, dp, d, d, i, i, d, i, ip, C.POINTER(C.c_double)]
     lib.chefsi_subspace_reserve.argtypes = [vp, i]
     lib.chefsi_subspace_reserve_kpt.argtypes = [vp, i]

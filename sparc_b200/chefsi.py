@@ -143,11 +143,13 @@ class ChefsiContext:
         return it.value, rn.value
 
     def Lanczos(self, x0, tol_min, tol_max, maxit=1000):
-        """(eigmin, eigmax, iterations) of H by Lanczos from x0 (src/eigenSolver.c:1920), vectors resident on the device."""
-        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1)
+        """(eigmin, eigmax, iterations) of H by Lanczos from x0 (src/eigenSolver.c:1920; complex x0: Lanczos_kpt,
+        src/eigenSolverKpt.c:1361, at the k-point set with set_kpoint), vectors resident on the device."""
+        cplx = np.iscomplexobj(x0)
+        x0 = np.ascontiguousarray(x0, dtype=np.complex128 if cplx else np.float64).reshape(-1)
         lo, hi, it = C.c_double(0), C.c_double(0), C.c_int(0)
-        self._check(self._lib.chefsi_lanczos(self._h, _addr(x0), float(tol_min), float(tol_max), int(maxit),
-                                             C.byref(lo), C.byref(hi), C.byref(it)))
+        fn = self._lib.chefsi_lanczos_kpt if cplx else self._lib.chefsi_lanczos
+        self._check(fn(self._h, _addr(x0), float(tol_min), float(tol_max), int(maxit), C.byref(lo), C.byref(hi), C.byref(it)))
         return lo.value, hi.value, it.value
 
     # -- Rayleigh-Ritz steps on the resident block (src/eigenSolver.c:939-1086, 1386-1443) ------------------------

@@ -62,6 +62,9 @@ void DP_Subspace_Rotation_kpt_ref(SPARC_OBJ *pSPARC, double _Complex *Psi_rot);
 void Lanczos_ref(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc,
                  NLOC_PROJ_OBJ *nlocProj, double *eigmin, double *eigmax, double *x0, double TOL_min, double TOL_max, int MAXIT,
                  int k, int spn_i, MPI_Comm comm, MPI_Request *req_veff_loc);
+void Lanczos_kpt_ref(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc,
+                     NLOC_PROJ_OBJ *nlocProj, double *eigmin, double *eigmax, double _Complex *x0, double TOL_min, double TOL_max,
+                     int MAXIT, int kpt, int spn_i, MPI_Comm comm, MPI_Request *req_veff_loc);
 void AAR_ref(SPARC_OBJ *pSPARC, void (*res_fun)(SPARC_OBJ *, int, double, double *, double *, double *, MPI_Comm, double *),
              void (*precond_fun)(SPARC_OBJ *, int, double, double *, double *, MPI_Comm), double c, int N, double *x, double *b,
              double omega, double beta, int m, int p, double tol, int max_iter, MPI_Comm comm);
@@ -841,6 +844,39 @@ void Lanczos(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NL
     }
     Lanczos_ref(pSPARC, DMVertices, Veff_loc, Atom_Influence_nloc, nlocProj, eigmin, eigmax, x0, TOL_min, TOL_max, MAXIT, k, spn_i,
                 comm, req_veff_loc);
+}
+
+/* The k-point Lanczos -- src/eigenSolverKpt.c:1361-1566: complex vectors, real-part inner products (tools.c:815-826).
+ * Same conditions and fallback as Lanczos above; the k-point is the one of index `kpt` (k1_loc / k2_loc / k3_loc). */
+void Lanczos_kpt(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc,
+                 NLOC_PROJ_OBJ *nlocProj, double *eigmin, double *eigmax, double _Complex *x0, double TOL_min, double TOL_max,
+                 int MAXIT, int kpt, int spn_i, MPI_Comm comm, MPI_Request *req_veff_loc)
+{
+    int ok = (comm != MPI_COMM_NULL) && !getenv("CHEFSI_B200_NO_LANCZOS") && pSPARC->kptcomm_inter == MPI_COMM_NULL;
+    int DMnd = 0;
+    if (ok) {
+        DMnd = (1 - DMVertices[0] + DMVertices[1]) * (1 - DMVertices[2] + DMVertices[3]) * (1 - DMVertices[4] + DMVertices[5]);
+        ok = shim_supported(pSPARC, DMnd, DMVertices, comm, nlocProj);
+    }
+    if (ok) {
+        shim_init();
+        const double t1 = MPI_Wtime();
+        MPI_Wait(req_veff_loc, MPI_STATUS_IGNORE); /* eigenSolverKpt.c:1443 */
+        shim_sync_grid(pSPARC);
+        shim_sync_projectors(pSPARC, Atom_Influence_nloc, nlocProj, 1);
+        shim_sync_veff(Veff_loc, (size_t)DMnd);
+        if (chefsi_set_kpoint(G.ctx, pSPARC->k1_loc[kpt], pSPARC->k2_loc[kpt], pSPARC->k3_loc[kpt]) != 0) shim_fatal("chefsi_set_kpoint");
+        int iters = 0;
+        if (chefsi_lanczos_kpt(G.ctx, x0, TOL_min, TOL_max, MAXIT, eigmin, eigmax, &iters) == 0) {
+            G.n_lanczos++;
+            G.n_lanczos_iter += (unsigned long long)iters;
+            G.t_lanczos += MPI_Wtime() - t1;
+            return;
+        }
+        if (G.verbose) fprintf(stderr, "[chefsi_b200 shim] Lanczos_kpt: %s -- this call runs the reference iteration\n", chefsi_last_error(G.ctx));
+    }
+    Lanczos_kpt_ref(pSPARC, DMVertices, Veff_loc, Atom_Influence_nloc, nlocProj, eigmin, eigmax, x0, TOL_min, TOL_max, MAXIT, kpt,
+                    spn_i, comm, req_veff_loc);
 }
 
 /* Alternating Anderson-Richardson solve -- src/linearSolver.c:38-146.  SPARC calls it with one operator

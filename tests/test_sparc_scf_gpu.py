@@ -57,6 +57,8 @@ def test_scf_energy_matches_reference(name, tmp_path):
     print(f"{name}: E = {e:.10f} Ha/atom, refout {e_ref:.10f}, diff {e - e_ref:+.2e}; "
           f"{n_filter} filter calls, {n_hmult} H applies on the GPU, {n_fwd} forwarded")
     assert n_filter > 0 and n_fwd == 0, "the CUDA path did not serve the filter calls"
+    m2 = re.search(r"(\d+) Lanczos calls \((\d+) iterations\)", log)
+    assert m2 and int(m2.group(1)) > 0, "Lanczos / Lanczos_kpt did not run on the device"
     if name == "O2_spin_coarse":
         # collinear spin: two filter calls per CheFSI pass (X = Xorb + spn_i * DMnd, ld = 2 DMnd, eigenSolver.c:325-328);
         # .refout = the unmodified reference at np = 1 (integration/cases_extra/README.md)

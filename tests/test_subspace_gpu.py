@@ -7,7 +7,7 @@ import pytest
 
 from oracle import next_rows  # checker only
 from sparc_b200 import problem as P
-from tests.cases import overlap_case, rel_fro, small_case
+from tests.cases import KVEC, overlap_case, rel_fro, small_case
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -116,6 +116,21 @@ def test_lanczos_extreme_eigenvalues(ctx, port, cell_typ, BC):
     tol = 1e-2
     lo, hi, it = ctx.Lanczos(x[0], tol, tol, maxit=300)
     emin, emax, j = next_rows.lanczos(port, g, proj, veff, x[0], tol, tol, 300)
+    assert it == j
+    assert abs(lo - emin) < 1e-9 * max(1.0, abs(emax)) and abs(hi - emax) < 1e-9 * max(1.0, abs(emax))
+
+
+@pytest.mark.parametrize("cell_typ,BC", [(0, (0, 0, 0)), (17, (0, 0, 0)), (0, (0, 0, 1))])
+def test_lanczos_kpt_extreme_eigenvalues(ctx, port, cell_typ, BC):
+    """chefsi_lanczos_kpt (Lanczos_kpt, eigenSolverKpt.c:1361-1566: complex vectors, real-part dot products) against the
+    oracle's restatement, itself pinned to the reference's own Lanczos_kpt by tests/test_next_rows_oracle.py."""
+    g, veff, proj, x = small_case(cell_typ, BC, ncol=1, complex_=True)
+    kvec = tuple(kk if bc == 0 else 0.0 for kk, bc in zip(KVEC, g.BC))
+    _setup(ctx, g, veff, proj)
+    ctx.set_kpoint(kvec)
+    tol = 1e-2
+    lo, hi, it = ctx.Lanczos(x[0], tol, tol, maxit=300)
+    emin, emax, j = next_rows.lanczos(port, g, proj, veff, x[0], tol, tol, 300, kvec=kvec)
     assert it == j
     assert abs(lo - emin) < 1e-9 * max(1.0, abs(emax)) and abs(hi - emax) < 1e-9 * max(1.0, abs(emax))
 
