@@ -153,7 +153,8 @@ int chefsi_laplacian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double a, double c, c
  * The three GEMMs run on the FP64 tensor cores (DMMA); only Hp, Mp, Q and the rotated block cross PCIe.
  * chefsi_subspace_reserve allocates the two resident blocks for `ncol` columns (fails when they do not fit).
  * chefsi_subspace_project takes Y from the device when the last filter call kept it (CHEFSI_FLAG_KEEP_Y, same host
- * address and column count), otherwise it uploads the host block. chefsi_subspace_rotate needs a preceding project. */
+ * address and column count), otherwise it uploads the host block. chefsi_subspace_rotate needs a preceding project;
+ * Q == NULL: the eigenvectors chefsi_subspace_eig left on the device. */
 int chefsi_subspace_reserve(chefsi_ctx_t *ctx, int ncol);
 int chefsi_subspace_project(chefsi_ctx_t *ctx, const double *Y, size_t ldy, int ncol, double *Hp, double *Mp, size_t ldp);
 int chefsi_subspace_rotate(chefsi_ctx_t *ctx, const double *Q, size_t ldq, int ncol, double *X, size_t ldx);
@@ -162,6 +163,28 @@ int chefsi_subspace_rotate(chefsi_ctx_t *ctx, const double *Q, size_t ldq, int n
 int chefsi_subspace_reserve_kpt(chefsi_ctx_t *ctx, int ncol);
 int chefsi_subspace_project_kpt(chefsi_ctx_t *ctx, const void *Y, size_t ldy, int ncol, void *Hp, void *Mp, size_t ldp);
 int chefsi_subspace_rotate_kpt(chefsi_ctx_t *ctx, const void *Q, size_t ldq, int ncol, void *X, size_t ldx);
+
+/* ---- the subspace eigenproblem and the density -----------------------------------------------------
+ * chefsi_subspace_eig[_kpt] <- DP_Solve_Generalized_EigenProblem      src/eigenSolver.c:1262-1375 (LAPACKE_dsygvd, itype 1, 'V'),
+ *                              DP_Solve_Generalized_EigenProblem_kpt  src/eigenSolverKpt.c:836-930 (LAPACKE_zhegvd):
+ *   Hp q = lambda Mp q.  Hp == Mp == NULL: the matrices chefsi_subspace_project[_kpt] left on the device (single-device
+ *   context, same ncol); otherwise they are uploaded (host, column-major, ld = ldp) -- the form a multi-device context
+ *   needs.  lambda: ncol ascending eigenvalues (host).  Q (host, column-major, ld = ldq; may be NULL): eigenvectors,
+ *   Q^H Mp Q = I.  They also stay on the device: chefsi_subspace_rotate[_kpt] with Q == NULL uses them.
+ *   The reference calls a LAPACK library here; this calls the same routine of cuSOLVER (cusolverDnDsygvd / Zhegvd),
+ *   loaded with dlopen on first use (CHEFSI_B200_CUSOLVER_LIB overrides the name); fails if it is absent.
+ * chefsi_density_accumulate[_kpt] <- the loop body of CalculateDensity_psi  src/electronDensity.c:104-200:
+ *   rho[i] += sum_n g[n] |X[i + n ldx]|^2 for one k-point / spin block (X, rho: host; g[n] = occfac * w_k * occ[n]).
+ *   With the band store on, chefsi_subspace_rotate keeps a device copy of each rotated block keyed by its host address
+ *   and the density reads that copy (consuming it); a block that is not resident is uploaded.  Filtering a host block
+ *   drops its copy.  chefsi_band_store(ctx, n): keep up to n blocks (k-points x spins of the rank); 0 frees them. */
+int chefsi_subspace_eig(chefsi_ctx_t *ctx, int ncol, const double *Hp, const double *Mp, size_t ldp, double *lambda, double *Q,
+                        size_t ldq);
+int chefsi_subspace_eig_kpt(chefsi_ctx_t *ctx, int ncol, const void *Hp, const void *Mp, size_t ldp, double *lambda, void *Q,
+                            size_t ldq);
+int chefsi_band_store(chefsi_ctx_t *ctx, int max_blocks);
+int chefsi_density_accumulate(chefsi_ctx_t *ctx, const double *X, size_t ldx, int ncol, const double *g, double *rho);
+int chefsi_density_accumulate_kpt(chefsi_ctx_t *ctx, const void *X, size_t ldx, int ncol, const double *g, double *rho);
 
 /* Extreme eigenvalues of H = -1/2 Lap + Veff + Vnl by the Lanczos iteration with every vector resident on the device
  * (SURVEY.md 8f-2): the body of Lanczos (src/eigenSolver.c:1920-2129) at one rank.  x0: start vector (host, Nd doubles);
@@ -253,6 +276,10 @@ typedef struct chefsi_stats {
     unsigned int round_barrier_timeouts; /* times a streaming kernel's producer gave up on the round barrier (results are */
                                         /* unaffected; a non-zero count means the xy-halo L2 sharing was lost: a perf cliff) */
     int reserved_;
+    unsigned int density_resident_blocks; /* chefsi_density_accumulate calls served from the band store (no upload)  */
+    unsigned int density_uploaded_blocks; /* ... that had to upload their block from the host                        */
+    unsigned int band_store_misses;       /* rotated blocks the band store could not keep (full, or out of memory)   */
+    unsigned int reserved2_;
 } chefsi_stats_t;
 int chefsi_get_stats(const chefsi_ctx_t *ctx, chefsi_stats_t *out);
 /* when on, every kernel of a filter call is bracketed by CUDA events (adds host

@@ -199,6 +199,28 @@ class Reference:
                              C.byref(lo), C.byref(hi))
         return lo.value, hi.value
 
+    def subspace_eig(self, Hp, Mp):
+        """The reference's own DP_Solve_Generalized_EigenProblem[_kpt] (src/eigenSolver.c:1262, src/eigenSolverKpt.c:836)
+        on column-major n x n Hp, Mp (numpy [n, m] = element (m, n)): (lambda, Q)."""
+        cplx = np.iscomplexobj(Hp)
+        dt = np.complex128 if cplx else np.float64
+        n = Hp.shape[0]
+        Hp = np.array(Hp, dtype=dt, copy=True, order="C")
+        Mp = np.array(Mp, dtype=dt, copy=True, order="C")
+        lam, Q = np.zeros(n), np.zeros((n, n), dtype=dt)
+        (self.lib.ref_subspace_eig_kpt if cplx else self.lib.ref_subspace_eig)(self.h, C.c_int(n), _ptr(Hp), _ptr(Mp), _ptr(lam), _ptr(Q))
+        return lam, Q
+
+    def density(self, X, occ, occfac=2.0, kptwt=1.0):
+        """The reference's own CalculateDensity_psi (src/electronDensity.c:104) for one k-point: rho[Nd]."""
+        cplx = np.iscomplexobj(X)
+        X = np.array(X, dtype=np.complex128 if cplx else np.float64, copy=True, order="C")
+        occ = np.array(occ, dtype=np.float64, copy=True, order="C")
+        rho = np.zeros(X.shape[1])
+        self.lib.ref_density(self.h, C.c_int(X.shape[0]), _ptr(X), C.c_int(int(cplx)), _ptr(occ), C.c_double(occfac),
+                             C.c_double(kptwt), _ptr(rho))
+        return rho
+
     def aar(self, c, x, b, omega=0.6, beta=0.6, m=7, p=6, tol=1e-8, max_iter=1000):
         """The reference's own AAR (src/linearSolver.c:38) with poisson_residual + Jacobi_preconditioner: returns x."""
         x = np.array(x, dtype=np.float64, copy=True, order="C").reshape(-1)

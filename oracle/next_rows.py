@@ -88,3 +88,19 @@ def project(port, grid, proj, veff, Y, kvec=None):
 def rotate(Y, Q):
     """X = Y Q with Q in column-major storage (numpy Q[n, m] = element (m, n)) -- src/eigenSolver.c:1386-1443."""
     return Q @ Y
+
+
+def subspace_eig(Hp, Mp):
+    """Hp q = lambda Mp q, eigenvalues ascending, Q^H Mp Q = I -- DP_Solve_Generalized_EigenProblem, src/eigenSolver.c:
+    1262-1375 (LAPACKE_dsygvd, itype 1) and its k-point twin, src/eigenSolverKpt.c:836-930 (LAPACKE_zhegvd).  Input and
+    output in the reference's column-major storage (numpy [n, m] = element (m, n); row n of Q = eigenvector n).
+    scipy's driver "gvd" is the same LAPACK routine.  Eigenvectors are defined up to a sign / phase each."""
+    import scipy.linalg
+    lam, V = scipy.linalg.eigh(Hp.T, Mp.T, driver="gvd", type=1)
+    return lam, np.ascontiguousarray(V.T)
+
+
+def density(X, g):
+    """rho[i] = sum_n g[n] |X[n, i]|^2 -- the loop body of CalculateDensity_psi, src/electronDensity.c:135-156 (g[n] =
+    occfac * kptWts_loc[k] / Nkpts * occ[n]; the caller scales by 1/dV, :190-196)."""
+    return np.einsum("n,ni->i", np.asarray(g, dtype=np.float64), (X.real ** 2 + X.imag ** 2) if np.iscomplexobj(X) else X * X)

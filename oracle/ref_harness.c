@@ -280,6 +280,60 @@ void ref_lanczos_kpt(void *h, double _Complex *x0, double tol_min, double tol_ma
                 maxit, 0, 0, MPI_COMM_SELF, &req);
 }
 
+/* DP_Solve_Generalized_EigenProblem (src/eigenSolver.c:1262-1375, LAPACK branch: LAPACKE_dsygvd itype 1 'V' 'U') on
+ * caller-provided n x n column-major Hp, Mp (both overwritten, as in the reference): lambda[n], Q = eig_vecs */
+void DP_Solve_Generalized_EigenProblem(SPARC_OBJ *pSPARC, int spn_i);
+void DP_Solve_Generalized_EigenProblem_kpt(SPARC_OBJ *pSPARC, int kpt, int spn_i);
+void ref_subspace_eig(void *h, int n, double *Hp, double *Mp, double *lambda, double *Q)
+{
+    ref_problem_t *P = (ref_problem_t *)h;
+    SPARC_OBJ *S = &P->S;
+    struct DP_CheFSI_s dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.Ns_dp = n; dp.rank_kpt = 0; dp.Hp_local = Hp; dp.Mp_local = Mp; dp.eig_vecs = Q; dp.kpt_comm = MPI_COMM_SELF;
+    void *save_dp = S->DP_CheFSI;
+    double *save_lambda = S->lambda;
+    const int save_lapack = S->useLAPACK, save_std = S->StandardEigenFlag;
+    S->DP_CheFSI = &dp; S->lambda = lambda; S->useLAPACK = 1; S->StandardEigenFlag = 0;
+    DP_Solve_Generalized_EigenProblem(S, 0);
+    S->DP_CheFSI = save_dp; S->lambda = save_lambda; S->useLAPACK = save_lapack; S->StandardEigenFlag = save_std;
+}
+
+/* DP_Solve_Generalized_EigenProblem_kpt (src/eigenSolverKpt.c:836-930, LAPACKE_zhegvd) */
+void ref_subspace_eig_kpt(void *h, int n, double _Complex *Hp, double _Complex *Mp, double *lambda, double _Complex *Q)
+{
+    ref_problem_t *P = (ref_problem_t *)h;
+    SPARC_OBJ *S = &P->S;
+    struct DP_CheFSI_kpt_s dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.Ns_dp = n; dp.rank_kpt = 0; dp.Hp_local = Hp; dp.Mp_local = Mp; dp.eig_vecs = Q; dp.kpt_comm = MPI_COMM_SELF;
+    void *save_dp = S->DP_CheFSI_kpt;
+    double *save_lambda = S->lambda;
+    const int save_lapack = S->useLAPACK, save_ns = S->Nstates, save_nk = S->Nkpts_kptcomm;
+    S->DP_CheFSI_kpt = &dp; S->lambda = lambda; S->useLAPACK = 1; S->Nstates = n; S->Nkpts_kptcomm = 1;
+    DP_Solve_Generalized_EigenProblem_kpt(S, 0, 0);
+    S->DP_CheFSI_kpt = save_dp; S->lambda = save_lambda; S->useLAPACK = save_lapack; S->Nstates = save_ns; S->Nkpts_kptcomm = save_nk;
+}
+
+/* CalculateDensity_psi (src/electronDensity.c:104-200) for one k-point, no spin: rho[Nd] (zeroed by the caller, as
+ * Calculate_elecDens does with calloc, :33) += occfac * kptwt * occ[n] |X_n|^2, then the 1/dV scaling (:190-196) */
+void CalculateDensity_psi(SPARC_OBJ *pSPARC, double *rho);
+void ref_density(void *h, int ncol, void *X, int is_complex, double *occ, double occfac, double kptwt, double *rho)
+{
+    ref_problem_t *P = (ref_problem_t *)h;
+    SPARC_OBJ *S = &P->S;
+    SPARC_OBJ keep = *S;
+    S->spincomm_index = 0; S->kptcomm_index = 0; S->bandcomm_index = 0; S->dmcomm = MPI_COMM_SELF;
+    S->Nstates = ncol; S->band_start_indx = 0; S->band_end_indx = ncol - 1;
+    S->Nspinor = 1; S->Nspinor_spincomm = 1; S->spinor_start_indx = 0; S->spin_typ = 0;
+    S->Nkpts_kptcomm = 1; S->Nkpts = 1; S->kptWts_loc = &kptwt; S->occfac = occfac; S->occ = occ;
+    S->isGammaPoint = !is_complex;
+    S->Xorb = (double *)X; S->Xorb_kpt = (double _Complex *)X;
+    S->npspin = 1; S->npkpt = 1; S->npband = 1; S->blacscomm = MPI_COMM_SELF;
+    CalculateDensity_psi(S, rho);
+    *S = keep;
+}
+
 /* AAR (src/linearSolver.c:38-146) with the operator pair SPARC uses: poisson_residual (lapVecRoutines.c:61) and
  * Jacobi_preconditioner; x is the start vector on entry and the solution on return */
 void ref_aar(void *h, double c, double *x, double *b, double omega, double beta, int m, int p, double tol, int max_iter)

@@ -12,4 +12,4 @@ end=$(date +%s%N)
 echo "== $name $* wall $(( (end - start) / 1000000 )) ms"
 grep -E "Free energy per atom|Total number of SCF|Total walltime" $name.out
 grep -E "Free energy per atom" $name.refout | sed 's/^/refout: /'
-tail -3 run.err
+grep -F "[chefsi_b200 shim]" run.err || tail -3 run.err

@@ -18,7 +18,7 @@ EXPORTS = (
     "chefsi_set_grid", "chefsi_set_projectors", "chefsi_set_veff", "chefsi_set_kpoint",
     "chefsi_chebyshev_filter", "chefsi_chebyshev_filter_kpt",
     "chefsi_hamiltonian_mult", "chefsi_hamiltonian_mult_kpt", "chefsi_laplacian_mult", "chefsi_laplacian_mult_kpt",
-    "chefsi_lanczos", "chefsi_lanczos_kpt", "chefsi_poisson_aar", "chefsi_subspace_reserve", "chefsi_subspace_reserve_kpt", "chefsi_subspace_project_kpt", "chefsi_subspace_rotate_kpt", "chefsi_subspace_project", "chefsi_subspace_rotate",
+    "chefsi_lanczos", "chefsi_lanczos_kpt", "chefsi_subspace_eig", "chefsi_subspace_eig_kpt", "chefsi_band_store", "chefsi_density_accumulate", "chefsi_density_accumulate_kpt", "chefsi_poisson_aar", "chefsi_subspace_reserve", "chefsi_subspace_reserve_kpt", "chefsi_subspace_project_kpt", "chefsi_subspace_rotate_kpt", "chefsi_subspace_project", "chefsi_subspace_rotate",
     "chefsi_device_ld",
     "chefsi_chebyshev_filter_device", "chefsi_chebyshev_filter_kpt_device",
     "chefsi_hamiltonian_mult_device", "chefsi_hamiltonian_mult_kpt_device",
@@ -40,6 +40,10 @@ class ChefsiStats(C.Structure):
         ("last_alpha_reduced", C.c_int),
         ("round_barrier_timeouts", C.c_uint),
         ("reserved_", C.c_int),
+        ("density_resident_blocks", C.c_uint),
+        ("density_uploaded_blocks", C.c_uint),
+        ("band_store_misses", C.c_uint),
+        ("reserved2_", C.c_uint),
     ]
 
 
@@ -83,6 +87,11 @@ def load_library() -> C.CDLL:
         getattr(lib, name).argtypes = [vp, i, d, d, dp, sz, dp, sz]
     lib.chefsi_lanczos.argtypes = [vp, dp, d, d, i, C.POINTER(C.c_double), C.POINTER(C.c_double), ip]
     lib.chefsi_lanczos_kpt.argtypes = [vp, vp, d, d, i, C.POINTER(C.c_double), C.POINTER(C.c_double), ip]
+    for name in ("chefsi_subspace_eig", "chefsi_subspace_eig_kpt"):
+        getattr(lib, name).argtypes = [vp, i, dp, dp, sz, dp, dp, sz]
+    lib.chefsi_band_store.argtypes = [vp, i]
+    for name in ("chefsi_density_accumulate", "chefsi_density_accumulate_kpt"):
+        getattr(lib, name).argtypes = [vp, dp, sz, i, dp, dp]
     lib.chefsi_poisson_aar.argtypes = [vp, d, dp, dp, d, d, i, i, d, i, ip, C.POINTER(C.c_double)]
     lib.chefsi_subspace_reserve.argtypes = [vp, i]
     lib.chefsi_subspace_reserve_kpt.argtypes = [vp, i]

@@ -167,12 +167,40 @@ class ChefsiContext:
 
     def DP_Subspace_Rotation(self, Q, X):
         """X = Y Q with the resident Y; Q given as the reference stores it: column-major ncol x ncol, i.e. the numpy
-        array Q[n, m] holds element (m, n)."""
-        ncol = Q.shape[0]
-        fn = self._lib.chefsi_subspace_rotate_kpt if _is_complex(Q) else self._lib.chefsi_subspace_rotate
-        self._check(fn(self._h, _addr(Q), Q.shape[1], ncol, _addr(X), X.shape[1]))
+        array Q[n, m] holds element (m, n).  Q = None: the eigenvectors DP_Solve_Generalized_EigenProblem left on the
+        device."""
+        fn = self._lib.chefsi_subspace_rotate_kpt if _is_complex(X) else self._lib.chefsi_subspace_rotate
+        if Q is None:
+            self._check(fn(self._h, None, 0, X.shape[0], _addr(X), X.shape[1]))
+        else:
+            self._check(fn(self._h, _addr(Q), Q.shape[1], Q.shape[0], _addr(X), X.shape[1]))
 
     DP_Subspace_Rotation_kpt = DP_Subspace_Rotation
+
+    def DP_Solve_Generalized_EigenProblem(self, ncol, Hp=None, Mp=None, is_complex=False, want_Q=True):
+        """Hp q = lambda Mp q (src/eigenSolver.c:1262, LAPACKE_dsygvd; k-point: src/eigenSolverKpt.c:836, zhegvd) on the
+        device.  Hp = Mp = None: the matrices the last DP_Project_Hamiltonian left there.  Returns (lambda, Q) with Q in
+        the reference's column-major storage (numpy Q[n, :] = eigenvector n), or (lambda, None)."""
+        if Hp is not None:
+            is_complex = _is_complex(Hp)
+        lam = np.zeros(ncol)
+        Q = np.zeros((ncol, ncol), dtype=np.complex128 if is_complex else np.float64) if want_Q else None
+        fn = self._lib.chefsi_subspace_eig_kpt if is_complex else self._lib.chefsi_subspace_eig
+        self._check(fn(self._h, int(ncol), _addr(Hp) if Hp is not None else None, _addr(Mp) if Mp is not None else None,
+                       Hp.shape[1] if Hp is not None else 0, _addr(lam), _addr(Q) if want_Q else None, ncol))
+        return lam, Q
+
+    def band_store(self, max_blocks):
+        """Keep device copies of up to max_blocks rotated blocks for CalculateDensity_psi (0: off)."""
+        self._check(self._lib.chefsi_band_store(self._h, int(max_blocks)))
+
+    def CalculateDensity_psi(self, X, g, rho):
+        """rho += sum_n g[n] |X[n]|^2 for one k-point / spin block (src/electronDensity.c:104-200, loop body)."""
+        ncol, ldx = X.shape
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        assert g.size == ncol and rho.dtype == np.float64 and rho.flags.c_contiguous
+        fn = self._lib.chefsi_density_accumulate_kpt if _is_complex(X) else self._lib.chefsi_density_accumulate
+        self._check(fn(self._h, _addr(X), ldx, ncol, _addr(g), _addr(rho)))
 
     def Lap_vec_mult(self, c, x, Lapx, a=1.0):
         """Lapx = (a Lap + c) x (src/lapVecRoutines.c:37: a = 1; no potential, no projectors)."""

@@ -119,6 +119,7 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     for (int i = 0; i < 3; i++) if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
     cudaFree(ctx->d_res_Y); cudaFree(ctx->d_res_W); cudaFree(ctx->d_res_T); cudaFree(ctx->d_gemm_ws); cudaFree(ctx->d_lanczos); cudaFree(ctx->d_aar);
     for (int i = 0; i < 3; i++) cudaFree(ctx->d_small[i]);
+    rayleigh_ritz_destroy(ctx);
     for (int i = 0; i < 12; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     cudaFree(ctx->d_sync);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -177,6 +178,8 @@ extern "C" int chefsi_set_grid(chefsi_ctx_t *ctx, const chefsi_grid_t *g)
         if (per[d] && N[d] < g->FDn) return chefsi_fail(ctx, "periodic axis %d has fewer points than the FD radius", d);
     ctx->grid = *g;
     ctx->Nd = (size_t)g->Nx * g->Ny * g->Nz;
+    band_store_clear(ctx); /* rayleigh_ritz.cu: blocks kept for the density have the old shape */
+    ctx->res_ncol = ctx->small_ncol = ctx->q_ncol = 0;
     {   /* internal layout = the reference's dense layout, ld rounded up to 16 doubles (see Layout) */
         Layout &L = ctx->lay;
         L.Nx = g->Nx; L.Ny = g->Ny; L.Nz = g->Nz;
@@ -729,6 +732,8 @@ static int filter_host(chefsi_ctx *ctx, void *X, size_t ldi, void *Y, size_t ldo
     if (ldi < ctx->Nd || ldo < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
     if (ctx->multi) return multi_filter_host(ctx, X, ldi, Y, ldo, ncol, m, a, b, a0, flags, is_complex);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    band_store_invalidate(ctx, X); /* the host blocks change: their device copies for the density are stale */
+    band_store_invalidate(ctx, Y);
     const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
     const int chunk = chunk_columns(ctx, ncol, esz);
     if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
@@ -923,6 +928,7 @@ static int subspace_reserve(chefsi_ctx *ctx, int ncol, bool is_complex)
     if (sm > ctx->small_bytes) {
         for (int i = 0; i < 3; i++) { cudaFree(ctx->d_small[i]); ctx->d_small[i] = nullptr; }
         ctx->small_bytes = 0;
+        ctx->small_ncol = ctx->q_ncol = 0;
         for (int i = 0; i < 3; i++) CHEFSI_CUDA(ctx, cudaMalloc(&ctx->d_small[i], sm));
         ctx->small_bytes = sm;
     }
@@ -938,6 +944,7 @@ static int subspace_project(chefsi_ctx *ctx, const void *Y, size_t ldy, int ncol
     if (ctx->multi) return multi_subspace_project(ctx, Y, ldy, ncol, Hp, Mp, ldp, is_complex);
     if (ncol <= 0 || ldp < (size_t)ncol || ldy < ctx->Nd) return chefsi_fail(ctx, "subspace_project: bad dimensions");
     if (subspace_reserve(ctx, ncol, is_complex)) return 1;
+    ctx->small_ncol = ctx->q_ncol = 0;
     const int words = is_complex ? 2 : 1;
     const size_t esz = sizeof(double) * words, row = ctx->Nd * esz, pitch = ctx->ld * esz;
     if (!(ctx->res_ncol == ncol && ctx->res_host == Y && ctx->res_complex == (int)is_complex)) {
@@ -980,6 +987,8 @@ static int subspace_project(chefsi_ctx *ctx, const void *Y, size_t ldy, int ncol
     CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(Hp, ldp * esz, dHp, w, w, ncol, cudaMemcpyDeviceToHost, ctx->stream));
     CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
     prof.finish();
+    ctx->small_ncol = ncol; /* Hp, Mp stay on the device for chefsi_subspace_eig (rayleigh_ritz.cu) */
+    ctx->small_complex = is_complex;
     return 0;
 }
 
@@ -999,12 +1008,15 @@ static int subspace_rotate(chefsi_ctx *ctx, const void *Q, size_t ldq, int ncol,
     if (ctx->multi) return multi_subspace_rotate(ctx, Q, ldq, ncol, X, ldx, is_complex);
     if (ctx->res_ncol != ncol || !ctx->d_res_Y || ctx->res_complex != (int)is_complex)
         return chefsi_fail(ctx, "subspace_rotate: no resident block of %d columns (call chefsi_subspace_project first)", ncol);
-    if (ldq < (size_t)ncol || ldx < ctx->Nd) return chefsi_fail(ctx, "subspace_rotate: bad dimensions");
+    if ((Q && ldq < (size_t)ncol) || ldx < ctx->Nd) return chefsi_fail(ctx, "subspace_rotate: bad dimensions");
+    if (!Q && (ctx->q_ncol != ncol || ctx->q_complex != (int)is_complex))
+        return chefsi_fail(ctx, "subspace_rotate: Q == NULL but no eigenvectors of %d columns are on the device (call chefsi_subspace_eig first)", ncol);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     const int words = is_complex ? 2 : 1;
     const size_t esz = sizeof(double) * words, w = (size_t)ncol * esz;
     double *dQ = (double *)ctx->d_small[2];
-    CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(dQ, w, Q, ldq * esz, w, ncol, cudaMemcpyHostToDevice, ctx->stream));
+    if (Q) CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(dQ, w, Q, ldq * esz, w, ncol, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->small_ncol = 0; /* the complex branch splits Q into the Hp / Mp slots */
     const size_t K = ctx->Nd * words, ldv = ctx->ld * words;
     int n;
     if (!is_complex) {
@@ -1020,20 +1032,22 @@ static int subspace_rotate(chefsi_ctx *ctx, const void *Q, size_t ldq, int ncol,
     }
     if (n < 0) return drain_streams(ctx, 1);
     ctx->stats.kernel_launches += n;
+    if (band_store_put(ctx, X, ncol, is_complex, ctx->d_res_W)) return drain_streams(ctx, 1); /* device copy for the density (rayleigh_ritz.cu) */
     CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(X, ldx * esz, ctx->d_res_W, ctx->ld * esz, ctx->Nd * esz, ncol, cudaMemcpyDeviceToHost, ctx->stream));
     CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->res_ncol = 0; /* the block has been consumed */
+    ctx->q_ncol = 0;
     return 0;
 }
 
 extern "C" int chefsi_subspace_rotate(chefsi_ctx_t *ctx, const double *Q, size_t ldq, int ncol, double *X, size_t ldx)
 {
-    if (!ctx || !Q || !X) return 1;
+    if (!ctx || !X) return 1;
     return subspace_rotate(ctx, Q, ldq, ncol, X, ldx, false);
 }
 extern "C" int chefsi_subspace_rotate_kpt(chefsi_ctx_t *ctx, const void *Q, size_t ldq, int ncol, void *X, size_t ldx)
 {
-    if (!ctx || !Q || !X) return 1;
+    if (!ctx || !X) return 1;
     return subspace_rotate(ctx, Q, ldq, ncol, X, ldx, true);
 }
 

@@ -128,6 +128,11 @@ struct chefsi_ctx {
     size_t gemm_ws_bytes = 0;
     void *d_small[3] = {nullptr, nullptr, nullptr}; /* Hp, Mp, Q (Ns x Ns) */
     size_t small_bytes = 0;
+    /* rayleigh_ritz.cu */
+    int small_ncol = 0, small_complex = 0;         /* d_small[0], d_small[1] hold Hp, Mp of the last projection (0: not) */
+    int q_ncol = 0, q_complex = 0;                 /* d_small[2] holds the eigenvectors of the last chefsi_subspace_eig */
+    struct EigState *eig = nullptr;                /* cuSOLVER handle and workspace */
+    struct BandStore *bands = nullptr;             /* device copies of the rotated blocks for the density */
     void *h_pin[3] = {nullptr, nullptr, nullptr};
     size_t h_pin_bytes = 0;
     int fast_small = 1;
@@ -208,6 +213,12 @@ int launch_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q
                    size_t ldc, int accumulate);
 int launch_rot90(chefsi_ctx *ctx, const void *in, void *out, size_t n, size_t ld, int ncol, double s);
 int launch_split_complex(chefsi_ctx *ctx, const void *Q, size_t ldq, int M, int N, double *Qr, double *Qi);
+
+/* rayleigh_ritz.cu */
+int band_store_put(chefsi_ctx *ctx, const void *host, int ncol, bool is_complex, const void *d_block);
+void band_store_invalidate(chefsi_ctx *ctx, const void *host);
+void band_store_clear(chefsi_ctx *ctx);
+void rayleigh_ritz_destroy(chefsi_ctx *ctx);
 
 /* util.cu */
 int launch_fill_random(chefsi_ctx *ctx, void *buf, int ncol, long long first_col, unsigned long long seed,

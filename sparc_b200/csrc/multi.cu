@@ -492,6 +492,7 @@ int multi_subspace_rotate(chefsi_ctx *lead, const void *Q, size_t ldq, int ncol,
     const int n = (int)ms->kids.size();
     if (ms->sub_ncol != ncol || ms->sub_complex != (int)is_complex)
         return chefsi_fail(lead, "subspace_rotate: no resident block of %d columns (call chefsi_subspace_project first)", ncol);
+    if (!Q) return chefsi_fail(lead, "subspace_rotate: a multi-device context needs the host copy of Q");
     if (ldq < (size_t)ncol || ldx < lead->Nd) return chefsi_fail(lead, "subspace_rotate: bad dimensions");
     const int words = is_complex ? 2 : 1;
     const size_t esz = sizeof(double) * words;

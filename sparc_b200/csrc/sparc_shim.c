@@ -58,7 +58,10 @@ void DP_Subspace_Rotation_ref(SPARC_OBJ *pSPARC, double *Psi_rot);
 void DP_Project_Hamiltonian_kpt_ref(SPARC_OBJ *pSPARC, int *DMVertices, double _Complex *Y, int ldi, double _Complex *HY, int ldo,
                                     double _Complex *Hp, double _Complex *Mp, int spn_i, int kpt);
 void DP_Subspace_Rotation_kpt_ref(SPARC_OBJ *pSPARC, double _Complex *Psi_rot);
+void DP_Solve_Generalized_EigenProblem_ref(SPARC_OBJ *pSPARC, int spn_i);
+void DP_Solve_Generalized_EigenProblem_kpt_ref(SPARC_OBJ *pSPARC, int kpt, int spn_i);
 #endif
+void CalculateDensity_psi_ref(SPARC_OBJ *pSPARC, double *rho);
 void Lanczos_ref(const SPARC_OBJ *pSPARC, int *DMVertices, double *Veff_loc, ATOM_NLOC_INFLUENCE_OBJ *Atom_Influence_nloc,
                  NLOC_PROJ_OBJ *nlocProj, double *eigmin, double *eigmax, double *x0, double TOL_min, double TOL_max, int MAXIT,
                  int k, int spn_i, MPI_Comm comm, MPI_Request *req_veff_loc);
@@ -88,6 +91,11 @@ static struct {
     unsigned long long n_filter, n_hmult, n_forward, n_lap, n_project, n_rotate, n_lanczos, n_lanczos_iter, n_aar, n_aar_iter;
     double t_lap, t_project, t_rotate, t_lanczos, t_aar;
     int subspace_pending;    /* the last DP_Project_Hamiltonian ran on the device: DP_Subspace_Rotation finds its block there */
+    int eig_on_device;       /* the last DP_Solve_Generalized_EigenProblem ran on the device: its eigenvectors are still there */
+    int band_store_blocks;   /* size of the device store of rotated blocks (0: not enabled yet) */
+    int rotated_on_device;   /* blocks rotated on the device since the last CalculateDensity_psi */
+    unsigned long long n_eig, n_density;
+    double t_eig, t_density;
     int multi;               /* the context owns several devices */
     double t_filter;
     double t_init, t_sync, t_hmult;  /* seconds in context creation, table/Veff synchronisation, H-apply calls */
@@ -120,6 +128,9 @@ static void shim_report(void)
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] %llu DP_Project_Hamiltonian calls %.3f s, %llu DP_Subspace_Rotation calls %.3f s on the device\n",
                 G.n_project, G.t_project, G.n_rotate, G.t_rotate);
+    if (G.verbose)
+        fprintf(stderr, "[chefsi_b200 shim] %llu subspace eigenproblems %.3f s, %llu CalculateDensity_psi calls %.3f s on the device\n",
+                G.n_eig, G.t_eig, G.n_density, G.t_density);
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] %llu Lanczos calls (%llu iterations) %.3f s with the vectors resident on the device\n",
                 G.n_lanczos, G.n_lanczos_iter, G.t_lanczos);
@@ -191,6 +202,18 @@ static void shim_init(void)
     }
     G.t_init += MPI_Wtime() - t_init0;
     if (G.verbose) fprintf(stderr, "[chefsi_b200 shim] %s on device %d of %d\n", chefsi_version(), device, ndev);
+}
+
+/* a device step that failed and is redone by the reference routine says so once per routine */
+static void shim_notice_once(const char *routine, const char *why)
+{
+    static const char *told[8];
+    for (int i = 0; i < 8; i++) {
+        if (told[i] == routine) return;
+        if (!told[i]) { told[i] = routine; break; }
+    }
+    if (!getenv("CHEFSI_B200_QUIET"))
+        fprintf(stderr, "[chefsi_b200 shim] %s: %s -- calls of this kind run the reference CPU routine\n", routine, why);
 }
 
 /* features handled natively; everything else goes to the reference routine (SURVEY.md 8b "Feature guard").
@@ -751,19 +774,70 @@ void DP_Project_Hamiltonian(SPARC_OBJ *pSPARC, int *DMVertices, double *Y, int l
     G.t_project += MPI_Wtime() - t1;
 }
 
+/* Hp q = lambda Mp q -- src/eigenSolver.c:1262-1375.  The reference calls LAPACKE_dsygvd on rank 0 (and
+ * an accelerator DSYGV in its SPARCX_ACCEL build, :1267); here the matrices DP_Project_Hamiltonian left on the device go
+ * to cuSOLVER's Dsygvd and the eigenvectors stay there for DP_Subspace_Rotation: only lambda (and a copy of Q for the
+ * host structure) comes back.  Below CHEFSI_B200_EIG_MIN_N states (default 200; measured crossover between 128 and 256,
+ * profiles/r2_eig_latency.txt) the host LAPACK call is faster than the device solver's launch sequence and the reference
+ * routine keeps the step. */
+static int shim_eig_min_n(void)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CHEFSI_B200_EIG_MIN_N");
+        v = e ? atoi(e) : 200;
+        if (getenv("CHEFSI_B200_NO_EIG")) v = 1 << 30;
+    }
+    return v;
+}
+
+void DP_Solve_Generalized_EigenProblem(SPARC_OBJ *pSPARC, int spn_i)
+{
+    DP_CheFSI_t dp = (DP_CheFSI_t)pSPARC->DP_CheFSI;
+    if (dp == NULL) return; /* eigenSolver.c:1265 */
+    G.eig_on_device = 0;
+    if (G.subspace_pending == 1 && dp->rank_kpt == 0 && !pSPARC->CyclixFlag && !pSPARC->StandardEigenFlag && dp->Ns_dp >= shim_eig_min_n()) {
+        const double t1 = MPI_Wtime();
+        const int n = dp->Ns_dp;
+        /* a multi-device context solves on its first device from the host copies the projection returned */
+        if (chefsi_subspace_eig(G.ctx, n, G.multi ? dp->Hp_local : NULL, G.multi ? dp->Mp_local : NULL, (size_t)n,
+                                pSPARC->lambda + (size_t)spn_i * n, dp->eig_vecs, (size_t)n) == 0) {
+            G.eig_on_device = !G.multi;
+            G.n_eig++;
+            G.t_eig += MPI_Wtime() - t1;
+            return;
+        }
+        shim_notice_once("DP_Solve_Generalized_EigenProblem", chefsi_last_error(G.ctx));
+    }
+    DP_Solve_Generalized_EigenProblem_ref(pSPARC, spn_i); /* the host copies of Hp, Mp are intact */
+}
+
+/* the rotated blocks of this rank (k-points x spins) stay on the device for CalculateDensity_psi */
+static void shim_band_store(const SPARC_OBJ *S)
+{
+    const int want = S->Nkpts_kptcomm * S->Nspinor_spincomm;
+    if (G.multi || getenv("CHEFSI_B200_NO_DENSITY") || want == G.band_store_blocks) return;
+    if (chefsi_band_store(G.ctx, want) == 0) G.band_store_blocks = want;
+}
+
 /* Psi_rot = Y Q -- src/eigenSolver.c:1386-1443; Q = DP_CheFSI->eig_vecs as left by DP_Solve_Generalized_EigenProblem */
 void DP_Subspace_Rotation(SPARC_OBJ *pSPARC, double *Psi_rot)
 {
     DP_CheFSI_t dp = (DP_CheFSI_t)pSPARC->DP_CheFSI;
     if (dp == NULL) return;
     if (G.subspace_pending != 1) {
+        G.eig_on_device = 0;
+        G.rotated_on_device = -1000000; /* a block was rotated on the host: this iteration's density is the reference's */
         DP_Subspace_Rotation_ref(pSPARC, Psi_rot);
         return;
     }
     const double t1 = MPI_Wtime();
-    if (chefsi_subspace_rotate(G.ctx, dp->eig_vecs, (size_t)dp->Ns_dp, dp->Ns_dp, Psi_rot, (size_t)dp->Ndsp_bp) != 0)
+    shim_band_store(pSPARC);
+    if (chefsi_subspace_rotate(G.ctx, G.eig_on_device ? NULL : dp->eig_vecs, (size_t)dp->Ns_dp, dp->Ns_dp, Psi_rot, (size_t)dp->Ndsp_bp) != 0)
         shim_fatal("chefsi_subspace_rotate");
     G.subspace_pending = 0;
+    G.eig_on_device = 0;
+    G.rotated_on_device++;
     G.n_rotate++;
     G.t_rotate += MPI_Wtime() - t1;
 }
@@ -795,22 +869,100 @@ void DP_Project_Hamiltonian_kpt(SPARC_OBJ *pSPARC, int *DMVertices, double _Comp
     G.t_project += MPI_Wtime() - t1;
 }
 
+/* k-point twin -- src/eigenSolverKpt.c:836-930 (LAPACKE_zhegvd) -> cusolverDnZhegvd */
+void DP_Solve_Generalized_EigenProblem_kpt(SPARC_OBJ *pSPARC, int kpt, int spn_i)
+{
+    DP_CheFSI_kpt_t dp = (DP_CheFSI_kpt_t)pSPARC->DP_CheFSI_kpt;
+    if (dp == NULL) return;
+    G.eig_on_device = 0;
+    if (G.subspace_pending == 2 && dp->rank_kpt == 0 && !pSPARC->CyclixFlag && dp->Ns_dp >= shim_eig_min_n()) {
+        const double t1 = MPI_Wtime();
+        const int n = dp->Ns_dp;
+        double *lam = pSPARC->lambda + (size_t)kpt * pSPARC->Nstates + (size_t)spn_i * pSPARC->Nkpts_kptcomm * pSPARC->Nstates; /* :880 */
+        if (chefsi_subspace_eig_kpt(G.ctx, n, G.multi ? dp->Hp_local : NULL, G.multi ? dp->Mp_local : NULL, (size_t)n, lam, dp->eig_vecs,
+                                    (size_t)n) == 0) {
+            G.eig_on_device = !G.multi;
+            G.n_eig++;
+            G.t_eig += MPI_Wtime() - t1;
+            return;
+        }
+        shim_notice_once("DP_Solve_Generalized_EigenProblem_kpt", chefsi_last_error(G.ctx));
+    }
+    DP_Solve_Generalized_EigenProblem_kpt_ref(pSPARC, kpt, spn_i);
+}
+
 void DP_Subspace_Rotation_kpt(SPARC_OBJ *pSPARC, double _Complex *Psi_rot)
 {
     DP_CheFSI_kpt_t dp = (DP_CheFSI_kpt_t)pSPARC->DP_CheFSI_kpt;
     if (dp == NULL) return;
     if (G.subspace_pending != 2) {
+        G.eig_on_device = 0;
+        G.rotated_on_device = -1000000;
         DP_Subspace_Rotation_kpt_ref(pSPARC, Psi_rot);
         return;
     }
     const double t1 = MPI_Wtime();
-    if (chefsi_subspace_rotate_kpt(G.ctx, dp->eig_vecs, (size_t)dp->Ns_dp, dp->Ns_dp, Psi_rot, (size_t)dp->Ndsp_bp) != 0)
+    shim_band_store(pSPARC);
+    if (chefsi_subspace_rotate_kpt(G.ctx, G.eig_on_device ? NULL : dp->eig_vecs, (size_t)dp->Ns_dp, dp->Ns_dp, Psi_rot, (size_t)dp->Ndsp_bp) != 0)
         shim_fatal("chefsi_subspace_rotate_kpt");
     G.subspace_pending = 0;
+    G.eig_on_device = 0;
+    G.rotated_on_device++;
     G.n_rotate++;
     G.t_rotate += MPI_Wtime() - t1;
 }
 #endif
+
+/* rho = sum over k-points, bands, spins of g_nk |psi_nk|^2 -- src/electronDensity.c:104-200.  Runs on the
+ * device when every block of this SCF iteration was rotated there and kept by the band store (no orbital crosses PCIe
+ * for the density: g in, Nd doubles per block out); otherwise the reference loop reads the host orbitals as before. */
+void CalculateDensity_psi(SPARC_OBJ *pSPARC, double *rho)
+{
+    if (pSPARC->spincomm_index < 0 || pSPARC->kptcomm_index < 0 || pSPARC->bandcomm_index < 0 || pSPARC->dmcomm == MPI_COMM_NULL) return; /* :106 */
+    const int Ns = pSPARC->Nstates, DMnd = pSPARC->Nd_d_dmcomm, nspinor = pSPARC->Nspinor_spincomm, nk = pSPARC->Nkpts_kptcomm;
+    const int rotated = G.rotated_on_device;
+    G.rotated_on_device = 0;
+    int ok = G.ctx && !G.multi && G.band_store_blocks == nk * nspinor && rotated >= nk * nspinor && !pSPARC->CyclixFlag &&
+             pSPARC->spin_typ <= 1 && pSPARC->Nspinor_eig == 1 && DMnd == pSPARC->Nd && pSPARC->band_start_indx == 0 &&
+             pSPARC->band_end_indx == Ns - 1;
+    if (ok) {
+        chefsi_stats_t st;
+        chefsi_get_stats(G.ctx, &st);
+        static unsigned int misses_seen;
+        if (st.band_store_misses != misses_seen) { misses_seen = st.band_store_misses; ok = 0; } /* a block did not fit: the upload would cost more than the host loop */
+    }
+    if (!ok) {
+        CalculateDensity_psi_ref(pSPARC, rho);
+        return;
+    }
+    const double t1 = MPI_Wtime();
+    double *g = (double *)malloc(sizeof(double) * (size_t)(Ns > 0 ? Ns : 1));
+    const size_t ldx = (size_t)DMnd * nspinor;
+    for (int k = 0; k < nk; k++) {
+        const double woccfac = pSPARC->occfac * (pSPARC->kptWts_loc[k] / pSPARC->Nkpts); /* :129 */
+        for (int spinor = 0; spinor < nspinor; spinor++) {
+            const int spinor_g = spinor + pSPARC->spinor_start_indx;
+            const double *occ = pSPARC->occ + (size_t)k * Ns;
+            if (pSPARC->spin_typ == 1) occ += (size_t)spinor * Ns * nk; /* :133 */
+            for (int n = 0; n < Ns; n++) g[n] = woccfac * occ[n];
+            const size_t off = (size_t)k * ldx * Ns + (size_t)spinor * DMnd;
+            const int rc = pSPARC->isGammaPoint
+                               ? chefsi_density_accumulate(G.ctx, pSPARC->Xorb + off, ldx, Ns, g, rho + (size_t)spinor_g * DMnd)
+                               : chefsi_density_accumulate_kpt(G.ctx, pSPARC->Xorb_kpt + off, ldx, Ns, g, rho + (size_t)spinor_g * DMnd);
+            if (rc != 0) shim_fatal("chefsi_density_accumulate");
+        }
+    }
+    free(g);
+    const int Nspinor = pSPARC->Nspinor;
+    /* the reductions over the other process groups, as in the reference (:161-181); no-ops at one rank */
+    if (pSPARC->npspin > 1) MPI_Allreduce(MPI_IN_PLACE, rho, Nspinor * DMnd, MPI_DOUBLE, MPI_SUM, pSPARC->spin_bridge_comm);
+    if (pSPARC->npkpt > 1) MPI_Allreduce(MPI_IN_PLACE, rho, Nspinor * DMnd, MPI_DOUBLE, MPI_SUM, pSPARC->kpt_bridge_comm);
+    if (pSPARC->npband) MPI_Allreduce(MPI_IN_PLACE, rho, Nspinor * DMnd, MPI_DOUBLE, MPI_SUM, pSPARC->blacscomm);
+    const double vscal = 1.0 / pSPARC->dV; /* :190-196 */
+    for (int i = 0; i < Nspinor * DMnd; i++) rho[i] *= vscal;
+    G.n_density++;
+    G.t_density += MPI_Wtime() - t1;
+}
 
 /* Extreme eigenvalues of H for the Chebyshev bounds -- src/eigenSolver.c:1920-2129.  One rank, real data,
  * single-device context: the whole iteration runs on the device (chefsi_lanczos); anything else, and the degenerate

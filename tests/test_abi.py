@@ -32,7 +32,7 @@ def test_struct_layout_matches_header():
     from sparc_b200.problem import CHEFSI_MAX_FDN, ChefsiGridC, ChefsiNlocC
     assert C.sizeof(ChefsiGridC) == 8 * 4 + 8 * 4 + 15 * 8 * (CHEFSI_MAX_FDN + 1)
     assert C.sizeof(ChefsiNlocC) == 11 * 8
-    assert C.sizeof(capi.ChefsiStats) == 8 + 3 * 8 + 6 * 4
+    assert C.sizeof(capi.ChefsiStats) == 8 + 3 * 8 + 10 * 4
 
 
 def test_no_cpu_fallback():

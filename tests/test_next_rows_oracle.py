@@ -52,3 +52,39 @@ def test_aar_restatement_vs_reference(port, ref_cls, cell_typ, BC, c):
     assert np.linalg.norm(x - x_r) <= 1e-6 * np.linalg.norm(x_r)
     r = b + port.lap_plus_diag(g, 1.0, 0.0, c, None, x_r[None, :].copy())[0]
     assert np.linalg.norm(r) <= 1.0001e-8 * np.linalg.norm(b)     # the reference's solution meets its own tolerance
+
+
+def _rand_pencil(n, complex_, seed=5):
+    """A Hermitian Hp and a Hermitian positive definite Mp (column-major storage: numpy [n, m] = element (m, n))."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if complex_ else 0)
+    Bm = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if complex_ else 0)
+    Hp = (A + A.conj().T) / 2
+    Mp = Bm @ Bm.conj().T / n + np.eye(n)
+    return np.ascontiguousarray(Hp.T), np.ascontiguousarray(Mp.T)
+
+
+@pytest.mark.parametrize("n,complex_", [(9, False), (30, False), (9, True), (40, True)])
+def test_subspace_eig_restatement_vs_reference(ref_cls, n, complex_):
+    """next_rows.subspace_eig against the reference's own DP_Solve_Generalized_EigenProblem[_kpt]: eigenvalues equal,
+    eigenvectors equal up to a sign / phase per vector."""
+    g, veff, proj, _ = small_case(0, (0, 0, 0), ncol=1)
+    ref = ref_cls(g, proj, veff)
+    Hp, Mp = _rand_pencil(n, complex_)
+    lam_r, Q_r = ref.subspace_eig(Hp, Mp)
+    lam, Q = next_rows.subspace_eig(Hp, Mp)
+    assert np.abs(lam - lam_r).max() < 1e-12 * np.abs(lam_r).max()
+    M = Mp.T
+    ov = np.einsum("ni,ij,nj->n", Q_r.conj(), M, Q)           # q_r^H Mp q per vector: unit modulus
+    assert np.abs(np.abs(ov) - 1).max() < 1e-10
+    assert np.abs(Q - Q_r * ov[:, None]).max() < 1e-9
+
+
+@pytest.mark.parametrize("complex_", [False, True])
+def test_density_restatement_vs_reference(ref_cls, complex_):
+    g, veff, proj, x = small_case(0, (0, 0, 0), ncol=7, complex_=complex_)
+    ref = ref_cls(g, proj, veff)
+    occ = np.random.default_rng(1).uniform(0, 1, 7)
+    rho_r = ref.density(x, occ, occfac=2.0, kptwt=0.25)
+    rho = next_rows.density(x, 2.0 * 0.25 * occ) / g.dV
+    assert np.abs(rho - rho_r).max() <= 1e-14 * np.abs(rho_r).max()

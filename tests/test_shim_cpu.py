@@ -1,5 +1,6 @@
 """The reference-side binding on a CPU-only box: with CHEFSI_B200_DISABLE=1 every replaced routine
-(ChebyshevFiltering, Hamiltonian_vectors_mult, Lap_vec_mult, AAR, Lanczos[_kpt], DP_Project_Hamiltonian, DP_Subspace_Rotation)
+(ChebyshevFiltering, Hamiltonian_vectors_mult, Lap_vec_mult, AAR, Lanczos[_kpt], DP_Project_Hamiltonian, DP_Subspace_Rotation,
+DP_Solve_Generalized_EigenProblem, CalculateDensity_psi)
 forwards to the reference's own definition kept in the executable as *_ref, no CUDA context is created, and the SCF
 energy of tests/Si8 is the reference's.  Checks the link-time substitution (integration/Makefile) without a GPU.
 Skipped where integration/_build is absent (it is derived from /root/reference)."""
@@ -21,7 +22,8 @@ def test_every_replaced_symbol_has_a_ref_twin():
     syms = subprocess.run(["nm", EXE], capture_output=True, text=True).stdout
     for name in ("ChebyshevFiltering", "ChebyshevFiltering_kpt", "Hamiltonian_vectors_mult", "Hamiltonian_vectors_mult_kpt",
                  "Lap_vec_mult", "AAR", "Lanczos", "Lanczos_kpt", "DP_Project_Hamiltonian", "DP_Subspace_Rotation",
-                 "DP_Project_Hamiltonian_kpt", "DP_Subspace_Rotation_kpt"):
+                 "DP_Project_Hamiltonian_kpt", "DP_Subspace_Rotation_kpt", "DP_Solve_Generalized_EigenProblem",
+                 "DP_Solve_Generalized_EigenProblem_kpt", "CalculateDensity_psi"):
         assert re.search(rf" T {name}$", syms, re.M), name
         assert re.search(rf" T {name}_ref$", syms, re.M), name + "_ref"
 

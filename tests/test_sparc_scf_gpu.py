@@ -77,3 +77,18 @@ def test_scf_on_a_multi_device_context(tmp_path):
     m = re.search(r"(\d+) ChebyshevFiltering calls .*?(\d+) Hamiltonian_vectors_mult calls, (\d+) calls forwarded", log)
     assert m and int(m.group(1)) > 0 and int(m.group(3)) == 0
     assert abs(e - e_ref) <= TOL_HA_PER_ATOM
+
+
+@pytest.mark.parametrize("name", ["Si8", "Si8_kpt", "O2_spin_coarse"])
+def test_scf_with_the_whole_rayleigh_ritz_step_on_the_device(name, tmp_path):
+    """with CHEFSI_B200_EIG_MIN_N=1 the subspace eigenproblem of these small systems (9-30 states; by
+    default below the size where the device solver pays) also runs on the device: projection -> eigenproblem -> rotation
+    -> density with Hp, Mp, Q and the rotated orbitals staying there.  Eigenvectors differ from LAPACK's by signs /
+    phases; the energy must not."""
+    e, e_ref, log, out = run_case(name, tmp_path, {"CHEFSI_B200_EIG_MIN_N": "1"})
+    m = re.search(r"(\d+) subspace eigenproblems [0-9.]+ s, (\d+) CalculateDensity_psi calls", log)
+    assert m, log[-1500:]
+    n_eig, n_dens = int(m.group(1)), int(m.group(2))
+    print(f"{name}: E = {e:.10f} Ha/atom, refout {e_ref:.10f}, diff {e - e_ref:+.2e}; {n_eig} eigenproblems, {n_dens} densities on the device")
+    assert n_eig > 0 and n_dens > 0
+    assert abs(e - e_ref) <= TOL_HA_PER_ATOM
