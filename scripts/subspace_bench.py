@@ -6,7 +6,8 @@ import torch
 from sparc_b200 import problem as P
 from sparc_b200.chefsi import ChefsiContext
 
-for n, ncol in ((96, 512), (128, 256), (64, 1024)):
+CASES = [(int(sys.argv[1]), int(sys.argv[2]))] if len(sys.argv) > 2 else [(96, 512), (128, 256), (64, 1024)]
+for n, ncol in CASES:
     L = 45.9 * n / 160.0
     g = P.make_grid((n, n, n), (L, L, L))
     ctx = ChefsiContext(0)

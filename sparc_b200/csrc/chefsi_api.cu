@@ -89,6 +89,8 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
     if (getenv("CHEFSI_B200_GRIDSYNC")) ctx->stream_gridsync = atoi(getenv("CHEFSI_B200_GRIDSYNC"));
     if (getenv("CHEFSI_B200_ALPHA_REDUCE_MIN")) ctx->alpha_reduce_min = atoi(getenv("CHEFSI_B200_ALPHA_REDUCE_MIN"));
     if (getenv("CHEFSI_B200_FAST_SMALL")) ctx->fast_small = atoi(getenv("CHEFSI_B200_FAST_SMALL"));
+    if (getenv("CHEFSI_B200_GEMM_BIG_TILES")) ctx->gemm_big_tiles = atoi(getenv("CHEFSI_B200_GEMM_BIG_TILES"));
+    if (getenv("CHEFSI_B200_GEMM_SYMMETRIC")) ctx->gemm_symmetric = atoi(getenv("CHEFSI_B200_GEMM_SYMMETRIC"));
     if (getenv("CHEFSI_B200_SMALL_BRICK")) ctx->small_brick = atoi(getenv("CHEFSI_B200_SMALL_BRICK"));
     if (getenv("CHEFSI_B200_TMA_L2PROMO")) ctx->tma_l2promo = atoi(getenv("CHEFSI_B200_TMA_L2PROMO")) & 3;
     *out = ctx;
@@ -969,16 +971,16 @@ static int subspace_project(chefsi_ctx *ctx, const void *Y, size_t ldy, int ncol
     double *dHp = (double *)ctx->d_small[0], *dMp = (double *)ctx->d_small[1];
     const double *Yv = (const double *)ctx->d_res_Y, *Wv = (const double *)ctx->d_res_W;
     const size_t K = ctx->Nd * words, ldv = ctx->ld * words; /* real view of the columns */
-    int n = launch_gemm_tn(ctx, Yv, ldv, Yv, ldv, ncol, ncol, K, 1.0, dMp, ncol, words);
-    if (n >= 0) { ctx->stats.kernel_launches += n; n = launch_gemm_tn(ctx, Yv, ldv, Wv, ldv, ncol, ncol, K, 1.0, dHp, ncol, words); }
+    int n = launch_gemm_tn(ctx, Yv, ldv, Yv, ldv, ncol, ncol, K, 1.0, dMp, ncol, words, +1);
+    if (n >= 0) { ctx->stats.kernel_launches += n; n = launch_gemm_tn(ctx, Yv, ldv, Wv, ldv, ncol, ncol, K, 1.0, dHp, ncol, words, +1); }
     if (n >= 0 && is_complex) {
         /* imaginary parts: Im(A^H B) = A_view^T (-i B)_view */
         ctx->stats.kernel_launches += n;
         const double *Tv = (const double *)ctx->d_res_T;
         n = launch_rot90(ctx, ctx->d_res_Y, ctx->d_res_T, ctx->Nd, ctx->ld, ncol, -1.0);
-        if (n >= 0) n = launch_gemm_tn(ctx, Yv, ldv, Tv, ldv, ncol, ncol, K, 1.0, dMp + 1, ncol, 2);
+        if (n >= 0) n = launch_gemm_tn(ctx, Yv, ldv, Tv, ldv, ncol, ncol, K, 1.0, dMp + 1, ncol, 2, -1);
         if (n >= 0) n = launch_rot90(ctx, ctx->d_res_W, ctx->d_res_T, ctx->Nd, ctx->ld, ncol, -1.0);
-        if (n >= 0) n = launch_gemm_tn(ctx, Yv, ldv, Tv, ldv, ncol, ncol, K, 1.0, dHp + 1, ncol, 2);
+        if (n >= 0) n = launch_gemm_tn(ctx, Yv, ldv, Tv, ldv, ncol, ncol, K, 1.0, dHp + 1, ncol, 2, -1);
         if (n >= 0) ctx->stats.kernel_launches += 6;
     }
     if (n < 0) return drain_streams(ctx, 1);

@@ -135,6 +135,8 @@ struct chefsi_ctx {
     struct BandStore *bands = nullptr;             /* device copies of the rotated blocks for the density */
     void *h_pin[3] = {nullptr, nullptr, nullptr};
     size_t h_pin_bytes = 0;
+    int gemm_big_tiles = 1;                        /* subspace.cu: 128 x 128 CTA tiles for more than 64 columns (0: 64 x 64 everywhere) */
+    int gemm_symmetric = 1;                        /* Y^T Y and Y^T H Y: upper-triangle tiles only, mirrored */
     int fast_small = 1;
     int small_brick = 1;                           /* launches with very few z-marching CTAs take the 3-D brick kernel */
     void *d_alpha[2] = {nullptr, nullptr}; /* per-image alpha partials: [cur] belongs to the current input */
@@ -208,7 +210,7 @@ void chefsi_free_nloc(NlocDev &d);
 
 /* subspace.cu */
 int launch_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B, size_t ldb, int M, int N, size_t K, double scale,
-                   double *C, size_t ldc, int cstride);
+                   double *C, size_t ldc, int cstride, int sym = 0);
 int launch_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q, size_t ldq, size_t K, int M, int N, double *C,
                    size_t ldc, int accumulate);
 int launch_rot90(chefsi_ctx *ctx, const void *in, void *out, size_t n, size_t ld, int ncol, double s);

@@ -34,6 +34,10 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -43,39 +47,54 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-constexpr int KC = 32;         /* depth of a staged operand chunk */
-constexpr int PITCH = KC + 4;  /* 36 doubles: 4 mod 16 -> the 8 x 4 fragment reads of a half warp hit 16 distinct banks pairs */
-constexpr int NSTG = 3;
+constexpr int NWARP_M = 2, NWARP_N = 4; /* gemm_tn: 8 warps as 2 (m) x 4 (n) */
 
 /* ---- C = A^T B --------------------------------------------------------------------------------------------- */
-/* grid: (tiles_m * tiles_n, nslab); block 256 threads = 8 warps as 2 (m) x 4 (n): warp tile 32 x 16 */
+/* grid: (tiles_m * tiles_n, nslab); block 256 threads = 8 warps as 2 (m) x 4 (n).  FM x FN 8 x 8 fragments per warp:
+ *   <4, 2, 32, 3>:  64 x  64 CTA tile, 32-deep chunks, 3 stages (110 KB, 2 CTAs per SM)   -- up to 64 columns
+ *   <8, 4, 16, 4>: 128 x 128 CTA tile, 16-deep chunks, 4 stages (164 KB, 1 CTA per SM)    -- half the L2 -> SM bytes per
+ *                  FMA and 32 independent DMMA chains per warp between two shared-memory fragment loads
+ * PITCH = KCH + 4 doubles (4 mod 16): the 8 x 4 fragment reads of a warp hit 32 distinct banks. */
+template <int FM, int FN, int KCH, int STG>
 __global__ void __launch_bounds__(256)
 gemm_tn_kernel(const double *__restrict__ A, size_t lda, const double *__restrict__ B, size_t ldb, int M, int N, size_t K,
-               size_t kslab, int tiles_m, double *__restrict__ part /* [nslab][tiles][64*64] */)
+               size_t kslab, int tiles_m, int upper, double *__restrict__ part /* [nslab][tiles][TM*TN] */)
 {
+    constexpr int TM = NWARP_M * 8 * FM, TN = NWARP_N * 8 * FN, PITCH = KCH + 4, QCH = KCH / 2 /* 16-byte chunks per column */;
+    constexpr int COPIES = (TM + TN) * QCH / 256;
+    static_assert((TM + TN) * QCH % 256 == 0, "copy loop");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sA = reinterpret_cast<double *>(smem_raw);            /* [NSTG][64][PITCH]: column m, k contiguous */
-    double *sB = sA + NSTG * 64 * PITCH;
-    const int tile = blockIdx.x, tm = tile % tiles_m, tn = tile / tiles_m;
-    const int m0 = tm * 64, n0 = tn * 64;
+    double *sA = reinterpret_cast<double *>(smem_raw);            /* [STG][TM][PITCH]: column m, k contiguous */
+    double *sB = sA + STG * TM * PITCH;                           /* [STG][TN][PITCH] */
+    const int tile = blockIdx.x;
+    int tm, tn;
+    if (upper) { /* tiles of the upper triangle only, column by column: column tn holds tm = 0..tn */
+        tn = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+        while ((tn + 1) * (tn + 2) / 2 <= tile) tn++;
+        while (tn * (tn + 1) / 2 > tile) tn--;
+        tm = tile - tn * (tn + 1) / 2;
+    } else {
+        tm = tile % tiles_m;
+        tn = tile / tiles_m;
+    }
+    const int m0 = tm * TM, n0 = tn * TN;
     const size_t k_begin = (size_t)blockIdx.y * kslab;
     const size_t k_end = (k_begin + kslab < K) ? k_begin + kslab : K;
-    const int nchunks = (k_end > k_begin) ? (int)((k_end - k_begin + KC - 1) / KC) : 0;
+    const int nchunks = (k_end > k_begin) ? (int)((k_end - k_begin + KCH - 1) / KCH) : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+    const int wm = (warp % NWARP_M) * 8 * FM, wn = (warp / NWARP_M) * 8 * FN;
 
     auto issue = [&](int c, int buf) {
-        const size_t k0 = k_begin + (size_t)c * KC;
-        /* 128 columns (64 of A, 64 of B) x 16 chunks of 16 bytes = 2048 copies / 256 threads */
+        const size_t k0 = k_begin + (size_t)c * KCH;
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
+        for (int t = 0; t < COPIES; t++) {
             const int idx = tid + t * 256;
-            const int col = idx >> 4, q = idx & 15;        /* column 0..127, 16-byte chunk 0..15 */
-            const bool isB = col >= 64;
-            const int cc = isB ? col - 64 : col;
+            const int col = idx / QCH, q = idx % QCH;       /* column 0..TM+TN-1, 16-byte chunk */
+            const bool isB = col >= TM;
+            const int cc = isB ? col - TM : col;
             const int gcol = (isB ? n0 : m0) + cc;
             const size_t k = k0 + 2 * q;
-            double *dst = (isB ? sB : sA) + ((size_t)buf * 64 + cc) * PITCH + 2 * q;
+            double *dst = (isB ? sB + ((size_t)buf * TN + cc) * PITCH : sA + ((size_t)buf * TM + cc) * PITCH) + 2 * q;
             const bool colok = gcol < (isB ? N : M);
             if (colok && k + 1 < k_end) {
                 cp_async16(dst, (isB ? B + (size_t)gcol * ldb : A + (size_t)gcol * lda) + k);
@@ -87,92 +106,109 @@ gemm_tn_kernel(const double *__restrict__ A, size_t lda, const double *__restric
         }
     };
 
-    double acc[4][2][2];
+    double acc[FM][FN][2];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < FM; i++)
 #pragma unroll
-        for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
-    for (int s = 0; s < NSTG - 1; s++) {
+    for (int s = 0; s < STG - 1; s++) {
         if (s < nchunks) issue(s, s);
         cp_async_commit();
     }
     for (int c = 0; c < nchunks; c++) {
-        const int buf = c % NSTG;
-        cp_async_wait<NSTG - 2>();
+        const int buf = c % STG;
+        cp_async_wait<STG - 2>();
         __syncthreads();
-        if (c + NSTG - 1 < nchunks) issue(c + NSTG - 1, (c + NSTG - 1) % NSTG);
+        if (c + STG - 1 < nchunks) issue(c + STG - 1, (c + STG - 1) % STG);
         cp_async_commit();
-        const double *a_base = sA + ((size_t)buf * 64 + wm + (lane >> 2)) * PITCH + (lane & 3);
-        const double *b_base = sB + ((size_t)buf * 64 + wn + (lane >> 2)) * PITCH + (lane & 3);
+        const double *a_base = sA + ((size_t)buf * TM + wm + (lane >> 2)) * PITCH + (lane & 3);
+        const double *b_base = sB + ((size_t)buf * TN + wn + (lane >> 2)) * PITCH + (lane & 3);
 #pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-            double af[4], bf[2];
+        for (int kk = 0; kk < KCH; kk += 4) {
+            double af[FM], bf[FN];
 #pragma unroll
-            for (int i = 0; i < 4; i++) af[i] = a_base[(size_t)i * 8 * PITCH + kk];
+            for (int i = 0; i < FM; i++) af[i] = a_base[(size_t)i * 8 * PITCH + kk];
 #pragma unroll
-            for (int j = 0; j < 2; j++) bf[j] = b_base[(size_t)j * 8 * PITCH + kk];
+            for (int j = 0; j < FN; j++) bf[j] = b_base[(size_t)j * 8 * PITCH + kk];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int i = 0; i < FM; i++)
 #pragma unroll
-                for (int j = 0; j < 2; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < FN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     cp_async_wait<0>();
-    /* partial tile of this slab, column-major 64 x 64 */
-    double *out = part + ((size_t)blockIdx.y * gridDim.x + tile) * 4096;
+    /* partial tile of this slab, column-major TM x TN */
+    double *out = part + ((size_t)blockIdx.y * gridDim.x + tile) * (TM * TN);
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < FM; i++)
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
+        for (int j = 0; j < FN; j++) {
             const int r = wm + i * 8 + (lane >> 2), cc = wn + j * 8 + 2 * (lane & 3);
-            out[(size_t)cc * 64 + r] = acc[i][j][0];
-            out[(size_t)(cc + 1) * 64 + r] = acc[i][j][1];
+            out[(size_t)cc * TM + r] = acc[i][j][0];
+            out[(size_t)(cc + 1) * TM + r] = acc[i][j][1];
         }
 }
 
-/* C[m + n ldc] = scale * sum over slabs (fixed order) of the partial tiles */
-__global__ void gemm_tn_reduce_kernel(const double *__restrict__ part, int nslab, int ntiles, int tiles_m, int M, int N, double scale,
-                                      double *__restrict__ C, size_t ldc, int cstride)
+/* C[m + n ldc] = scale * sum over slabs (fixed order) of the partial T x T tiles.  sym != 0: the tiles are those of the
+ * upper triangle; every element with m <= n is written to (m, n) and, times sym, to (n, m) (sym = +1: symmetric product,
+ * -1: the antisymmetric imaginary part of a Hermitian one) */
+__global__ void gemm_tn_reduce_kernel(const double *__restrict__ part, int nslab, int ntiles, int tiles_m, int T, int M, int N, double scale,
+                                      double *__restrict__ C, size_t ldc, int cstride, int sym)
 {
-    const size_t total = (size_t)ntiles * 4096;
+    const size_t tsz = (size_t)T * T, total = (size_t)ntiles * tsz;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int tile = (int)(e / 4096), r = (int)(e % 64), c = (int)((e / 64) % 64);
-        const int m = (tile % tiles_m) * 64 + r, n = (tile / tiles_m) * 64 + c;
-        if (m >= M || n >= N) continue;
+        const int tile = (int)(e / tsz), r = (int)(e % T), c = (int)((e / T) % T);
+        int tm, tn;
+        if (sym) {
+            tn = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+            while ((tn + 1) * (tn + 2) / 2 <= tile) tn++;
+            while (tn * (tn + 1) / 2 > tile) tn--;
+            tm = tile - tn * (tn + 1) / 2;
+        } else {
+            tm = tile % tiles_m;
+            tn = tile / tiles_m;
+        }
+        const int m = tm * T + r, n = tn * T + c;
+        if (m >= M || n >= N || (sym && m > n)) continue;
         double s = 0.0;
         for (int sl = 0; sl < nslab; sl++) s += part[(size_t)sl * total + e];
         C[((size_t)n * ldc + m) * cstride] = scale * s;
+        if (sym && m < n) C[((size_t)m * ldc + n) * cstride] = sym * scale * s;
     }
 }
 
 /* ---- C = A Q ----------------------------------------------------------------------------------------------- */
 constexpr int RT = 128;          /* rows per CTA tile */
 constexpr int RPITCH = RT + 4;   /* 132 = 4 mod 16 */
-/* grid: (row tiles, column tiles of 64); block 256 = 8 warps as 4 (rows) x 2 (cols): warp tile 32 rows x 32 columns */
+/* 1-D grid, column tile fastest (the CTAs that share a row tile of A run together: A comes from DRAM once, then from
+ * L2); block 256 = 8 warps as 4 (rows) x 2 (cols); warp tile 32 rows x 8 FNN columns:
+ *   <4, 32, 3>: 128 x  64 CTA tile (up to 64 columns)      <8, 16, 4>: 128 x 128 CTA tile */
+template <int FNN, int KCH, int STG>
 __global__ void __launch_bounds__(256)
-gemm_nn_kernel(const double *__restrict__ A, size_t lda, const double *__restrict__ Qm, size_t ldq, size_t K, int M, int N,
+gemm_nn_kernel(const double *__restrict__ A, size_t lda, const double *__restrict__ Qm, size_t ldq, size_t K, int M, int N, int tiles_n,
                double *__restrict__ C, size_t ldc, int accumulate)
 {
+    constexpr int CT = 2 * 8 * FNN, PITCH = KCH + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sA = reinterpret_cast<double *>(smem_raw);   /* [NSTG][KC (m)][RPITCH]: column m of A, rows contiguous */
-    double *sQ = sA + NSTG * KC * RPITCH;                /* [NSTG][64 (n)][PITCH]: column n of Q, m contiguous */
-    const size_t r0 = (size_t)blockIdx.x * RT;
-    const int n0 = blockIdx.y * 64;
+    double *sA = reinterpret_cast<double *>(smem_raw);   /* [STG][KCH (m)][RPITCH]: column m of A, rows contiguous */
+    double *sQ = sA + STG * KCH * RPITCH;                /* [STG][CT (n)][PITCH]: column n of Q, m contiguous */
+    const size_t r0 = (size_t)(blockIdx.x / tiles_n) * RT;
+    const int n0 = (int)(blockIdx.x % tiles_n) * CT;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wr = (warp & 3) * 32, wn = (warp >> 2) * 32;
-    const int nchunks = (M + KC - 1) / KC;
+    const int wr = (warp & 3) * 32, wn = (warp >> 2) * 8 * FNN;
+    const int nchunks = (M + KCH - 1) / KCH;
 
     auto issue = [&](int c, int buf) {
-        const int mc0 = c * KC;
-        /* A chunk: 32 columns x 128 rows = 32 x 64 16-byte chunks = 2048 copies */
+        const int mc0 = c * KCH;
+        /* A chunk: KCH columns x 128 rows = KCH x 64 16-byte chunks */
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
+        for (int t = 0; t < KCH / 4; t++) {
             const int idx = tid + t * 256;
             const int mcol = idx >> 6, q = idx & 63;
             const size_t r = r0 + 2 * q;
-            double *dst = sA + ((size_t)buf * KC + mcol) * RPITCH + 2 * q;
+            double *dst = sA + ((size_t)buf * KCH + mcol) * RPITCH + 2 * q;
             const int gm = mc0 + mcol;
             if (gm < M && r + 1 < K) cp_async16(dst, A + (size_t)gm * lda + r);
             else {
@@ -180,54 +216,56 @@ gemm_nn_kernel(const double *__restrict__ A, size_t lda, const double *__restric
                 dst[1] = 0.0;
             }
         }
-        /* Q chunk: 64 columns (n) x 32 (m): 64 x 16 chunks = 1024 copies; element alignment of Q is only 8 bytes in general */
+        /* Q chunk: CT columns (n) x KCH (m); a column of Q is only 8-byte aligned in general: 8-byte copies */
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
+        for (int t = 0; t < CT * KCH / 256; t++) {
             const int idx = tid + t * 256;
-            const int ncol = idx >> 5, mm = idx & 31;
+            const int ncol = idx / KCH, mm = idx % KCH;
             const int gn = n0 + ncol, gm = mc0 + mm;
-            sQ[((size_t)buf * 64 + ncol) * PITCH + mm] = (gn < N && gm < M) ? Qm[(size_t)gn * ldq + gm] : 0.0;
+            double *dst = sQ + ((size_t)buf * CT + ncol) * PITCH + mm;
+            if (gn < N && gm < M) cp_async8(dst, Qm + (size_t)gn * ldq + gm);
+            else *dst = 0.0;
         }
     };
 
-    double acc[4][4][2];
+    double acc[4][FNN][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < FNN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
-    for (int s = 0; s < NSTG - 1; s++) {
+    for (int s = 0; s < STG - 1; s++) {
         if (s < nchunks) issue(s, s);
         cp_async_commit();
     }
     for (int c = 0; c < nchunks; c++) {
-        const int buf = c % NSTG;
-        cp_async_wait<NSTG - 2>();
+        const int buf = c % STG;
+        cp_async_wait<STG - 2>();
         __syncthreads();
-        if (c + NSTG - 1 < nchunks) issue(c + NSTG - 1, (c + NSTG - 1) % NSTG);
+        if (c + STG - 1 < nchunks) issue(c + STG - 1, (c + STG - 1) % STG);
         cp_async_commit();
         /* a = A[row = lane/4][m = lane%4] -> sA[m][row]; b = Q[m = lane%4][n = lane/4] -> sQ[n][m] */
-        const double *a_base = sA + ((size_t)buf * KC + (lane & 3)) * RPITCH + wr + (lane >> 2);
-        const double *b_base = sQ + ((size_t)buf * 64 + wn + (lane >> 2)) * PITCH + (lane & 3);
+        const double *a_base = sA + ((size_t)buf * KCH + (lane & 3)) * RPITCH + wr + (lane >> 2);
+        const double *b_base = sQ + ((size_t)buf * CT + wn + (lane >> 2)) * PITCH + (lane & 3);
 #pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-            double af[4], bf[4];
+        for (int kk = 0; kk < KCH; kk += 4) {
+            double af[4], bf[FNN];
 #pragma unroll
             for (int i = 0; i < 4; i++) af[i] = a_base[(size_t)kk * RPITCH + i * 8];
 #pragma unroll
-            for (int j = 0; j < 4; j++) bf[j] = b_base[(size_t)j * 8 * PITCH + kk];
+            for (int j = 0; j < FNN; j++) bf[j] = b_base[(size_t)j * 8 * PITCH + kk];
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < FNN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     cp_async_wait<0>();
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < FNN; j++) {
             const size_t r = r0 + wr + i * 8 + (lane >> 2);
             const int cc = n0 + wn + j * 8 + 2 * (lane & 3);
             if (r < K) {
@@ -273,45 +311,81 @@ int ensure_bytes(chefsi_ctx *ctx, void **p, size_t *have, size_t need)
 
 }  // namespace
 
-/* C(M x N, ld ldc, device) = scale * A^T B with A: K x M (lda), B: K x N (ldb), all device, column-major */
-int launch_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B, size_t ldb, int M, int N, size_t K, double scale,
-                   double *C, size_t ldc, int cstride)
+template <int FM, int FN, int KCH, int STG>
+static int run_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B, size_t ldb, int M, int N, size_t K, double scale,
+                       double *C, size_t ldc, int cstride, int sym, int ctas_per_sm)
 {
-    const int tiles_m = (M + 63) / 64, tiles_n = (N + 63) / 64, ntiles = tiles_m * tiles_n;
-    /* slabs: enough CTAs to fill the GPU twice, at least 8 chunks per slab */
-    size_t nslab = (size_t)std::max(1, (2 * ctx->num_sms + ntiles - 1) / ntiles);
-    const size_t max_slab = (K + 8 * KC - 1) / (8 * KC);
-    if (nslab > max_slab) nslab = max_slab ? max_slab : 1;
+    constexpr int T = NWARP_M * 8 * FM;
+    static_assert(T == NWARP_N * 8 * FN, "square CTA tiles");
+    if (sym && M != N) { chefsi_fail(ctx, "gemm_tn: a symmetric product needs M == N"); return -1; }
+    const int tiles_m = (M + T - 1) / T, tiles_n = (N + T - 1) / T, ntiles = sym ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
+    /* split K into slabs over CTAs (tall-skinny operands give a few tiles only): at least two waves of CTAs, and among
+       the slab counts of the next wave the one that fills whole waves best -- a tail wave of a few CTAs costs a full
+       slab time (Ns = 512, 128 x 128 tiles: 16 tiles x 19 slabs = 2.05 waves would run at 68 %) */
+    const size_t wave = (size_t)ctx->num_sms * ctas_per_sm;
+    const size_t max_slab = std::max<size_t>(1, (K + 8 * KCH - 1) / (8 * KCH)); /* at least 8 chunks per slab */
+    const size_t lo = std::max<size_t>(1, (2 * wave + ntiles - 1) / ntiles), hi = lo + (wave + ntiles - 1) / ntiles + 1;
+    size_t nslab = std::min(lo, max_slab);
+    double best = -1.0;
+    for (size_t cand = lo; cand <= hi && cand <= max_slab; cand++) {
+        const size_t ctas = cand * ntiles, waves = (ctas + wave - 1) / wave;
+        const double eff = (double)ctas / (double)(waves * wave);
+        if (eff > best + 1e-9) { best = eff; nslab = cand; }
+    }
     if (nslab > 65535) nslab = 65535;
     size_t kslab = (K + nslab - 1) / nslab;
-    kslab = (kslab + KC - 1) / KC * KC;                 /* slabs start on even element offsets */
+    kslab = (kslab + KCH - 1) / KCH * KCH;                 /* slabs start on even element offsets */
     nslab = (K + kslab - 1) / kslab;
-    if (ensure_bytes(ctx, &ctx->d_gemm_ws, &ctx->gemm_ws_bytes, nslab * ntiles * 4096 * sizeof(double))) return -1;
-    const size_t smem = (size_t)2 * NSTG * 64 * PITCH * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ensure_bytes(ctx, &ctx->d_gemm_ws, &ctx->gemm_ws_bytes, nslab * ntiles * T * T * sizeof(double))) return -1;
+    const size_t smem = (size_t)2 * STG * T * (KCH + 4) * sizeof(double);
+    auto kern = gemm_tn_kernel<FM, FN, KCH, STG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(gemm_tn): %s", cudaGetErrorString(e)); return -1; }
-    gemm_tn_kernel<<<dim3((unsigned)ntiles, (unsigned)nslab), 256, smem, ctx->stream>>>(A, lda, B, ldb, M, N, K, kslab, tiles_m,
-                                                                                          (double *)ctx->d_gemm_ws);
-    gemm_tn_reduce_kernel<<<std::min(4 * ctx->num_sms, (ntiles * 4096 + 255) / 256), 256, 0, ctx->stream>>>(
-        (const double *)ctx->d_gemm_ws, (int)nslab, ntiles, tiles_m, M, N, scale, C, ldc, cstride);
+    kern<<<dim3((unsigned)ntiles, (unsigned)nslab), 256, smem, ctx->stream>>>(A, lda, B, ldb, M, N, K, kslab, tiles_m, sym != 0,
+                                                                              (double *)ctx->d_gemm_ws);
+    gemm_tn_reduce_kernel<<<std::min(4 * ctx->num_sms, (ntiles * T * T + 255) / 256), 256, 0, ctx->stream>>>(
+        (const double *)ctx->d_gemm_ws, (int)nslab, ntiles, tiles_m, T, M, N, scale, C, ldc, cstride, sym);
     e = cudaGetLastError();
     if (e != cudaSuccess) { chefsi_fail(ctx, "gemm_tn launch: %s", cudaGetErrorString(e)); return -1; }
     return 2;
+}
+
+/* C(M x N, ld ldc, device) = scale * A^T B with A: K x M (lda), B: K x N (ldb), all device, column-major.
+   sym = +1 / -1: the caller knows the product is symmetric / antisymmetric (Y^T Y, Y^T H Y and the imaginary parts of their
+   complex forms): only the tiles of the upper triangle are computed and mirrored, about half the work.  What consumes
+   these matrices (dsygvd / zhegvd with uplo = 'U', eigenSolver.c:1318) reads the upper triangle only. */
+int launch_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B, size_t ldb, int M, int N, size_t K, double scale,
+                   double *C, size_t ldc, int cstride, int sym)
+{
+    if (!ctx->gemm_symmetric) sym = 0;
+    if (std::max(M, N) > 64 && ctx->gemm_big_tiles)
+        return run_gemm_tn<8, 4, 16, 4>(ctx, A, lda, B, ldb, M, N, K, scale, C, ldc, cstride, sym, 1);
+    return run_gemm_tn<4, 2, 32, 3>(ctx, A, lda, B, ldb, M, N, K, scale, C, ldc, cstride, sym, 2);
+}
+
+template <int FNN, int KCH, int STG>
+static int run_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q, size_t ldq, size_t K, int M, int N, double *C,
+                       size_t ldc, int accumulate)
+{
+    constexpr int CT = 2 * 8 * FNN;
+    const size_t smem = ((size_t)STG * KCH * RPITCH + (size_t)STG * CT * (KCH + 4)) * sizeof(double);
+    auto kern = gemm_nn_kernel<FNN, KCH, STG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(gemm_nn): %s", cudaGetErrorString(e)); return -1; }
+    const size_t rt = (K + RT - 1) / RT, tiles_n = (size_t)(N + CT - 1) / CT;
+    if (rt * tiles_n > 0x7fffffffULL) { chefsi_fail(ctx, "gemm_nn: too many tiles"); return -1; }
+    kern<<<(unsigned)(rt * tiles_n), 256, smem, ctx->stream>>>(A, lda, Q, ldq, K, M, N, (int)tiles_n, C, ldc, accumulate);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { chefsi_fail(ctx, "gemm_nn launch: %s", cudaGetErrorString(e)); return -1; }
+    return 1;
 }
 
 /* C(K x N, ldc) = A Q with A: K x M (lda), Q: M x N (ldq); C must not alias A */
 int launch_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q, size_t ldq, size_t K, int M, int N, double *C,
                    size_t ldc, int accumulate)
 {
-    const size_t smem = ((size_t)NSTG * KC * RPITCH + (size_t)NSTG * 64 * PITCH) * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(gemm_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(gemm_nn): %s", cudaGetErrorString(e)); return -1; }
-    const size_t rt = (K + RT - 1) / RT;
-    if (rt > 0x7fffffffULL) { chefsi_fail(ctx, "gemm_nn: too many row tiles"); return -1; }
-    gemm_nn_kernel<<<dim3((unsigned)rt, (unsigned)((N + 63) / 64)), 256, smem, ctx->stream>>>(A, lda, Q, ldq, K, M, N, C, ldc, accumulate);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { chefsi_fail(ctx, "gemm_nn launch: %s", cudaGetErrorString(e)); return -1; }
-    return 1;
+    if (N > 64 && ctx->gemm_big_tiles) return run_gemm_nn<8, 16, 4>(ctx, A, lda, Q, ldq, K, M, N, C, ldc, accumulate);
+    return run_gemm_nn<4, 32, 3>(ctx, A, lda, Q, ldq, K, M, N, C, ldc, accumulate);
 }
 
 /* out = s * i * in for ncol interleaved complex columns of n elements (column stride ld complex elements) */

@@ -79,6 +79,16 @@ def test_project_and_rotate_streaming_kernel_many_columns(ctx, port):
     _check(ctx, port, g, veff, proj, y)
 
 
+@pytest.mark.parametrize("complex_,ncol", [(False, 150), (False, 129), (True, 97)])
+def test_project_and_rotate_several_big_tiles(ctx, port, complex_, ncol):
+    """More than 64 columns take the 128 x 128 CTA tiles: two tiles per side with a ragged edge, several K slabs."""
+    g, veff, proj, y = overlap_case("stream", ncol=ncol, complex_=complex_)
+    _setup(ctx, g, veff, proj)
+    if complex_:
+        ctx.set_kpoint(KVEC)
+    _check(ctx, port, g, veff, proj, y, kvec=KVEC if complex_ else (0, 0, 0))
+
+
 @pytest.mark.parametrize("complex_", [False, True])
 def test_filter_keeps_y_resident(ctx, port, complex_):
     """ChebyshevFiltering with KEEP_Y and no Y copy-back, then projection and rotation from the device copy: the
