@@ -144,6 +144,17 @@ int chefsi_laplacian_mult(chefsi_ctx_t *ctx, int ncol, double a, double c, const
 int chefsi_laplacian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double a, double c, const void *x, size_t ldi,
                               void *y, size_t ldo);
 
+/* Dx = (D_dir + c) x: the first-derivative stencil along lattice direction dir (0: x, 1: y, 2: z) with the weights
+ * D1_{x,y,z} of chefsi_grid_t, periodic wrap or zero halo along dir.  Replaces Gradient_vectors_dir
+ * (src/gradVecRoutines.c:32-51 -> Gradient_vec_dir :59-311 -> Calc_DX :318-442) and, for complex columns,
+ * Gradient_vectors_dir_kpt (src/gradVecRoutinesKpt.c:35-55 -> :63-340): kdir is the k-point component along dir (what
+ * the reference passes as *kpt_vec); halo values from beyond the low / high face are multiplied by exp(-/+ i kdir L_dir)
+ * (:179-191).  SURVEY.md 8f-4 ("gradient ops sharing the stencil": GGA density gradients, force / stress terms). */
+int chefsi_gradient_mult(chefsi_ctx_t *ctx, int ncol, double c, const double *x, size_t ldi, double *Dx, size_t ldo,
+                         int dir);
+int chefsi_gradient_mult_kpt(chefsi_ctx_t *ctx, int ncol, double c, const void *x, size_t ldi, void *Dx, size_t ldo,
+                             int dir, double kdir);
+
 /* ---- Rayleigh-Ritz projection and subspace rotation with the block resident on the device -------
  * Replaces, for real (Gamma-point) data on a single-device context:
  *   chefsi_subspace_project <- DP_Project_Hamiltonian  src/eigenSolver.c:939-1086 (Project_Hamiltonian :1477-1669):
@@ -228,6 +239,9 @@ int chefsi_hamiltonian_mult_device(chefsi_ctx_t *ctx, int ncol, double c, const 
                                    double *Hx);
 int chefsi_hamiltonian_mult_kpt_device(chefsi_ctx_t *ctx, int ncol, double c, const void *x,
                                        void *Hx);
+/* chefsi_gradient_mult[_kpt] on a device-resident block in the internal layout (enqueued, no synchronisation) */
+int chefsi_gradient_mult_device(chefsi_ctx_t *ctx, int ncol, double c, const void *x, void *Dx, int dir, double kdir,
+                                int is_complex);
 /* Building blocks of the optional DOMAIN SPLIT (z slabs over ranks, sparc_b200/domain_split.py), real data:
  * the reference exchanges FDn halo planes per face before every stencil application
  * (Lap_plus_diag_vec_mult_orth, src/lapVecRoutines.c:387-442,494-534) and all-reduces the projector

@@ -228,3 +228,16 @@ class Reference:
         self.lib.ref_aar(self.h, C.c_double(c), _ptr(x), _ptr(b), C.c_double(omega), C.c_double(beta), C.c_int(m),
                          C.c_int(p), C.c_double(tol), C.c_int(max_iter))
         return x
+
+    def gradient_dir(self, c, x, dir, kdir=0.0):
+        """The reference's own Gradient_vectors_dir (src/gradVecRoutines.c:32) / Gradient_vectors_dir_kpt
+        (src/gradVecRoutinesKpt.c:35; kdir = *kpt_vec) on this problem's grid: Dx."""
+        x = np.ascontiguousarray(x)
+        Dx = np.empty_like(x)
+        ncol, ld = x.shape
+        if np.iscomplexobj(x):
+            self.lib.ref_gradient_dir_kpt(self.h, C.c_int(ncol), C.c_double(c), _ptr(x), C.c_int(ld), _ptr(Dx), C.c_int(ld),
+                                          C.c_int(dir), C.c_double(kdir))
+        else:
+            self.lib.ref_gradient_dir(self.h, C.c_int(ncol), C.c_double(c), _ptr(x), C.c_int(ld), _ptr(Dx), C.c_int(ld), C.c_int(dir))
+        return Dx

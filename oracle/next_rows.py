@@ -104,3 +104,32 @@ def density(X, g):
     """rho[i] = sum_n g[n] |X[n, i]|^2 -- the loop body of CalculateDensity_psi, src/electronDensity.c:135-156 (g[n] =
     occfac * kptWts_loc[k] / Nkpts * occ[n]; the caller scales by 1/dV, :190-196)."""
     return np.einsum("n,ni->i", np.asarray(g, dtype=np.float64), (X.real ** 2 + X.imag ** 2) if np.iscomplexobj(X) else X * X)
+
+
+def gradient_dir(grid, c, x, dir, kdir=0.0):
+    """(D_dir + c) x for a block x[ncol, Nd] -- Gradient_vec_dir, src/gradVecRoutines.c:59-311 (np = 1 branch): x is
+    extended by FDn points along `dir` only, wrapped on a periodic axis (:262-284) or zero on a Dirichlet axis (:285-298),
+    then Calc_DX (:318-409): temp = c x; temp += (x[+r] - x[-r]) w[r], r = 1..FDn, w = D1_stencil_coeffs_{x,y,z}.
+    Complex x: Gradient_vec_dir_kpt, src/gradVecRoutinesKpt.c:63-340: wrapped values from beyond the low face are
+    multiplied by cos(k L) - i sin(k L), from beyond the high face by its conjugate (:179-191,301-311)."""
+    F = grid.FDn
+    N3 = (int(grid.N[2]), int(grid.N[1]), int(grid.N[0]))
+    ax = 3 - dir                       # numpy axis of the lattice direction in x.reshape(ncol, Nz, Ny, Nx)
+    N = N3[2 - dir]
+    bc = grid.BC[dir]
+    L = grid.L[dir]
+    w = grid.coefs[("D1_x", "D1_y", "D1_z")[dir]]
+    v = x.reshape((x.shape[0],) + N3)
+    lo = np.take(v, range(N - F, N), axis=ax)
+    hi = np.take(v, range(0, F), axis=ax)
+    if bc:
+        lo, hi = np.zeros_like(lo), np.zeros_like(hi)
+    elif np.iscomplexobj(x):
+        ph = np.cos(kdir * L) - 1j * np.sin(kdir * L)
+        lo, hi = lo * ph, hi * np.conj(ph)
+    ex = np.concatenate([lo, v, hi], axis=ax)
+    sl = lambda s: np.take(ex, range(F + s, F + s + N), axis=ax)
+    out = v * c
+    for r in range(1, F + 1):
+        out = out + (sl(r) - sl(-r)) * w[r]
+    return out.reshape(x.shape)

@@ -341,3 +341,22 @@ void ref_aar(void *h, double c, double *x, double *b, double omega, double beta,
     ref_problem_t *P = (ref_problem_t *)h;
     AAR(&P->S, poisson_residual, Jacobi_preconditioner, c, P->Nd, x, b, omega, beta, m, p, tol, max_iter, MPI_COMM_SELF);
 }
+
+/* Gradient_vectors_dir (src/gradVecRoutines.c:32-51) and Gradient_vectors_dir_kpt (src/gradVecRoutinesKpt.c:35-55):
+ * (D_dir + c) x on ncol columns; the k-point routine takes a pointer to the k component along dir */
+void Gradient_vectors_dir(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c,
+                          const double *x, const int ldi, double *Dx, const int ldo, const int dir, MPI_Comm comm);
+void Gradient_vectors_dir_kpt(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c,
+                              const double _Complex *x, const int ldi, double _Complex *Dx, const int ldo, const int dir,
+                              const double *kpt_vec, MPI_Comm comm);
+void ref_gradient_dir(void *h, int ncol, double c, const double *x, int ldi, double *Dx, int ldo, int dir)
+{
+    ref_problem_t *P = (ref_problem_t *)h;
+    Gradient_vectors_dir(&P->S, (int)P->Nd, P->DMVertices, ncol, c, x, ldi, Dx, ldo, dir, MPI_COMM_SELF);
+}
+void ref_gradient_dir_kpt(void *h, int ncol, double c, const double _Complex *x, int ldi, double _Complex *Dx, int ldo, int dir,
+                          double kdir)
+{
+    ref_problem_t *P = (ref_problem_t *)h;
+    Gradient_vectors_dir_kpt(&P->S, (int)P->Nd, P->DMVertices, ncol, c, x, ldi, Dx, ldo, dir, &kdir, MPI_COMM_SELF);
+}

@@ -18,6 +18,7 @@ EXPORTS = (
     "chefsi_set_grid", "chefsi_set_projectors", "chefsi_set_veff", "chefsi_set_kpoint",
     "chefsi_chebyshev_filter", "chefsi_chebyshev_filter_kpt",
     "chefsi_hamiltonian_mult", "chefsi_hamiltonian_mult_kpt", "chefsi_laplacian_mult", "chefsi_laplacian_mult_kpt",
+    "chefsi_gradient_mult", "chefsi_gradient_mult_kpt", "chefsi_gradient_mult_device",
     "chefsi_lanczos", "chefsi_lanczos_kpt", "chefsi_subspace_eig", "chefsi_subspace_eig_kpt", "chefsi_band_store", "chefsi_density_accumulate", "chefsi_density_accumulate_kpt", "chefsi_poisson_aar", "chefsi_subspace_reserve", "chefsi_subspace_reserve_kpt", "chefsi_subspace_project_kpt", "chefsi_subspace_rotate_kpt", "chefsi_subspace_project", "chefsi_subspace_rotate",
     "chefsi_device_ld",
     "chefsi_chebyshev_filter_device", "chefsi_chebyshev_filter_kpt_device",
@@ -85,6 +86,9 @@ def load_library() -> C.CDLL:
         getattr(lib, name).argtypes = [vp, i, d, dp, sz, dp, sz]
     for name in ("chefsi_laplacian_mult", "chefsi_laplacian_mult_kpt"):
         getattr(lib, name).argtypes = [vp, i, d, d, dp, sz, dp, sz]
+    lib.chefsi_gradient_mult.argtypes = [vp, i, d, dp, sz, dp, sz, i]
+    lib.chefsi_gradient_mult_kpt.argtypes = [vp, i, d, dp, sz, dp, sz, i, d]
+    lib.chefsi_gradient_mult_device.argtypes = [vp, i, d, vp, vp, i, d, i]
     lib.chefsi_lanczos.argtypes = [vp, dp, d, d, i, C.POINTER(C.c_double), C.POINTER(C.c_double), ip]
     lib.chefsi_lanczos_kpt.argtypes = [vp, vp, d, d, i, C.POINTER(C.c_double), C.POINTER(C.c_double), ip]
     for name in ("chefsi_subspace_eig", "chefsi_subspace_eig_kpt"):

@@ -208,6 +208,16 @@ class ChefsiContext:
         fn = self._lib.chefsi_laplacian_mult_kpt if _is_complex(x) else self._lib.chefsi_laplacian_mult
         self._check(fn(self._h, ncol, float(a), float(c), _addr(x), ldi, _addr(Lapx), Lapx.shape[1]))
 
+    def Gradient_vectors_dir(self, c, x, Dx, dir, kdir=0.0):
+        """Dx = (D_dir + c) x along lattice direction dir (src/gradVecRoutines.c:32; complex x: Gradient_vectors_dir_kpt,
+        src/gradVecRoutinesKpt.c:35, kdir = the k-point component the reference passes as *kpt_vec)."""
+        ncol, ldi = x.shape
+        if _is_complex(x):
+            self._check(self._lib.chefsi_gradient_mult_kpt(self._h, ncol, float(c), _addr(x), ldi, _addr(Dx), Dx.shape[1],
+                                                           int(dir), float(kdir)))
+        else:
+            self._check(self._lib.chefsi_gradient_mult(self._h, ncol, float(c), _addr(x), ldi, _addr(Dx), Dx.shape[1], int(dir)))
+
     # -- device-resident entry points -------------------------------------------------------------
     def filter_device(self, bufA, bufB, bufC, ncol, m, a, b, a0, is_complex=False):
         """Enqueue one filter on device buffers; returns (y_slot, x_slot) in {0,1,2}."""

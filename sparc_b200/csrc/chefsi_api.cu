@@ -1107,6 +1107,85 @@ extern "C" int chefsi_laplacian_mult_kpt(chefsi_ctx_t *ctx, int ncol, double a, 
     return ctx ? lapmult_host(ctx, ncol, a, c, x, ldi, y, ldo, true) : 1;
 }
 
+/* ---- (D_dir + c) x: the first-derivative stencil along one lattice direction (kernels: gradient.cu) -------------
+ * Gradient_vectors_dir[_kpt] (src/gradVecRoutines.c:32-51, src/gradVecRoutinesKpt.c:35-55): the operator of the GGA
+ * density gradient, of the local / nonlocal force and stress terms; SURVEY.md 8f-4 "gradient ops sharing the stencil". */
+static int gradmult_host(chefsi_ctx *ctx, int ncol, double c, const void *x, size_t ldi, void *Dx, size_t ldo, int dir, double kdir,
+                         bool is_complex)
+{
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (dir < 0 || dir > 2) return chefsi_fail(ctx, "gradient_mult: dir must be 0, 1 or 2");
+    if (ncol <= 0) return 0;
+    if (ldi < ctx->Nd || ldo < ctx->Nd) return chefsi_fail(ctx, "leading dimension smaller than the grid");
+    if (ctx->multi) return multi_gradmult_host(ctx, ncol, c, x, ldi, Dx, ldo, dir, kdir, is_complex);
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t esz = is_complex ? 2 * sizeof(double) : sizeof(double);
+    const int chunk = chunk_columns(ctx, ncol, esz);
+    if (ensure_bufs(ctx, (size_t)chunk * ctx->ld * esz)) return 1;
+    const size_t row = ctx->Nd * esz, pitch = ctx->ld * esz;
+    if (chunk == ncol && want_staging(ctx, x, Dx, (size_t)ncol * row)) {
+        if (staged_h2d(ctx, 0, ctx->d_buf[0], pitch, x, ldi * esz, row, ncol)) return drain_streams(ctx, 1);
+        const int n = launch_gradient(ctx, ctx->d_buf[0], ctx->d_buf[1], ncol, dir, c, kdir, is_complex);
+        if (n < 0) return drain_streams(ctx, 1);
+        ctx->stats.kernel_launches += n;
+        if (staged_d2h_begin(ctx, 1, ctx->d_buf[1], pitch, row, ncol)) return drain_streams(ctx, 1);
+        CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
+        staged_d2h_finish(ctx, 1, Dx, ldo * esz, row, ncol);
+        return 0;
+    }
+    /* large blocks: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernel of chunk k through two buffer pairs
+       (the kernel is one pass over the chunk, so the call is bound by the host link: both directions busy) */
+    if (ensure_bufs2(ctx, (size_t)chunk * ctx->ld * esz) || ensure_pipe_events(ctx)) return 1;
+    void *in[2] = {ctx->d_buf[0], ctx->d_buf2[0]}, *out[2] = {ctx->d_buf[1], ctx->d_buf2[1]};
+    cudaEvent_t *ev_h2d = ctx->pipe_ev, *ev_out = ctx->pipe_ev + 6, *ev_d2h = ctx->pipe_ev + 9;
+    int k = 0;
+    for (int c0 = 0; c0 < ncol; c0 += chunk, k++) {
+        const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk, s = k & 1;
+        /* pair s is free again when the kernel of chunk k-2 has read in[s] and its result has left out[s] */
+        if (k >= 2) CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->h2d_stream, ev_out[s], 0));
+        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync(in[s], pitch, (const char *)x + (size_t)c0 * ldi * esz, ldi * esz, row, nc,
+                                                 cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CHEFSI_CUDA_DRAIN(ctx, cudaEventRecord(ev_h2d[s], ctx->h2d_stream));
+        CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[s], 0));
+        if (k >= 2) CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[s], 0));
+        const int n = launch_gradient(ctx, in[s], out[s], nc, dir, c, kdir, is_complex);
+        if (n < 0) return drain_streams(ctx, 1);
+        ctx->stats.kernel_launches += n;
+        CHEFSI_CUDA_DRAIN(ctx, cudaEventRecord(ev_out[s], ctx->stream));
+        CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev_out[s], 0));
+        CHEFSI_CUDA_DRAIN(ctx, cudaMemcpy2DAsync((char *)Dx + (size_t)c0 * ldo * esz, ldo * esz, out[s], pitch, row, nc,
+                                                 cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        CHEFSI_CUDA_DRAIN(ctx, cudaEventRecord(ev_d2h[s], ctx->d2h_stream));
+    }
+    for (int s = 0; s < 2 && s < k; s++) CHEFSI_CUDA_DRAIN(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[s], 0));
+    CHEFSI_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int chefsi_gradient_mult_device(chefsi_ctx_t *ctx, int ncol, double c, const void *x, void *Dx, int dir, double kdir,
+                                           int is_complex)
+{
+    if (!ctx) return 1;
+    if (ctx->multi) return chefsi_fail(ctx, kMultiDeviceApi);
+    if (!ctx->have_grid) return chefsi_fail(ctx, "set_grid must be called first");
+    if (dir < 0 || dir > 2) return chefsi_fail(ctx, "gradient_mult: dir must be 0, 1 or 2");
+    if (ncol <= 0) return 0;
+    CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = launch_gradient(ctx, x, Dx, ncol, dir, c, kdir, is_complex != 0);
+    if (n < 0) return 1;
+    ctx->stats.kernel_launches += n;
+    return 0;
+}
+extern "C" int chefsi_gradient_mult(chefsi_ctx_t *ctx, int ncol, double c, const double *x, size_t ldi, double *Dx, size_t ldo,
+                                    int dir)
+{
+    return ctx ? gradmult_host(ctx, ncol, c, x, ldi, Dx, ldo, dir, 0.0, false) : 1;
+}
+extern "C" int chefsi_gradient_mult_kpt(chefsi_ctx_t *ctx, int ncol, double c, const void *x, size_t ldi, void *Dx, size_t ldo,
+                                        int dir, double kdir)
+{
+    return ctx ? gradmult_host(ctx, ncol, c, x, ldi, Dx, ldo, dir, kdir, true) : 1;
+}
+
 /* ---- misc ---------------------------------------------------------------------------------------- */
 extern "C" int chefsi_fill_random_device(chefsi_ctx_t *ctx, void *buf, int ncol, long long first_col,
                                          unsigned long long seed, int is_complex)

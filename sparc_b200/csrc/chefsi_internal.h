@@ -200,6 +200,7 @@ int multi_filter_host(chefsi_ctx *lead, void *X, size_t ldi, void *Y, size_t ldo
                       int flags, bool is_complex);
 int multi_hmult_host(chefsi_ctx *lead, int ncol, double c, const void *x, size_t ldi, void *Hx, size_t ldo, bool is_complex);
 int multi_lapmult_host(chefsi_ctx *lead, int ncol, double a, double c, const void *x, size_t ldi, void *y, size_t ldo, bool is_complex);
+int multi_gradmult_host(chefsi_ctx *lead, int ncol, double c, const void *x, size_t ldi, void *Dx, size_t ldo, int dir, double kdir, bool is_complex);
 int multi_synchronize(chefsi_ctx *lead);
 void multi_set_profiling(chefsi_ctx *lead, int on);
 int multi_subspace_reserve(chefsi_ctx *lead, int ncol, bool is_complex);
@@ -213,6 +214,8 @@ int launch_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B
                    double *C, size_t ldc, int cstride, int sym = 0);
 int launch_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q, size_t ldq, size_t K, int M, int N, double *C,
                    size_t ldc, int accumulate);
+/* gradient.cu */
+int launch_gradient(chefsi_ctx *ctx, const void *x, void *out, int ncol, int dir, double c, double kdir, bool is_complex);
 int launch_rot90(chefsi_ctx *ctx, const void *in, void *out, size_t n, size_t ld, int ncol, double s);
 int launch_split_complex(chefsi_ctx *ctx, const void *Q, size_t ldq, int M, int N, double *Qr, double *Qi);
 

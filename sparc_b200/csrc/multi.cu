@@ -329,6 +329,18 @@ int multi_lapmult_host(chefsi_ctx *lead, int ncol, double a, double c, const voi
     });
 }
 
+int multi_gradmult_host(chefsi_ctx *lead, int ncol, double c, const void *x, size_t ldi, void *Dx, size_t ldo, int dir, double kdir,
+                        bool is_complex)
+{
+    const size_t esz = is_complex ? 16 : 8;
+    return multi_split(lead, ncol, [=](chefsi_ctx *k, int c0, int nc) {
+        const char *xi = (const char *)x + (size_t)c0 * ldi * esz;
+        char *yo = (char *)Dx + (size_t)c0 * ldo * esz;
+        return is_complex ? chefsi_gradient_mult_kpt(k, nc, c, xi, ldi, yo, ldo, dir, kdir)
+                          : chefsi_gradient_mult(k, nc, c, (const double *)xi, ldi, (double *)yo, ldo, dir);
+    });
+}
+
 int multi_synchronize(chefsi_ctx *lead)
 {
     for (chefsi_ctx *k : lead->multi->kids) {

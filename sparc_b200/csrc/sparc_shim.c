@@ -75,6 +75,11 @@ void poisson_residual(SPARC_OBJ *pSPARC, int N, double c, double *x, double *b, 
 void Jacobi_preconditioner(SPARC_OBJ *pSPARC, int N, double c, double *r, double *f, MPI_Comm comm);
 void Lap_vec_mult_ref(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c, double *x,
                       const int ldi, double *Lapx, const int ldo, MPI_Comm comm);
+void Gradient_vectors_dir_ref(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c,
+                              const double *x, const int ldi, double *Dx, const int ldo, const int dir, MPI_Comm comm);
+void Gradient_vectors_dir_kpt_ref(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c,
+                                  const double _Complex *x, const int ldi, double _Complex *Dx, const int ldo, const int dir,
+                                  const double *kpt_vec, MPI_Comm comm);
 
 /* ------------------------------------------------------------------------------------------------ */
 static struct {
@@ -90,6 +95,8 @@ static struct {
     int npinned;
     unsigned long long n_filter, n_hmult, n_forward, n_lap, n_project, n_rotate, n_lanczos, n_lanczos_iter, n_aar, n_aar_iter;
     double t_lap, t_project, t_rotate, t_lanczos, t_aar;
+    unsigned long long n_grad, n_grad_host;
+    double t_grad;
     int subspace_pending;    /* the last DP_Project_Hamiltonian ran on the device: DP_Subspace_Rotation finds its block there */
     int eig_on_device;       /* the last DP_Solve_Generalized_EigenProblem ran on the device: its eigenvectors are still there */
     int band_store_blocks;   /* size of the device store of rotated blocks (0: not enabled yet) */
@@ -125,6 +132,9 @@ static void shim_report(void)
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] %llu Lap_vec_mult calls (Poisson residual, Kerker mixing, Lanczos of the Laplacian) %.3f s\n",
                 G.n_lap, G.t_lap);
+    if (G.verbose)
+        fprintf(stderr, "[chefsi_b200 shim] %llu Gradient_vectors_dir calls on the device %.3f s (%llu below the work threshold left on the host)\n",
+                G.n_grad, G.t_grad, G.n_grad_host);
     if (G.verbose)
         fprintf(stderr, "[chefsi_b200 shim] %llu DP_Project_Hamiltonian calls %.3f s, %llu DP_Subspace_Rotation calls %.3f s on the device\n",
                 G.n_project, G.t_project, G.n_rotate, G.t_rotate);
@@ -746,6 +756,65 @@ void Lap_vec_mult(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices
     if (chefsi_laplacian_mult(G.ctx, ncol, 1.0, c, x, (size_t)ldi, Lapx, (size_t)ldo) != 0) shim_fatal("chefsi_laplacian_mult");
     G.n_lap++;
     G.t_lap += MPI_Wtime() - t1;
+}
+
+/* (D_dir + c) x -- src/gradVecRoutines.c:32-51 and src/gradVecRoutinesKpt.c:35-55: the gradient of the density for GGA
+ * functionals (exchangeCorrelation.c), of the orbitals for the nonlocal force / stress / pressure terms (forces.c:1050,
+ * stress.c:1543, pressure.c:1059: every band, three directions).  SURVEY.md 8f-4 "gradient ops sharing the stencil".
+ * A call on fewer than CHEFSI_B200_GRAD_MIN_WORK grid-pt * columns (default 2e5: the single density columns of the SCF
+ * test systems, whose 13-point line stencil costs the host less than one PCIe round trip) stays with the reference. */
+static int shim_grad_why(const SPARC_OBJ *pSPARC, int DMnd, const int *DMVertices, int ncol, MPI_Comm comm)
+{
+    if (getenv("CHEFSI_B200_DISABLE") || getenv("CHEFSI_B200_NO_GRAD")) return 1;
+    if (!(pSPARC->cell_typ == 0 || (pSPARC->cell_typ >= 11 && pSPARC->cell_typ <= 17)) || pSPARC->CyclixFlag) return 2;
+    if (pSPARC->order / 2 > CHEFSI_MAX_FDN) return 7;
+    int nproc = 1;
+    MPI_Comm_size(comm, &nproc);
+    const int FDn = pSPARC->order / 2;
+    if (nproc != 1) return 8;
+    if (DMnd != pSPARC->Nd || DMVertices[0] != 0 || DMVertices[1] != pSPARC->Nx - 1 || DMVertices[2] != 0 ||
+        DMVertices[3] != pSPARC->Ny - 1 || DMVertices[4] != 0 || DMVertices[5] != pSPARC->Nz - 1) return 9;
+    if ((pSPARC->BCx == 0 && pSPARC->Nx < FDn) || (pSPARC->BCy == 0 && pSPARC->Ny < FDn) || (pSPARC->BCz == 0 && pSPARC->Nz < FDn)) return 11;
+    static double min_work = -1.0;
+    if (min_work < 0.0) min_work = getenv("CHEFSI_B200_GRAD_MIN_WORK") ? atof(getenv("CHEFSI_B200_GRAD_MIN_WORK")) : 2e5;
+    if ((double)DMnd * ncol < min_work) return -1;
+    return 0;
+}
+
+void Gradient_vectors_dir(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c,
+                          const double *x, const int ldi, double *Dx, const int ldo, const int dir, MPI_Comm comm)
+{
+    const int why = shim_grad_why(pSPARC, DMnd, DMVertices, ncol, comm);
+    if (why) {
+        if (why < 0) G.n_grad_host++; else G.n_forward++;
+        Gradient_vectors_dir_ref(pSPARC, DMnd, DMVertices, ncol, c, x, ldi, Dx, ldo, dir, comm);
+        return;
+    }
+    shim_init();
+    const double t1 = MPI_Wtime();
+    shim_sync_grid(pSPARC);
+    if (chefsi_gradient_mult(G.ctx, ncol, c, x, (size_t)ldi, Dx, (size_t)ldo, dir) != 0) shim_fatal("chefsi_gradient_mult");
+    G.n_grad++;
+    G.t_grad += MPI_Wtime() - t1;
+}
+
+void Gradient_vectors_dir_kpt(const SPARC_OBJ *pSPARC, const int DMnd, const int *DMVertices, const int ncol, const double c,
+                              const double _Complex *x, const int ldi, double _Complex *Dx, const int ldo, const int dir,
+                              const double *kpt_vec, MPI_Comm comm)
+{
+    const int why = shim_grad_why(pSPARC, DMnd, DMVertices, ncol, comm);
+    if (why) {
+        if (why < 0) G.n_grad_host++; else G.n_forward++;
+        Gradient_vectors_dir_kpt_ref(pSPARC, DMnd, DMVertices, ncol, c, x, ldi, Dx, ldo, dir, kpt_vec, comm);
+        return;
+    }
+    shim_init();
+    const double t1 = MPI_Wtime();
+    shim_sync_grid(pSPARC);
+    if (chefsi_gradient_mult_kpt(G.ctx, ncol, c, x, (size_t)ldi, Dx, (size_t)ldo, dir, *kpt_vec) != 0)
+        shim_fatal("chefsi_gradient_mult_kpt");
+    G.n_grad++;
+    G.t_grad += MPI_Wtime() - t1;
 }
 
 #ifdef USE_DP_SUBEIG

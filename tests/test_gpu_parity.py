@@ -167,6 +167,31 @@ def test_lap_vec_mult(ctx, port, cell_typ, N, BC, path):
         assert rel_fro(y, port.lap_plus_diag(g, 1.0, 0.0, c, None, x)) < TOL
 
 
+@pytest.mark.parametrize("cell_typ,N,BC,FDn", [(0, (14, 13, 15), (0, 0, 0), 6), (17, (14, 13, 15), (0, 1, 0), 6),
+                                               (0, (40, 39, 21), (1, 0, 1), 6), (14, (64, 40, 33), (0, 0, 0), 6),
+                                               (0, (14, 13, 15), (0, 0, 1), 4), (0, (37, 14, 13), (0, 0, 0), 6),
+                                               (0, (131, 9, 8), (1, 0, 0), 6)])
+@pytest.mark.parametrize("complex_", [False, True])
+def test_gradient_vectors_dir(ctx, cell_typ, N, BC, FDn, complex_):
+    """Gradient_vectors_dir[_kpt] (gradVecRoutines.c:32, gradVecRoutinesKpt.c:35): (D_dir + c) x along each lattice
+    direction -- the marching kernel (y, z at FD radius 6, several chunks along the marching axis), the shared-memory
+    row kernel (x at radius 6; even and odd Nx, rows longer than two warp passes) and the gather kernel (any other
+    radius) -- periodic / Dirichlet faces, Bloch phases for complex columns, single column and a small
+    block, vs the numpy restatement pinned to the compiled reference (tests/test_next_rows_oracle.py)."""
+    from oracle import next_rows
+    g = P.make_grid(N, tuple(0.45 * n for n in N), BC=BC, FDn=FDn, latvec=P.LATVEC_BY_CELL_TYP[cell_typ])
+    _setup(ctx, g, P.synthetic_veff(g), None)
+    for ncol, c in ((1, 0.0), (3, -0.37)):
+        x = P.random_columns(g.Nd, ncol, seed=29)
+        if complex_:
+            x = np.ascontiguousarray(x + 1j * P.random_columns(g.Nd, ncol, first_col=500, seed=29))
+        for dir in range(3):
+            kdir = KVEC[dir] if (complex_ and BC[dir] == 0) else 0.0
+            Dx = np.empty_like(x)
+            ctx.Gradient_vectors_dir(c, x, Dx, dir, kdir)
+            assert rel_fro(Dx, next_rows.gradient_dir(g, c, x, dir, kdir)) < 1e-13, (dir, ncol)
+
+
 def test_fd_radius_four(ctx, port):
     g, veff, proj, x = small_case(17, FDn=4)
     _setup(ctx, g, veff, proj)

@@ -88,3 +88,18 @@ def test_density_restatement_vs_reference(ref_cls, complex_):
     rho_r = ref.density(x, occ, occfac=2.0, kptwt=0.25)
     rho = next_rows.density(x, 2.0 * 0.25 * occ) / g.dV
     assert np.abs(rho - rho_r).max() <= 1e-14 * np.abs(rho_r).max()
+
+
+@pytest.mark.parametrize("cell_typ,BC,complex_", [(0, (0, 0, 0), False), (17, (0, 0, 0), False), (0, (1, 0, 1), False),
+                                                  (0, (0, 0, 0), True), (14, (0, 0, 0), True), (0, (0, 1, 0), True)])
+def test_gradient_restatement_vs_reference(ref_cls, cell_typ, BC, complex_):
+    """Gradient_vectors_dir[_kpt] (gradVecRoutines.c:32, gradVecRoutinesKpt.c:35): all three directions, with and
+    without the diagonal term; for k-points the Bloch phase of the wrapped halo."""
+    g, veff, proj, x = small_case(cell_typ, BC, ncol=2, complex_=complex_, with_proj=False)
+    ref = ref_cls(g, None, veff)
+    for dir in range(3):
+        for c in (0.0, -0.37):
+            kdir = KVEC[dir] if (complex_ and BC[dir] == 0) else 0.0
+            want = ref.gradient_dir(c, x, dir, kdir)
+            got = next_rows.gradient_dir(g, c, x, dir, kdir)
+            assert np.linalg.norm(got - want) <= 1e-14 * np.linalg.norm(want), (dir, c)

@@ -92,3 +92,45 @@ def test_scf_with_the_whole_rayleigh_ritz_step_on_the_device(name, tmp_path):
     print(f"{name}: E = {e:.10f} Ha/atom, refout {e_ref:.10f}, diff {e - e_ref:+.2e}; {n_eig} eigenproblems, {n_dens} densities on the device")
     assert n_eig > 0 and n_dens > 0
     assert abs(e - e_ref) <= TOL_HA_PER_ATOM
+
+
+def _static_blocks(path):
+    """(forces [n_atom, 3], stress [3, 3]) of a SPARC .static / .refstatic file."""
+    import numpy as np
+    lines = open(path).read().splitlines()
+    def block(title):
+        i = max(k for k, l in enumerate(lines) if l.startswith(title))
+        rows = []
+        for l in lines[i + 1:]:
+            try:
+                rows.append([float(v) for v in l.split()])
+            except ValueError:
+                break
+            if not rows[-1]:
+                rows.pop()
+                break
+        return np.array(rows)
+    return block("Atomic forces"), block("Stress")
+
+
+@pytest.mark.parametrize("name", ["Si8", "Si8_kpt"])
+def test_scf_forces_and_stress_with_gradients_on_the_device(name, tmp_path):
+    """SURVEY.md 8f-4 (gradient ops): with CHEFSI_B200_GRAD_MIN_WORK=0 every Gradient_vectors_dir[_kpt] call of the run --
+    the GGA density gradients of each SCF iteration, the orbital gradients of the nonlocal force / stress / pressure
+    terms (forces.c:1050, stress.c:1543) -- goes through chefsi_gradient_mult[_kpt].  Energy, atomic forces and stress
+    against the reference's committed outputs at the reference's own tolerances (SPARC_testing_script.py:24-26:
+    1e-6 Ha/atom, 1e-5 Ha/Bohr, 0.1 % of the stress)."""
+    import numpy as np
+    e, e_ref, log, out = run_case(name, tmp_path, {"CHEFSI_B200_GRAD_MIN_WORK": "0"})
+    m = re.search(r"(\d+) Gradient_vectors_dir calls on the device .*?\((\d+) below the work threshold", log)
+    assert m, log[-1500:]
+    n_grad, n_host = int(m.group(1)), int(m.group(2))
+    print(f"{name}: {n_grad} gradient calls on the device, E diff {e - e_ref:+.2e}")
+    assert n_grad > 0 and n_host == 0
+    assert abs(e - e_ref) <= TOL_HA_PER_ATOM
+    static, ref = out[:-4] + ".static", out[:-4] + ".refstatic"
+    if os.path.exists(ref):
+        f, s = _static_blocks(static)
+        f_ref, s_ref = _static_blocks(ref)
+        assert f.shape == f_ref.shape and np.abs(f - f_ref).max() <= 1e-5
+        assert s.shape == s_ref.shape and np.abs(s - s_ref).max() <= 1e-3 * np.abs(s_ref).max()
