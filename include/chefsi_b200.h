@@ -217,6 +217,30 @@ int chefsi_lanczos_kpt(chefsi_ctx_t *ctx, const void *x0, double tol_min, double
 int chefsi_poisson_aar(chefsi_ctx_t *ctx, double c, double *x, const double *b, double omega, double beta, int m, int p,
                        double tol, int max_iter, int *iterations, double *res_norm);
 
+/* ---- band-parallel ranks, ONE PROCESS PER GPU: the subspace products over CUDA IPC peer memory (ranks.cu) -------------
+ * The reference's band communicator (NB = ceil(Ns / P) columns per rank, src/parallelization.c:403-428) needs an exchange
+ * for Mp = Y^T Y, Hp = Y^T H Y and X = Y Q: BP2DP (MPI_Alltoallv, src/parallelization.c:2535; eigenSolver.c:977-990) or
+ * pdgemr2d + pdgemm (Project_Hamiltonian :1504-1582, Subspace_Rotation :1854-1918).  Here rank I computes the column
+ * block I of Hp / Mp / Y Q and its GEMM kernels read the other ranks' resident blocks Y_J in place, through addresses
+ * obtained with CUDA IPC (NVLink peer memory between GPUs): the all-gather is fused into the product.  The caller owns
+ * the handle exchange and the barriers between the steps (sparc_b200/band_parallel.py, torch.distributed):
+ *   rank_load / KEEP_Y filter -> barrier -> rank_project -> (all-gather of the blocks, eigensolve)
+ *   -> rank_rotate_prepare -> barrier -> rank_rotate -> barrier.
+ * ncols[nranks]: columns of every rank (rank order = column order); peerY / peerT [nranks]: device addresses of the
+ * other ranks' Y (and, complex data, T = i Y) blocks valid in THIS process (entry `rank` ignored; peerT may be NULL for
+ * real data).  Blocks of Hp / Mp / Q are host arrays of Ns rows x ncols[rank] columns, column-major. */
+#define CHEFSI_IPC_HANDLE_BYTES 64
+int chefsi_rank_load(chefsi_ctx_t *ctx, const void *Y, size_t ldy, int ncol, int is_complex);
+void *chefsi_resident_ptr(chefsi_ctx_t *ctx, int which); /* 0: Y, 1: W, 2: T -- for ranks that share one process */
+int chefsi_ipc_export(chefsi_ctx_t *ctx, int which, void *handle64);
+int chefsi_ipc_open(chefsi_ctx_t *ctx, const void *handle64, void **dptr);
+int chefsi_ipc_close(chefsi_ctx_t *ctx, void *dptr);
+int chefsi_rank_project(chefsi_ctx_t *ctx, int is_complex, int nranks, int rank, const int *ncols, void *const *peerY,
+                        void *Hp_blk, void *Mp_blk, size_t ldp);
+int chefsi_rank_rotate_prepare(chefsi_ctx_t *ctx, int is_complex);
+int chefsi_rank_rotate(chefsi_ctx_t *ctx, int is_complex, int nranks, int rank, const int *ncols, void *const *peerY,
+                       void *const *peerT, const void *Q_blk, size_t ldq, void *X_blk, size_t ldx);
+
 /* ---- device-resident entry points ---------------------------------------------------
  * Buffers are device pointers (256-byte aligned) holding ncol columns in the library's INTERNAL
  * layout: chefsi_device_ld(ctx) elements (doubles, or complex pairs for the _kpt variants) per

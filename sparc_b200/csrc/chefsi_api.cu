@@ -122,6 +122,7 @@ extern "C" void chefsi_destroy(chefsi_ctx_t *ctx)
     cudaFree(ctx->d_res_Y); cudaFree(ctx->d_res_W); cudaFree(ctx->d_res_T); cudaFree(ctx->d_gemm_ws); cudaFree(ctx->d_lanczos); cudaFree(ctx->d_aar);
     for (int i = 0; i < 3; i++) cudaFree(ctx->d_small[i]);
     rayleigh_ritz_destroy(ctx);
+    rank_state_destroy(ctx);
     for (int i = 0; i < 12; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     cudaFree(ctx->d_sync);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

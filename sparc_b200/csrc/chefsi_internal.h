@@ -120,6 +120,7 @@ struct chefsi_ctx {
     int res_ncol = 0;                              /* columns of the resident Y (0: none) */
     const void *res_host = nullptr;                /* host address the resident Y stands for */
     const void *res_unwritten_host = nullptr;      /* host block whose copy-back was skipped (NO_Y_COPYBACK): its contents are stale */
+    void *rank_state = nullptr;                    /* ranks.cu: Hp / Mp / Q column blocks of a one-process-per-GPU run */
     void *d_aar = nullptr;                         /* aar.cu: x, b, r, x_old, f, f_old, the two histories, scalars */
     size_t aar_bytes = 0;
     void *d_lanczos = nullptr;                     /* lanczos.cu: three vectors + scalars */
@@ -214,6 +215,8 @@ int launch_gemm_tn(chefsi_ctx *ctx, const double *A, size_t lda, const double *B
                    double *C, size_t ldc, int cstride, int sym = 0);
 int launch_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q, size_t ldq, size_t K, int M, int N, double *C,
                    size_t ldc, int accumulate);
+/* ranks.cu */
+void rank_state_destroy(chefsi_ctx *ctx);
 /* gradient.cu */
 int launch_gradient(chefsi_ctx *ctx, const void *x, void *out, int ncol, int dir, double c, double kdir, bool is_complex);
 int launch_rot90(chefsi_ctx *ctx, const void *in, void *out, size_t n, size_t ld, int ncol, double s);
