@@ -174,11 +174,8 @@ int launch_t(chefsi_ctx *ctx, const GradArgs &a)
     } else if (a.dir == 0 && a.F == 6 && (size_t)8 * ((a.Nx + 2 * 6 + 2) & ~1) * sizeof(T) <= (size_t)200 << 10) {
         const int line_elems = (a.Nx + 2 * 6 + 2) & ~1; /* an odd Nx reads one element past its halo: keep it inside the line */
         const size_t smem = (size_t)8 * line_elems * sizeof(T);
-        static bool attr_set[2] = {false, false};
-        if (smem > ((size_t)48 << 10) && !attr_set[sizeof(T) == 16]) {
+        if (smem > ((size_t)48 << 10)) /* per device, so not cached in a static: a multi-device context launches on each of its GPUs */
             CHEFSI_CUDA(ctx, cudaFuncSetAttribute(xline_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
-            attr_set[sizeof(T) == 16] = true;
-        }
         const size_t nrows = (size_t)a.Ny * a.Nz * a.ncol;
         size_t blocks = (nrows + 7) / 8;
         if (blocks > (size_t)148 * 32) blocks = (size_t)148 * 32;

@@ -285,6 +285,46 @@ def test_dense_stream_kernel_vs_oracle(ctx_dense, port, N, BC):
     assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
 
 
+# disjoint spheres on grids the dense streaming kernel takes: several atoms per tile, spheres cut by tile edges,
+# by a shifted (overlapping) last tile and by periodic / Dirichlet faces, segmented and whole sphere images
+DISJOINT_CASES = {
+    # name: (N, BC, frac, rc, nproj, ncol, degree)
+    "one_tile": ((32, 32, 24), (0, 0, 0), [[0.02, 0.5, 0.97], [0.5, 0.5, 0.5]], [2.4, 2.0], [18, 7], 3, 8),
+    "shifted_tiles": ((48, 40, 20), (0, 0, 0), [[0.64, 0.78, 0.3], [0.2, 0.2, 0.8], [0.97, 0.03, 0.5]], [2.3, 2.6, 2.0], [18, 13, 7], 5, 6),
+    "dirichlet": ((64, 32, 16), (1, 0, 1), [[0.05, 0.5, 0.1], [0.5, 0.97, 0.5], [0.8, 0.4, 0.9]], [2.4, 2.0, 2.2], [18, 7, 9], 4, 5),
+    "many_atoms": ((96, 96, 13), (0, 0, 0), [[(i + 0.37) / 6, (j + 0.61) / 6, 0.21 + 0.5 * ((i + j) % 2)]
+                                            for i in range(6) for j in range(6)], 2.1, 18, 6, 4),
+    "degree_two": ((36, 64, 12), (0, 0, 1), [[0.3, 0.3, 0.5], [0.7, 0.8, 0.4]], [2.2, 2.5], [26, 18], 2, 2),
+    "many_columns": ((64, 64, 12), (0, 0, 0), [[0.25, 0.25, 0.5], [0.75, 0.75, 0.1], [0.5, 0.02, 0.6]], [2.4, 2.4, 2.0], [18, 18, 5], 70, 3),
+}
+
+
+def _disjoint_case(name):
+    N, BC, frac, rc, nproj, ncol, m = DISJOINT_CASES[name]
+    g = P.make_grid(N, tuple(0.45 * n for n in N), BC=BC)
+    veff = P.synthetic_veff(g)
+    proj = P.make_projectors(g, np.array(frac), rc=rc, nproj=nproj, seed=5)
+    assert sphere_overlap_count(proj, g.Nd) == 0
+    x = P.random_columns(g.Nd, ncol, seed=17)
+    return g, veff, proj, x, m
+
+
+@pytest.mark.parametrize("name", sorted(DISJOINT_CASES))
+def test_fused_projector_chain_disjoint_spheres(ctx, port, name):
+    """Disjoint spheres on the dense streaming path: one stencil launch + one FUSED projector launch per degree
+    (expand with the input's alpha, project the final output for the next degree), alpha partials per image /
+    segment summed in a fixed order, first degree PROJECT, last degree EXPAND."""
+    g, veff, proj, x, m = _disjoint_case(name)
+    _setup(ctx, g, veff, proj)
+    a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+    X, Y = x.copy(), np.empty_like(x)
+    ctx.ChebyshevFiltering(X, Y, m, a, b, a0)
+    st = ctx.stats()
+    assert st["last_path"] == 1 and st["last_nloc_atomic"] == 0
+    Xw, Yw = port.chebyshev_filter(g, proj, veff, x, m, a, b, a0)
+    assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+
+
 @pytest.mark.parametrize("cell_typ", [11, 12, 13, 14, 15, 16, 17])
 @pytest.mark.parametrize("N,BC", [((32, 32, 14), (0, 0, 0)), ((64, 40, 13), (0, 0, 0)), ((38, 70, 12), (0, 0, 0)),
                                    ((32, 32, 16), (1, 0, 1)), ((36, 64, 12), (0, 1, 0)), ((40, 39, 12), (1, 1, 1)),
