@@ -92,23 +92,24 @@ struct DenseMaps {
  * reads 2 x 7 chunks for the two x windows, 12 chunks for the rows r0-6 .. r0-1 and r0+2 .. r0+7 (each
  * halo row serves both output rows) and 2 + 2 chunks of Veff / xprev: 30 LDS.128 per 4 points.  A quarter
  * warp reads 8 consecutive chunks of one row: conflict free for any pitch.                            */
-template <class Cfg, int U>
+template <class Cfg, int U, bool HASV, bool HASX, bool STEADY>
 __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepArgs &a, const unsigned char *stage, int p,
-                                                bool active, bool act0, bool act1, int xp, int r0,
-                                                double *__restrict__ out_row, size_t plane_elems,
+                                                bool active, bool act0, bool act1, uint32_t yoff, uint32_t voff,
+                                                double *__restrict__ &dst, size_t plane_elems,
                                                 double (&in)[7][4], double (&acc)[7][4], bool plane_is_zero)
 {
+    /* STEADY: R <= p < Nz, i.e. the plane is inside the grid and so is the plane it completes: no case distinctions */
     const int Nz = d.Nz;
-    const bool interior = (p >= 0) && (p < Nz);
+    const bool interior = STEADY || ((p >= 0) && (p < Nz));
     const int o = p - R;
-    const bool emit = o >= 0 && o < Nz;
+    const bool emit = STEADY || (o >= 0 && o < Nz);
     const double *ytile = reinterpret_cast<const double *>(stage);
     const double *vtile = reinterpret_cast<const double *>(stage + Cfg::OFF_V);
     const double *xtile = reinterpret_cast<const double *>(stage + Cfg::OFF_X);
 
     double v[4] = {0, 0, 0, 0};
-    if (active && !plane_is_zero) {
-        const double *cp = ytile + (r0 + HT) * Cfg::YP + 2 * xp + R; /* centre chunk of row r0 */
+    if (active && (STEADY || !plane_is_zero)) {
+        const double *cp = ytile + yoff; /* centre chunk of row r0: (r0 + HT) * YP + 2 xp + R */
         if (interior) {
             double xr[2][14];
 #pragma unroll
@@ -120,9 +121,9 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
                 xr[1][2 * t] = w1.x; xr[1][2 * t + 1] = w1.y;
             }
             double ve[4] = {0, 0, 0, 0};
-            if (a.veff) {
-                const double2 w0 = *reinterpret_cast<const double2 *>(vtile + r0 * Cfg::XP + 2 * xp);
-                const double2 w1 = *reinterpret_cast<const double2 *>(vtile + (r0 + 1) * Cfg::XP + 2 * xp);
+            if (HASV) {
+                const double2 w0 = *reinterpret_cast<const double2 *>(vtile + voff); /* r0 * XP + 2 xp */
+                const double2 w1 = *reinterpret_cast<const double2 *>(vtile + voff + Cfg::XP);
                 ve[0] = w0.x; ve[1] = w0.y; ve[2] = w1.x; ve[3] = w1.y;
             }
             /* d.w*, d.coef0 carry the recurrence scale s1 (and the shift c), see launch_cfg: 40 FP64 instructions per point */
@@ -131,7 +132,7 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
             for (int i = 0; i < 4; i++) {
                 const int row = i >> 1, j = i & 1;
                 v[i] = xr[row][R + j];
-                const double diag = a.veff ? fma(a.s1, ve[i], d.coef0) : d.coef0;
+                const double diag = HASV ? fma(a.s1, ve[i], d.coef0) : d.coef0;
                 sx[i] = fma(d.wx[1], xr[row][R + j - 1] + xr[row][R + j + 1], diag * v[i]);
                 sz[i] = d.wz[1] * in[(U - 1 + 7) % 7][i];
             }
@@ -170,7 +171,7 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
             v[0] = w0.x; v[1] = w0.y; v[2] = w1.x; v[3] = w1.y;
         }
     }
-    if (p >= 0) { /* scatter the z terms into the 6 accumulators behind this plane */
+    if (STEADY || p >= 0) { /* scatter the z terms into the 6 accumulators behind this plane */
 #pragma unroll
         for (int r = 1; r <= R; r++)
 #pragma unroll
@@ -181,9 +182,9 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
 
     if (emit && active) {
         double res[4];
-        if (a.s2 != 0.0) {
-            const double2 w0 = *reinterpret_cast<const double2 *>(xtile + r0 * Cfg::XP + 2 * xp);
-            const double2 w1 = *reinterpret_cast<const double2 *>(xtile + (r0 + 1) * Cfg::XP + 2 * xp);
+        if (HASX) {
+            const double2 w0 = *reinterpret_cast<const double2 *>(xtile + voff);
+            const double2 w1 = *reinterpret_cast<const double2 *>(xtile + voff + Cfg::XP);
             res[0] = fma(-a.s2, w0.x, acc[(U + 1) % 7][0]);
             res[1] = fma(-a.s2, w0.y, acc[(U + 1) % 7][1]);
             res[2] = fma(-a.s2, w1.x, acc[(U + 1) % 7][2]);
@@ -192,13 +193,13 @@ __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepAr
 #pragma unroll
             for (int i = 0; i < 4; i++) res[i] = acc[(U + 1) % 7][i];
         }
-        double *dst = out_row + (size_t)o * plane_elems;
         if (act0) stg128(dst, res[0], res[1]);
         if (act1) stg128(dst + d.Nx, res[2], res[3]);
     }
+    if (emit) dst += plane_elems; /* running output pointer: planes are emitted in order */
 }
 
-template <int WX, int WY>
+template <int WX, int WY, bool HASV, bool HASX>
 __global__ void __launch_bounds__(TileCfg<WX, WY>::THREADS, 1)
 stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constant__ DenseDesc d, const StepArgs a,
                     const int nitems, unsigned int *__restrict__ sync_counter, const unsigned int sync_base)
@@ -224,7 +225,10 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
     const int Nx = d.Nx, Ny = d.Ny, Nz = d.Nz;
     const bool xper = (d.bc[0] == 0), yper = (d.bc[1] == 0), zper = (d.bc[2] == 0);
     const size_t plane_elems = (size_t)Nx * Ny;
-    uint32_t it = 0; /* ring position, continues across work items */
+    /* ring position (stage, parity of its current use), continues across work items; kept as a pair of counters: the
+       stage index as it % 5 is a multiply-high chain in front of every barrier wait */
+    uint32_t rs = 0, rpar = 0;
+#define CHEFSI_RING_ADVANCE() do { if (++rs == (uint32_t)kStages) { rs = 0; rpar ^= 1u; } } while (0)
 
     if (warp >= Cfg::CONSUMER_WARPS) {
         /* ================= producer warpgroup (one elected lane issues the TMA boxes) ================= */
@@ -263,12 +267,12 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
                     if (p < 0) kz += Nz; else if (p >= Nz) kz -= Nz;
                     const int o = p - R;
                     const bool need_y = interior || zper;          /* Dirichlet z: planes outside are zero */
-                    const bool need_v = interior && a.veff != nullptr;
-                    const bool need_x = (o >= 0 && o < Nz) && a.s2 != 0.0;
+                    const bool need_v = interior && HASV;
+                    const bool need_x = (o >= 0 && o < Nz) && HASX;
                     if (!need_y && !need_x) continue;
-                    const int s = it % kStages;
+                    const int s = (int)rs;
                     unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
-                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    mbar_wait(&empty[s], rpar ^ 1u);
                     mbar_expect_tx(&tb[s], (need_y ? ybytes : 0u) + (uint32_t)((need_v ? Cfg::XP * Cfg::TY * 8 : 0) +
                                                                                 (need_x ? Cfg::XP * Cfg::TY * 8 : 0)));
                     if (need_y) {
@@ -284,7 +288,7 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
                     }
                     if (need_v) tma_load_4d(stage + Cfg::OFF_V, &maps.veff, x0, y0, p, 0, &tb[s]);
                     if (need_x) tma_load_4d(stage + Cfg::OFF_X, &maps.xprev, x0, y0, o, n, &tb[s]);
-                    it++;
+                    CHEFSI_RING_ADVANCE();
                 }
             }
         } else if (warp > Cfg::CONSUMER_WARPS) {
@@ -292,7 +296,6 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
                producer lane; they copy the periodic-x strips of a landed stage into the zero-filled halo columns of
                its tile, so that the consumers read every x window with constant offsets ---- */
             const int ft = (int)threadIdx.x - (Cfg::CONSUMER_WARPS + 1) * 32; /* 0 .. 95 */
-            uint32_t itf = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int tile = item % (d.ntx * d.nty);
                 const int x0 = tile_origin(tile % d.ntx, Cfg::TX, Nx);
@@ -301,11 +304,11 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
                     const bool interior = (p >= 0 && p < Nz);
                     const int o = p - R;
                     const bool need_y = interior || zper;
-                    const bool need_x = (o >= 0 && o < Nz) && a.s2 != 0.0;
+                    const bool need_x = (o >= 0 && o < Nz) && HASX;
                     if (!need_y && !need_x) continue;
-                    const int s = itf % kStages;
+                    const int s = (int)rs;
                     unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
-                    mbar_wait(&landed[s], (itf / kStages) & 1);
+                    mbar_wait(&landed[s], rpar);
                     if (need_y && (need_l || need_r)) {
                         double *tile_d = reinterpret_cast<double *>(stage);
                         const double *sl = reinterpret_cast<const double *>(stage + Cfg::OFF_L);
@@ -327,7 +330,7 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
                     }
                     asm volatile("bar.sync 2, 96;" ::: "memory");
                     if (ft == 0) mbar_arrive(&full[s]);
-                    itf++;
+                    CHEFSI_RING_ADVANCE();
                 }
             }
         }
@@ -337,6 +340,12 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
         /* a thread owns a 2 x 2 patch (qx: x-pair index, ry: first of its two rows) */
         const int qx = lane & 15;
         const int ry = warp * 4 + 2 * (lane >> 4);
+        /* the thread's offsets (doubles) into the haloed tile and into the Veff / xprev tiles; made opaque so that
+           they live in a register instead of being re-derived from %tid (S2R + 6 ALU ops on the critical path of
+           every plane step) */
+        uint32_t yoff = (uint32_t)((ry + HT) * Cfg::YP + 2 * qx + R), voff = (uint32_t)(ry * Cfg::XP + 2 * qx);
+        uint32_t lane0 = (lane == 0) ? 1u : 0u;
+        asm volatile("" : "+r"(yoff), "+r"(voff), "+r"(lane0));
         double in[7][4], acc[7][4];
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
@@ -347,45 +356,54 @@ stream_dense_kernel(const __grid_constant__ DenseMaps maps, const __grid_constan
             const bool act0 = (gx >= tx * Cfg::TX) && (gy >= ty * Cfg::TY);
             const bool act1 = (gx >= tx * Cfg::TX) && (gy + 1 >= ty * Cfg::TY); /* second row of the 2 x 2 patch */
             const bool active = act1;
-            double *out_row = reinterpret_cast<double *>(a.out) + (size_t)n * a.ld + (size_t)gy * Nx + gx;
+            double *dst = reinterpret_cast<double *>(a.out) + (size_t)n * a.ld + (size_t)gy * Nx + gx; /* output plane 0 */
 #pragma unroll
             for (int u = 0; u < 7; u++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) { in[u][j] = 0.0; acc[u][j] = 0.0; }
 
-#define CHEFSI_STEP(U)                                                                                   \
-    if (p + (U) < Nz + R) {                                                                              \
+#define CHEFSI_STEP(U, STEADY)                                                                           \
+    if (STEADY || p + (U) < Nz + R) {                                                                    \
         const int pp = p + (U);                                                                          \
-        const bool zplane = !zper && (pp < 0 || pp >= Nz);   /* Dirichlet z: the plane is zero */        \
-        const bool use_stage = !zplane || (pp - R >= 0 && pp - R < Nz && a.s2 != 0.0);                   \
+        const bool zplane = !(STEADY) && !zper && (pp < 0 || pp >= Nz); /* Dirichlet z: the plane is zero */ \
+        const bool use_stage = (STEADY) || !zplane || (pp - R >= 0 && pp - R < Nz && HASX);              \
         const unsigned char *stage = ring;                                                               \
         int s = 0;                                                                                       \
         if (use_stage) {                                                                                 \
-            s = it % kStages;                                                                            \
+            s = (int)rs;                                                                                 \
             stage = ring + (size_t)s * Cfg::STAGE_BYTES;                                                 \
-            mbar_wait(&full[s], (it / kStages) & 1);                                                     \
+            mbar_wait(&full[s], rpar);                                                                   \
         }                                                                                                \
-        consume_plane22<Cfg, (U)>(d, a, stage, pp, active, act0, act1, qx, ry, out_row, plane_elems, in, acc, zplane); \
+        consume_plane22<Cfg, (U), HASV, HASX, (STEADY)>(d, a, stage, pp, active, act0, act1, yoff, voff, dst, plane_elems, in, acc, zplane); \
         if (use_stage) {                                                                                 \
             __syncwarp();                                                                                \
-            if (lane == 0) mbar_arrive(&empty[s]);                                                       \
-            it++;                                                                                        \
+            if (lane0) mbar_arrive(&empty[s]);                                                           \
+            CHEFSI_RING_ADVANCE();                                                                       \
         }                                                                                                \
     }
+#define CHEFSI_GROUP(STEADY)                                                                             \
+    {                                                                                                    \
+        if ((STEADY) || p + 0 >= -R) { CHEFSI_STEP(0, STEADY) }                                          \
+        CHEFSI_STEP(1, STEADY)                                                                           \
+        CHEFSI_STEP(2, STEADY)                                                                           \
+        CHEFSI_STEP(3, STEADY)                                                                           \
+        CHEFSI_STEP(4, STEADY)                                                                           \
+        CHEFSI_STEP(5, STEADY)                                                                           \
+        CHEFSI_STEP(6, STEADY)                                                                           \
+    }
             /* p runs over -6 .. Nz+5; groups start at p = -7 so that the phase U == (pp + 7) % 7 is
-               compile-time inside the unrolled body (pp = -7 itself is skipped) */
-            for (int p = -R - 1; p < Nz + R; p += 7) {
-                if (p + 0 >= -R) { CHEFSI_STEP(0) }
-                CHEFSI_STEP(1)
-                CHEFSI_STEP(2)
-                CHEFSI_STEP(3)
-                CHEFSI_STEP(4)
-                CHEFSI_STEP(5)
-                CHEFSI_STEP(6)
-            }
+               compile-time inside the unrolled body (pp = -7 itself is skipped).  Groups whose seven planes all lie
+               in [R, Nz) -- the plane is inside the grid and so is the plane it completes -- take a body without the
+               boundary case distinctions */
+            int p = -R - 1;
+            for (; p < R && p < Nz + R; p += 7) CHEFSI_GROUP(false)
+            for (; p + 6 < Nz; p += 7) CHEFSI_GROUP(true)
+            for (; p < Nz + R; p += 7) CHEFSI_GROUP(false)
+#undef CHEFSI_GROUP
 #undef CHEFSI_STEP
         }
     }
+#undef CHEFSI_RING_ADVANCE
 }
 
 /* ---- host side ---------------------------------------------------------------------------- */
@@ -403,7 +421,7 @@ bool make_map(CUtensorMap *map, const void *base, const Layout &L, int ncol, int
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int WX, int WY>
+template <int WX, int WY, bool HASV, bool HASX>
 int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
 {
     using Cfg = TileCfg<WX, WY>;
@@ -433,7 +451,7 @@ int launch_cfg(chefsi_ctx *ctx, const StepArgs &a)
         return -1;
     }
     static_assert(Cfg::TX == 32 && Cfg::TY == 4 * Cfg::CONSUMER_WARPS && Cfg::CONSUMER_WARPS % 4 == 0, "2 x 2 mapping: 16 pairs x 4 rows per warp");
-    auto kern = stream_dense_kernel<WX, WY>;
+    auto kern = stream_dense_kernel<WX, WY, HASV, HASX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(stream): %s", cudaGetErrorString(e)); return -1; }
     const int grid = (int)((nitems < ctx->num_sms) ? nitems : ctx->num_sms);
@@ -492,5 +510,8 @@ bool stream_dense_supported(const chefsi_ctx *ctx, bool is_complex)
 int launch_stencil_stream_dense(chefsi_ctx *ctx, const StepArgs &a)
 {
     if (a.ncol <= 0) return 0;
-    return launch_cfg<2, 4>(ctx, a);
+    /* with / without the Veff tile and the xprev tile: compile-time, so the plane step carries no selects for them */
+    const bool hv = a.veff != nullptr, hx = a.s2 != 0.0;
+    if (hv) return hx ? launch_cfg<2, 4, true, true>(ctx, a) : launch_cfg<2, 4, true, false>(ctx, a);
+    return hx ? launch_cfg<2, 4, false, true>(ctx, a) : launch_cfg<2, 4, false, false>(ctx, a);
 }

@@ -591,6 +591,41 @@ def test_bench_problem_parity(ctx, port):
     torch.cuda.empty_cache()
 
 
+def test_empty_block_and_degenerate_projector_tables(ctx, port):
+    """Edge cases the reference's loops pass through silently: a block with no columns (every entry point returns
+    without touching its output), an atom type without projectors (nlocVecRoutines.c:811 `if (!nproj) continue`), a
+    sphere image with no grid points in the domain (`if (!ndc) continue`, :816), degree 1."""
+    g = P.make_grid((32, 32, 16), (14.4, 14.4, 7.2))
+    veff = P.synthetic_veff(g)
+    pr = P.make_projectors(g, np.array([[0.2, 0.3, 0.4], [0.7, 0.7, 0.6], [0.5, 0.1, 0.2]]), rc=[2.0, 2.2, 1.8],
+                           nproj=[0, 7, 5], seed=3)
+    assert pr.IP_displ[1] == 0 and sphere_overlap_count(pr, g.Nd) == 0
+    proj = P.Projectors(n_atom=pr.n_atom, IP_displ=pr.IP_displ, gamma=pr.gamma,
+                        img_atom=np.append(pr.img_atom, 1).astype(np.int32), img_ndc=np.append(pr.img_ndc, 0).astype(np.int32),
+                        img_coords=np.append(pr.img_coords, [99.0, 99.0, 99.0]),
+                        pos_off=np.append(pr.pos_off, pr.pos_off[-1]).astype(np.int64),
+                        chi_off=np.append(pr.chi_off, pr.chi_off[-1]).astype(np.int64), grid_pos=pr.grid_pos, chi=pr.chi)
+    _setup(ctx, g, veff, proj)
+    a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+    x = P.random_columns(g.Nd, 3, seed=23)
+    for m in (1, 4):
+        X, Y = x.copy(), np.empty_like(x)
+        ctx.ChebyshevFiltering(X, Y, m, a, b, a0)
+        Xw, Yw = port.chebyshev_filter(g, proj, veff, x, m, a, b, a0)
+        assert rel_fro(Y, Yw) < TOL and rel_fro(X, Xw) < TOL
+    Hx = np.empty_like(x)
+    ctx.Hamiltonian_vectors_mult(0.2, x, Hx)
+    assert rel_fro(Hx, port.hamiltonian_mult(g, proj, veff, 0.2, x)) < TOL
+    # no columns
+    launches = ctx.stats()["kernel_launches"]
+    e_in, e_out = np.empty((0, g.Nd)), np.empty((0, g.Nd))
+    ctx.ChebyshevFiltering(e_in, e_out, 4, a, b, a0)
+    ctx.Hamiltonian_vectors_mult(0.2, e_in, e_out)
+    ctx.Lap_vec_mult(0.0, e_in, e_out)
+    ctx.Gradient_vectors_dir(0.0, e_in, e_out, 1)
+    assert ctx.stats()["kernel_launches"] == launches
+
+
 def test_device_resident_entry_point_and_rng(ctx, port):
     import torch
     g, veff, proj, _ = small_case(0, N=(32, 32, 16), L=(14.0, 14.0, 7.0))
