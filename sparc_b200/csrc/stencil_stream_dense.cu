@@ -92,86 +92,124 @@ struct DenseMaps {
  * reads 2 x 7 chunks for the two x windows, 12 chunks for the rows r0-6 .. r0-1 and r0+2 .. r0+7 (each
  * halo row serves both output rows) and 2 + 2 chunks of Veff / xprev: 30 LDS.128 per 4 points.  A quarter
  * warp reads 8 consecutive chunks of one row: conflict free for any pitch.                            */
+/* the in-plane part of an interior plane: v = the centre values, acc[U] = x + y terms + the z terms of the 6 planes
+   behind (from the input queue) */
+template <class Cfg, int U, bool HASV>
+__device__ __forceinline__ void interior_plane22(const DenseDesc &d, const StepArgs &a, const double *cp, const double *vtile,
+                                                 uint32_t voff, const double (&in)[7][4], double (&acc)[7][4], double (&v)[4])
+{
+    double xr[2][14];
+#pragma unroll
+    for (int t = 0; t < 7; t++) {
+        /* the periodic-x strips were merged into the tile's halo columns: constant offsets */
+        const double2 w0 = *reinterpret_cast<const double2 *>(cp + 2 * (t - 3));
+        const double2 w1 = *reinterpret_cast<const double2 *>(cp + 2 * (t - 3) + Cfg::YP);
+        xr[0][2 * t] = w0.x; xr[0][2 * t + 1] = w0.y;
+        xr[1][2 * t] = w1.x; xr[1][2 * t + 1] = w1.y;
+    }
+    double ve[4] = {0, 0, 0, 0};
+    if (HASV) {
+        const double2 w0 = *reinterpret_cast<const double2 *>(vtile + voff); /* r0 * XP + 2 xp */
+        const double2 w1 = *reinterpret_cast<const double2 *>(vtile + voff + Cfg::XP);
+        ve[0] = w0.x; ve[1] = w0.y; ve[2] = w1.x; ve[3] = w1.y;
+    }
+    /* d.w*, d.coef0 carry the recurrence scale s1 (and the shift c), see launch_cfg: 40 FP64 instructions per point */
+    double sx[4], sy[4], sz[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int row = i >> 1, j = i & 1;
+        v[i] = xr[row][R + j];
+        const double diag = HASV ? fma(a.s1, ve[i], d.coef0) : d.coef0;
+        sx[i] = fma(d.wx[1], xr[row][R + j - 1] + xr[row][R + j + 1], diag * v[i]);
+        sz[i] = d.wz[1] * in[(U - 1 + 7) % 7][i];
+    }
+#pragma unroll
+    for (int r = 2; r <= R; r++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int row = i >> 1, j = i & 1;
+            sx[i] = fma(d.wx[r], xr[row][R + j - r] + xr[row][R + j + r], sx[i]);
+            sz[i] = fma(d.wz[r], in[(U - r + 7) % 7][i], sz[i]);
+        }
+    /* y: up[k] = row r0-k, dn[k] = row r0+1+k (k = 1..6); row r0 pairs up[k] with (k == 1 ? own row 1 : dn[k-1]),
+       row r0+1 pairs (k == 1 ? own row 0 : up[k-1]) with dn[k]; the y chains start from the z sums */
+    double2 up[R + 1], dn[R + 1];
+    up[0] = make_double2(v[0], v[1]); /* row r0   */
+    dn[0] = make_double2(v[2], v[3]); /* row r0+1 */
+#pragma unroll
+    for (int k = 1; k <= R; k++) {
+        up[k] = *reinterpret_cast<const double2 *>(cp - k * Cfg::YP);
+        dn[k] = *reinterpret_cast<const double2 *>(cp + (1 + k) * Cfg::YP);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) sy[i] = sz[i];
+#pragma unroll
+    for (int k = 1; k <= R; k++) {
+        const double a0 = up[k].x + dn[k - 1].x, a1 = up[k].y + dn[k - 1].y;
+        const double b0 = up[k - 1].x + dn[k].x, b1 = up[k - 1].y + dn[k].y;
+        sy[0] = fma(d.wy[k], a0, sy[0]); sy[1] = fma(d.wy[k], a1, sy[1]);
+        sy[2] = fma(d.wy[k], b0, sy[2]); sy[3] = fma(d.wy[k], b1, sy[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[U][i] = sx[i] + sy[i];
+}
+
 template <class Cfg, int U, bool HASV, bool HASX, bool STEADY>
 __device__ __forceinline__ void consume_plane22(const DenseDesc &d, const StepArgs &a, const unsigned char *stage, int p,
                                                 bool active, bool act0, bool act1, uint32_t yoff, uint32_t voff,
                                                 double *__restrict__ &dst, size_t plane_elems,
                                                 double (&in)[7][4], double (&acc)[7][4], bool plane_is_zero)
 {
-    /* STEADY: R <= p < Nz, i.e. the plane is inside the grid and so is the plane it completes: no case distinctions */
     const int Nz = d.Nz;
-    const bool interior = STEADY || ((p >= 0) && (p < Nz));
-    const int o = p - R;
-    const bool emit = STEADY || (o >= 0 && o < Nz);
     const double *ytile = reinterpret_cast<const double *>(stage);
     const double *vtile = reinterpret_cast<const double *>(stage + Cfg::OFF_V);
     const double *xtile = reinterpret_cast<const double *>(stage + Cfg::OFF_X);
+    if (STEADY) {
+        /* R <= p < Nz: the plane is inside the grid and so is the plane it completes -- one straight block, the xprev
+           values are fetched with everything else */
+        if (active) {
+            double v[4];
+            double2 xw0 = make_double2(0.0, 0.0), xw1 = xw0;
+            if (HASX) {
+                xw0 = *reinterpret_cast<const double2 *>(xtile + voff);
+                xw1 = *reinterpret_cast<const double2 *>(xtile + voff + Cfg::XP);
+            }
+            interior_plane22<Cfg, U, HASV>(d, a, ytile + yoff, vtile, voff, in, acc, v);
+#pragma unroll
+            for (int r = 1; r <= R; r++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[(U - r + 7) % 7][i] = fma(d.wz[r], v[i], acc[(U - r + 7) % 7][i]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) in[U][i] = v[i];
+            double res[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) res[i] = acc[(U + 1) % 7][i];
+            if (HASX) {
+                res[0] = fma(-a.s2, xw0.x, res[0]); res[1] = fma(-a.s2, xw0.y, res[1]);
+                res[2] = fma(-a.s2, xw1.x, res[2]); res[3] = fma(-a.s2, xw1.y, res[3]);
+            }
+            if (act0) stg128(dst, res[0], res[1]);
+            stg128(dst + d.Nx, res[2], res[3]); /* active == act1 */
+        }
+        dst += plane_elems;
+        return;
+    }
+    const bool interior = (p >= 0) && (p < Nz);
+    const int o = p - R;
+    const bool emit = o >= 0 && o < Nz;
 
     double v[4] = {0, 0, 0, 0};
-    if (active && (STEADY || !plane_is_zero)) {
+    if (active && !plane_is_zero) {
         const double *cp = ytile + yoff; /* centre chunk of row r0: (r0 + HT) * YP + 2 xp + R */
         if (interior) {
-            double xr[2][14];
-#pragma unroll
-            for (int t = 0; t < 7; t++) {
-                /* the periodic-x strips were merged into the tile's halo columns: constant offsets */
-                const double2 w0 = *reinterpret_cast<const double2 *>(cp + 2 * (t - 3));
-                const double2 w1 = *reinterpret_cast<const double2 *>(cp + 2 * (t - 3) + Cfg::YP);
-                xr[0][2 * t] = w0.x; xr[0][2 * t + 1] = w0.y;
-                xr[1][2 * t] = w1.x; xr[1][2 * t + 1] = w1.y;
-            }
-            double ve[4] = {0, 0, 0, 0};
-            if (HASV) {
-                const double2 w0 = *reinterpret_cast<const double2 *>(vtile + voff); /* r0 * XP + 2 xp */
-                const double2 w1 = *reinterpret_cast<const double2 *>(vtile + voff + Cfg::XP);
-                ve[0] = w0.x; ve[1] = w0.y; ve[2] = w1.x; ve[3] = w1.y;
-            }
-            /* d.w*, d.coef0 carry the recurrence scale s1 (and the shift c), see launch_cfg: 40 FP64 instructions per point */
-            double sx[4], sy[4], sz[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int row = i >> 1, j = i & 1;
-                v[i] = xr[row][R + j];
-                const double diag = HASV ? fma(a.s1, ve[i], d.coef0) : d.coef0;
-                sx[i] = fma(d.wx[1], xr[row][R + j - 1] + xr[row][R + j + 1], diag * v[i]);
-                sz[i] = d.wz[1] * in[(U - 1 + 7) % 7][i];
-            }
-#pragma unroll
-            for (int r = 2; r <= R; r++)
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int row = i >> 1, j = i & 1;
-                    sx[i] = fma(d.wx[r], xr[row][R + j - r] + xr[row][R + j + r], sx[i]);
-                    sz[i] = fma(d.wz[r], in[(U - r + 7) % 7][i], sz[i]);
-                }
-            /* y: up[k] = row r0-k, dn[k] = row r0+1+k (k = 1..6); row r0 pairs up[k] with (k == 1 ? own row 1 : dn[k-1]),
-               row r0+1 pairs (k == 1 ? own row 0 : up[k-1]) with dn[k]; the y chains start from the z sums */
-            double2 up[R + 1], dn[R + 1];
-            up[0] = make_double2(v[0], v[1]); /* row r0   */
-            dn[0] = make_double2(v[2], v[3]); /* row r0+1 */
-#pragma unroll
-            for (int k = 1; k <= R; k++) {
-                up[k] = *reinterpret_cast<const double2 *>(cp - k * Cfg::YP);
-                dn[k] = *reinterpret_cast<const double2 *>(cp + (1 + k) * Cfg::YP);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) sy[i] = sz[i];
-#pragma unroll
-            for (int k = 1; k <= R; k++) {
-                const double a0 = up[k].x + dn[k - 1].x, a1 = up[k].y + dn[k - 1].y;
-                const double b0 = up[k - 1].x + dn[k].x, b1 = up[k - 1].y + dn[k].y;
-                sy[0] = fma(d.wy[k], a0, sy[0]); sy[1] = fma(d.wy[k], a1, sy[1]);
-                sy[2] = fma(d.wy[k], b0, sy[2]); sy[3] = fma(d.wy[k], b1, sy[3]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) acc[U][i] = sx[i] + sy[i];
+            interior_plane22<Cfg, U, HASV>(d, a, cp, vtile, voff, in, acc, v);
         } else {
             const double2 w0 = *reinterpret_cast<const double2 *>(cp);
             const double2 w1 = *reinterpret_cast<const double2 *>(cp + Cfg::YP);
             v[0] = w0.x; v[1] = w0.y; v[2] = w1.x; v[3] = w1.y;
         }
     }
-    if (STEADY || p >= 0) { /* scatter the z terms into the 6 accumulators behind this plane */
+    if (p >= 0) { /* scatter the z terms into the 6 accumulators behind this plane */
 #pragma unroll
         for (int r = 1; r <= R; r++)
 #pragma unroll

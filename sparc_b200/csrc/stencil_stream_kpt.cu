@@ -130,29 +130,32 @@ __device__ __forceinline__ void fix_phases(const KptDesc &d, unsigned char *stag
  * U = (p + 7) mod 7 (compile time): register-queue rotation by renaming.
  * The periodic-x strips (phase applied) have been merged into the tile and the wrapped y rows multiplied by their
  * phase in shared memory (fix_phases) by now: every window is read with constant offsets. */
-template <int U>
+/* yoff / voff / xoff: the thread's offsets (doubles) into the haloed tile, the Veff tile and the xprev tile, kept in
+ * registers by the caller; HASV / HASX: the step has a Veff / an xprev operand; STEADY: R <= p < Nz, the plane is
+ * inside the grid and so is the plane it completes (no boundary case distinctions); dst: running output pointer. */
+template <int U, bool HASV, bool HASX, bool STEADY>
 __device__ __forceinline__ void consume_plane(const KptDesc &d, const StepArgs &a, const unsigned char *stage, int p,
-                                              bool active, bool act0, bool act1, int xp, int r0,
-                                              double *__restrict__ out_row,
+                                              bool active, bool act0, bool act1, uint32_t yoff, uint32_t voff, uint32_t xoff,
+                                              double *__restrict__ &dst,
                                               size_t plane_doubles, double (&in)[7][4], double (&acc)[7][4],
                                               bool plane_is_zero)
 {
     const int Nz = d.Nz;
-    const bool interior = (p >= 0) && (p < Nz);
+    const bool interior = STEADY || ((p >= 0) && (p < Nz));
     const int o = p - R;
-    const bool emit = o >= 0 && o < Nz;
+    const bool emit = STEADY || (o >= 0 && o < Nz);
     const double *ytile = reinterpret_cast<const double *>(stage);
     const double *vtile = reinterpret_cast<const double *>(stage + Cfg::OFF_V);
     const double *xtile = reinterpret_cast<const double *>(stage + Cfg::OFF_X);
 
     double v[4] = {0, 0, 0, 0};
-    if (active && !plane_is_zero) {
-        const double *cp = ytile + (r0 + HT) * Cfg::YP + 2 * xp + 2 * R; /* this point, row r0 */
+    if (active && (STEADY || !plane_is_zero)) {
+        const double *cp = ytile + yoff; /* this point, row r0: (r0 + HT) * YP + 2 xp + 2 R */
         if (interior) {
             double ve[2] = {0.0, 0.0};
-            if (a.veff) {
-                ve[0] = vtile[r0 * Cfg::VP + xp];
-                ve[1] = vtile[(r0 + 1) * Cfg::VP + xp];
+            if (HASV) {
+                ve[0] = vtile[voff]; /* r0 * VP + xp */
+                ve[1] = vtile[voff + Cfg::VP];
             }
             /* d.w*, d.coef0 carry the recurrence scale s1 (and the shift c), see launch */
             double sx[4], sy[4], sz[4];
@@ -172,7 +175,7 @@ __device__ __forceinline__ void consume_plane(const KptDesc &d, const StepArgs &
                 }
                 v[2 * row] = w[6].x;
                 v[2 * row + 1] = w[6].y;
-                const double diag = a.veff ? fma(a.s1, ve[row], d.coef0) : d.coef0;
+                const double diag = HASV ? fma(a.s1, ve[row], d.coef0) : d.coef0;
                 double s0 = fma(d.wx[1], w[5].x + w[7].x, diag * w[6].x);
                 double s1 = fma(d.wx[1], w[5].y + w[7].y, diag * w[6].y);
 #pragma unroll
@@ -213,7 +216,7 @@ __device__ __forceinline__ void consume_plane(const KptDesc &d, const StepArgs &
             v[0] = c0.x; v[1] = c0.y; v[2] = c1.x; v[3] = c1.y;
         }
     }
-    if (p >= 0) { /* scatter the z terms into the 6 accumulators behind this plane */
+    if (STEADY || p >= 0) { /* scatter the z terms into the 6 accumulators behind this plane */
 #pragma unroll
         for (int r = 1; r <= R; r++)
 #pragma unroll
@@ -224,9 +227,9 @@ __device__ __forceinline__ void consume_plane(const KptDesc &d, const StepArgs &
 
     if (emit && active) {
         double res[4];
-        if (a.s2 != 0.0) {
-            const double2 q0 = *reinterpret_cast<const double2 *>(xtile + r0 * Cfg::XP + 2 * xp);
-            const double2 q1 = *reinterpret_cast<const double2 *>(xtile + (r0 + 1) * Cfg::XP + 2 * xp);
+        if (HASX) {
+            const double2 q0 = *reinterpret_cast<const double2 *>(xtile + xoff); /* r0 * XP + 2 xp */
+            const double2 q1 = *reinterpret_cast<const double2 *>(xtile + xoff + Cfg::XP);
             res[0] = fma(-a.s2, q0.x, acc[(U + 1) % 7][0]);
             res[1] = fma(-a.s2, q0.y, acc[(U + 1) % 7][1]);
             res[2] = fma(-a.s2, q1.x, acc[(U + 1) % 7][2]);
@@ -235,12 +238,13 @@ __device__ __forceinline__ void consume_plane(const KptDesc &d, const StepArgs &
 #pragma unroll
             for (int i = 0; i < 4; i++) res[i] = acc[(U + 1) % 7][i];
         }
-        double *dst = out_row + (size_t)o * plane_doubles;
         if (act0) stg128(dst, res[0], res[1]);
         if (act1) stg128(dst + 2 * d.Nx, res[2], res[3]);
     }
+    if (emit) dst += plane_doubles; /* planes are emitted in order */
 }
 
+template <bool HASV, bool HASX>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ KptDesc d, const StepArgs a, const int nitems,
                   unsigned int *__restrict__ sync_counter, const unsigned int sync_base)
@@ -265,7 +269,9 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
     const int Nx = d.Nx, Ny = d.Ny, Nz = d.Nz;
     const bool xper = (d.bc[0] == 0), yper = (d.bc[1] == 0), zper = (d.bc[2] == 0);
     const size_t plane_doubles = (size_t)2 * Nx * Ny;
-    uint32_t it = 0; /* ring position, continues across work items */
+    /* ring position (stage, parity of its current use), continues across work items */
+    uint32_t rs = 0, rpar = 0;
+#define CHEFSI_RING_ADVANCE() do { if (++rs == (uint32_t)kStages) { rs = 0; rpar ^= 1u; } } while (0)
 
     if (warp >= Cfg::CONSUMER_WARPS) {
         /* ================= producer warpgroup (one elected lane issues the TMA boxes) ================= */
@@ -298,12 +304,12 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
                     if (p < 0) kz += Nz; else if (p >= Nz) kz -= Nz;
                     const int o = p - R;
                     const bool need_y = interior || zper;
-                    const bool need_v = interior && a.veff != nullptr;
-                    const bool need_x = (o >= 0 && o < Nz) && a.s2 != 0.0;
+                    const bool need_v = interior && HASV;
+                    const bool need_x = (o >= 0 && o < Nz) && HASX;
                     if (!need_y && !need_x) continue;
-                    const int s = it % kStages;
+                    const int s = (int)rs;
                     unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
-                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    mbar_wait(&empty[s], rpar ^ 1u);
                     mbar_expect_tx(&landed[s], (need_y ? ybytes : 0u) + (uint32_t)((need_v ? Cfg::VP * TY * 8 : 0) +
                                                                                 (need_x ? Cfg::XP * TY * 8 : 0)));
                     const int xd = 2 * (x0 - R); /* x coordinates of the complex maps are in doubles */
@@ -320,13 +326,12 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
                     }
                     if (need_v) tma_load_4d(stage + Cfg::OFF_V, &maps.veff, x0, y0, p, 0, &landed[s]);
                     if (need_x) tma_load_4d(stage + Cfg::OFF_X, &maps.xprev, 2 * x0, y0, o, n, &landed[s]);
-                    it++;
+                    CHEFSI_RING_ADVANCE();
                 }
             }
         } else if (warp > Cfg::CONSUMER_WARPS) {
             /* ---- fix-up warps: same (item, plane) sequence as the producer lane ---- */
             const int ft = (int)threadIdx.x - (Cfg::CONSUMER_WARPS + 1) * 32; /* 0 .. 95 */
-            uint32_t itf = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int tile = item % (d.ntx * d.nty);
                 const int x0 = tile_origin(tile % d.ntx, TXC, Nx), y0 = tile_origin(tile / d.ntx, TY, Ny);
@@ -337,15 +342,15 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
                     const bool interior = (p >= 0 && p < Nz);
                     const int o = p - R;
                     const bool need_y = interior || zper;
-                    const bool need_x = (o >= 0 && o < Nz) && a.s2 != 0.0;
+                    const bool need_x = (o >= 0 && o < Nz) && HASX;
                     if (!need_y && !need_x) continue;
-                    const int s = itf % kStages;
+                    const int s = (int)rs;
                     unsigned char *stage = ring + (size_t)s * Cfg::STAGE_BYTES;
-                    mbar_wait(&landed[s], (itf / kStages) & 1);
+                    mbar_wait(&landed[s], rpar);
                     if (fix_any && need_y) fix_phases(d, stage, ft, 96, x0, need_l, need_r, wrap_top, wrap_bot);
                     asm volatile("bar.sync 2, 96;" ::: "memory");
                     if (ft == 0) mbar_arrive(&full[s]);
-                    itf++;
+                    CHEFSI_RING_ADVANCE();
                 }
             }
         }
@@ -354,6 +359,10 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
         const int xp = lane & 15;                    /* complex point inside the tile */
         const int r0 = warp * 4 + 2 * (lane >> 4);   /* first of the thread's two rows */
+        /* made opaque so that they live in registers instead of being re-derived from %tid in every plane step */
+        uint32_t yoff = (uint32_t)((r0 + HT) * Cfg::YP + 2 * xp + 2 * R), voff = (uint32_t)(r0 * Cfg::VP + xp);
+        uint32_t xoff = (uint32_t)(r0 * Cfg::XP + 2 * xp), lane0 = (lane == 0) ? 1u : 0u;
+        asm volatile("" : "+r"(yoff), "+r"(voff), "+r"(xoff), "+r"(lane0));
         double in[7][4], acc[7][4];
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int tile = item % (d.ntx * d.nty), n = item / (d.ntx * d.nty);
@@ -364,44 +373,52 @@ stream_kpt_kernel(const __grid_constant__ KptMaps maps, const __grid_constant__ 
             const bool act0 = (gx >= tx * TXC) && (gy >= ty * TY);
             const bool act1 = (gx >= tx * TXC) && (gy + 1 >= ty * TY);
             const bool active = act1;
-            double *out_row = reinterpret_cast<double *>(a.out) + 2 * ((size_t)n * a.ld + (size_t)gy * Nx + gx);
+            double *dst = reinterpret_cast<double *>(a.out) + 2 * ((size_t)n * a.ld + (size_t)gy * Nx + gx); /* output plane 0 */
 #pragma unroll
             for (int u = 0; u < 7; u++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) { in[u][j] = 0.0; acc[u][j] = 0.0; }
 
-#define CHEFSI_STEP(U)                                                                                   \
-    if (p + (U) < Nz + R) {                                                                              \
+#define CHEFSI_STEP(U, STEADY)                                                                           \
+    if ((STEADY) || p + (U) < Nz + R) {                                                                  \
         const int pp = p + (U);                                                                          \
-        const bool zplane = !zper && (pp < 0 || pp >= Nz);   /* Dirichlet z: the plane is zero */        \
-        const bool use_stage = !zplane || (pp - R >= 0 && pp - R < Nz && a.s2 != 0.0);                   \
+        const bool zplane = !(STEADY) && !zper && (pp < 0 || pp >= Nz); /* Dirichlet z: the plane is zero */ \
+        const bool use_stage = (STEADY) || !zplane || (pp - R >= 0 && pp - R < Nz && HASX);              \
         const unsigned char *stage = ring;                                                               \
         int s = 0;                                                                                       \
         if (use_stage) {                                                                                 \
-            s = it % kStages;                                                                            \
+            s = (int)rs;                                                                                 \
             stage = ring + (size_t)s * Cfg::STAGE_BYTES;                                                 \
-            mbar_wait(&full[s], (it / kStages) & 1);                                                     \
+            mbar_wait(&full[s], rpar);                                                                   \
         }                                                                                                \
-        consume_plane<(U)>(d, a, stage, pp, active, act0, act1, xp, r0, out_row,                          \
-                           plane_doubles, in, acc, zplane);                                              \
+        consume_plane<(U), HASV, HASX, (STEADY)>(d, a, stage, pp, active, act0, act1, yoff, voff, xoff, dst, \
+                                                 plane_doubles, in, acc, zplane);                       \
         if (use_stage) {                                                                                 \
             __syncwarp();                                                                                \
-            if (lane == 0) mbar_arrive(&empty[s]);                                                       \
-            it++;                                                                                        \
+            if (lane0) mbar_arrive(&empty[s]);                                                           \
+            CHEFSI_RING_ADVANCE();                                                                       \
         }                                                                                                \
     }
-            for (int p = -R - 1; p < Nz + R; p += 7) {
-                if (p + 0 >= -R) { CHEFSI_STEP(0) }
-                CHEFSI_STEP(1)
-                CHEFSI_STEP(2)
-                CHEFSI_STEP(3)
-                CHEFSI_STEP(4)
-                CHEFSI_STEP(5)
-                CHEFSI_STEP(6)
-            }
+#define CHEFSI_GROUP(STEADY)                                                                             \
+    {                                                                                                    \
+        if ((STEADY) || p + 0 >= -R) { CHEFSI_STEP(0, STEADY) }                                          \
+        CHEFSI_STEP(1, STEADY)                                                                           \
+        CHEFSI_STEP(2, STEADY)                                                                           \
+        CHEFSI_STEP(3, STEADY)                                                                           \
+        CHEFSI_STEP(4, STEADY)                                                                           \
+        CHEFSI_STEP(5, STEADY)                                                                           \
+        CHEFSI_STEP(6, STEADY)                                                                           \
+    }
+            /* groups whose seven planes all lie in [R, Nz) take a body without the boundary case distinctions */
+            int p = -R - 1;
+            for (; p < R && p < Nz + R; p += 7) CHEFSI_GROUP(false)
+            for (; p + 6 < Nz; p += 7) CHEFSI_GROUP(true)
+            for (; p < Nz + R; p += 7) CHEFSI_GROUP(false)
+#undef CHEFSI_GROUP
 #undef CHEFSI_STEP
         }
     }
+#undef CHEFSI_RING_ADVANCE
 }
 
 /* ---- host side ---------------------------------------------------------------------------- */
@@ -468,7 +485,10 @@ int launch_stencil_stream_kpt(chefsi_ctx *ctx, const StepArgs &a)
         chefsi_fail(ctx, "cuTensorMapEncodeTiled failed (k-point)");
         return -1;
     }
-    auto kern = stream_kpt_kernel;
+    /* with / without the Veff tile and the xprev tile: compile-time, so the plane step carries no selects for them */
+    const bool hv = a.veff != nullptr, hx = a.s2 != 0.0;
+    auto kern = hv ? (hx ? stream_kpt_kernel<true, true> : stream_kpt_kernel<true, false>)
+                   : (hx ? stream_kpt_kernel<false, true> : stream_kpt_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) { chefsi_fail(ctx, "cudaFuncSetAttribute(k-point stream): %s", cudaGetErrorString(e)); return -1; }
     const int grid = (int)((nitems < ctx->num_sms) ? nitems : ctx->num_sms);
