@@ -35,20 +35,23 @@ ncols = [v[0] for v in info]
 peerY = [0 if r == rank else bp.peers.address(info[r][1]) for r in range(world)]
 Q = np.ascontiguousarray(np.random.default_rng(0).standard_normal((nc, ncol)))
 X = torch.empty((nc, g.Nd), dtype=torch.float64).pin_memory()
-t = torch.zeros(2, dtype=torch.float64, device="cuda")
+t = torch.zeros(3, dtype=torch.float64, device="cuda")
 for rep in range(3):
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter(); Hp, Mp = rank_project(ctx, False, rank, ncols, peerY); t1 = time.perf_counter()
     dist.barrier()
     t2 = time.perf_counter(); rank_rotate(ctx, False, rank, ncols, peerY, None, Q, X.numpy()); t3 = time.perf_counter()
-    t[0], t[1] = t1 - t0, t3 - t2
+    dist.barrier()
+    t4 = time.perf_counter(); rank_project(ctx, False, rank, ncols, peerY, share=True); t5 = time.perf_counter()
+    t[0], t[1], t[2] = t1 - t0, t3 - t2, t5 - t4
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     fl = 2.0 * g.Nd * ncol * ncol
     chk = float(np.abs(Mp[0, first:first + 1] - y[0] @ y[0]).max() / abs(y[0] @ y[0]))
     print(f"{world} ranks, {n}^3 x {ncol}: project (H Y + 2 products + D2H of the blocks) {1e3*t[0].item():.1f} ms = "
           f"{2*fl/t[0].item()/1e12:.1f} TFLOP/s over all ranks; rotate (product + D2H of X) {1e3*t[1].item():.1f} ms = "
-          f"{fl/t[1].item()/1e12:.1f} TFLOP/s; Mp check {chk:.1e}", flush=True)
+          f"{fl/t[1].item()/1e12:.1f} TFLOP/s; Mp check {chk:.1e}; project with every Hermitian block pair formed once "
+          f"{1e3*t[2].item():.1f} ms", flush=True)
 dist.barrier()
 bp.close(); ctx.close()
 dist.destroy_process_group()

@@ -54,14 +54,42 @@ def _ptr_array(addrs):
     return arr
 
 
-def rank_project(ctx, is_complex, rank, ncols, peerY):
-    """Column block `rank` of (Hp, Mp): numpy arrays [ncols[rank], Ns] (row n = column n of the block: column-major)."""
+def rank_forms_block(J: int, rank: int, nranks: int) -> bool:
+    """Hp and Mp are Hermitian, so each off-diagonal block pair is formed once: rank I forms block (J, I) -- rows of rank J,
+    its own columns -- for the floor((P - 1) / 2) ranks J that follow it cyclically, and for even P the lower rank of an
+    antipodal pair forms that block (the rule of ``chefsi_rank_forms_block`` in ranks.cu, restated here for the host)."""
+    if J == rank:
+        return True
+    dist = (J - rank) % nranks
+    return 2 * dist < nranks or (2 * dist == nranks and rank < J)
+
+
+def assemble_hermitian(blocks, ncols):
+    """Full column-major matrix (as a C-ordered [Ns, Ns] array G with G[col, row]) from the per-rank column blocks of a
+    shared projection (``rank_project(..., share=True)``): block (J, I) that rank I did not form is the conjugate
+    transpose of block (I, J), which rank J formed."""
+    P = len(ncols)
+    G = np.ascontiguousarray(np.concatenate([np.asarray(b) for b in blocks if b.shape[0] > 0]))
+    off = np.concatenate([[0], np.cumsum(ncols)]).astype(int)
+    for I in range(P):
+        for J in range(P):
+            if ncols[I] == 0 or ncols[J] == 0 or rank_forms_block(J, I, P):
+                continue
+            # G[cols of I, rows of J] = conj(G[cols of J, rows of I])^T
+            G[off[I]:off[I + 1], off[J]:off[J + 1]] = np.conj(G[off[J]:off[J + 1], off[I]:off[I + 1]]).T
+    return G
+
+
+def rank_project(ctx, is_complex, rank, ncols, peerY, share=False):
+    """Column block `rank` of (Hp, Mp): numpy arrays [ncols[rank], Ns] (row n = column n of the block: column-major).
+    share: form only this rank's share of the Hermitian block pairs (``rank_forms_block``); the rest comes back as zeros
+    and is mirrored by ``assemble_hermitian`` after the all-gather."""
     ns, nc = int(sum(ncols)), int(ncols[rank])
     dt = np.complex128 if is_complex else np.float64
     Hp, Mp = np.zeros((nc, ns), dtype=dt), np.zeros((nc, ns), dtype=dt)
     nc_arr = (C.c_int * len(ncols))(*[int(v) for v in ncols])
-    ctx._check(ctx._lib.chefsi_rank_project(ctx._h, int(is_complex), len(ncols), rank, nc_arr, _ptr_array(peerY),
-                                            _addr(Hp), _addr(Mp), ns))
+    fn = ctx._lib.chefsi_rank_project_shared if share else ctx._lib.chefsi_rank_project
+    ctx._check(fn(ctx._h, int(is_complex), len(ncols), rank, nc_arr, _ptr_array(peerY), _addr(Hp), _addr(Mp), ns))
     return Hp, Mp
 
 
@@ -125,13 +153,13 @@ class BandParallelSubspace:
         peerT = [0 if r == rank or ncols[r] == 0 or not is_complex else self.peers.address(info[r][2]) for r in range(self.world)]
         ns, c0 = int(sum(ncols)), int(sum(ncols[:rank]))
         self.dist.barrier(group=self.group)                       # every rank's Y is resident
-        Hp_blk, Mp_blk = rank_project(ctx, is_complex, rank, ncols, peerY)
+        Hp_blk, Mp_blk = rank_project(ctx, is_complex, rank, ncols, peerY, share=True)  # each Hermitian block pair once
         blocks = self._gather_objects((Hp_blk, Mp_blk))           # Ns x nc blocks: small next to the orbitals
         dt = np.complex128 if is_complex else np.float64
         lam, Q = np.zeros(ns), np.zeros((ns, ns), dtype=dt)
         if rank == 0:                                             # eigenSolver.c:1262-1375: rank 0 solves, then MPI_Bcast
-            Hp = np.ascontiguousarray(np.concatenate([b[0] for b in blocks]))
-            Mp = np.ascontiguousarray(np.concatenate([b[1] for b in blocks]))
+            Hp = assemble_hermitian([b[0] for b in blocks], ncols)
+            Mp = assemble_hermitian([b[1] for b in blocks], ncols)
             lam, Q = ctx.DP_Solve_Generalized_EigenProblem(ns, Hp, Mp)
         self._broadcast_array(lam)
         self._broadcast_array(Q)

@@ -125,23 +125,41 @@ extern "C" int chefsi_ipc_close(chefsi_ctx_t *ctx, void *dptr)
     return 0;
 }
 
+/* Hp and Mp are Hermitian, so every off-diagonal block pair (J, I) / (I, J) has to be formed only once.  Rank I forms
+ * block (J, I) -- rows of rank J, its own columns -- when J is one of the floor((P - 1) / 2) ranks that follow it
+ * cyclically, and for even P the lower rank of each antipodal pair forms that block: a balanced share of
+ * (P + 1) / 2 instead of P blocks per rank (the diagonal one counts half: upper-triangle tiles, mirrored).  The host
+ * mirrors the others after the all-gather (sparc_b200/band_parallel.py: assemble_hermitian). */
+static bool rank_forms_block(int J, int I, int P)
+{
+    if (J == I) return true;
+    const int dist = ((J - I) % P + P) % P;
+    return 2 * dist < P || (2 * dist == P && I < J);
+}
+
 /* column block `rank` of Mp = Y^H Y and Hp = Y^H H Y: rows = all Ns columns of all ranks, columns = this rank's.
  * peerY[J]: device address of rank J's resident block in THIS process (chefsi_ipc_open, or chefsi_resident_ptr when
- * the ranks share a process); entry `rank` is ignored.  Hp_blk / Mp_blk: host, Ns x ncols[rank], column-major, ld = ldp. */
-extern "C" int chefsi_rank_project(chefsi_ctx_t *ctx, int is_complex, int nranks, int rank, const int *ncols, void *const *peerY,
-                                   void *Hp_blk, void *Mp_blk, size_t ldp)
+ * the ranks share a process); entry `rank` is ignored.  Hp_blk / Mp_blk: host, Ns x ncols[rank], column-major, ld = ldp.
+ * share != 0: only the blocks rank_forms_block assigns to this rank are formed, the others are returned as zeros. */
+static int rank_project_impl(chefsi_ctx_t *ctx, int is_complex, int nranks, int rank, const int *ncols, void *const *peerY,
+                             void *Hp_blk, void *Mp_blk, size_t ldp, int share)
 {
     if (!ctx || !Hp_blk || !Mp_blk) return 1;
     int ncol = 0, c0I = 0;
     if (check_ranks(ctx, "rank_project", is_complex, nranks, rank, ncols, &ncol, &c0I)) return 1;
     if (ldp < (size_t)ncol) return chefsi_fail(ctx, "rank_project: ldp smaller than the total number of columns");
     for (int J = 0; J < nranks; J++)
-        if (J != rank && ncols[J] > 0 && (!peerY || !peerY[J])) return chefsi_fail(ctx, "rank_project: no address for rank %d's block", J);
+        if (J != rank && ncols[J] > 0 && (!share || rank_forms_block(J, rank, nranks)) && (!peerY || !peerY[J]))
+            return chefsi_fail(ctx, "rank_project: no address for rank %d's block", J);
     CHEFSI_CUDA(ctx, cudaSetDevice(ctx->device));
     const int words = is_complex ? 2 : 1, ncI = ncols[rank];
     const size_t esz = sizeof(double) * words;
     RankBufs *rb = rank_bufs(ctx, (size_t)ncol * ncI * esz);
     if (!rb) return chefsi_fail(ctx, "rank_project: no device memory for the %d x %d blocks", ncol, ncI);
+    if (share) {
+        CHEFSI_CUDA(ctx, cudaMemsetAsync(rb->d[0], 0, (size_t)ncol * ncI * esz, ctx->stream));
+        CHEFSI_CUDA(ctx, cudaMemsetAsync(rb->d[1], 0, (size_t)ncol * ncI * esz, ctx->stream));
+    }
     /* W_I = H Y_I (c = 0): local */
     if (is_complex ? chefsi_hamiltonian_mult_kpt_device(ctx, ncI, 0.0, ctx->d_res_Y, ctx->d_res_W)
                    : chefsi_hamiltonian_mult_device(ctx, ncI, 0.0, (const double *)ctx->d_res_Y, (double *)ctx->d_res_W))
@@ -165,9 +183,12 @@ extern "C" int chefsi_rank_project(chefsi_ctx_t *ctx, int is_complex, int nranks
             double *Cblk = (which ? dHp : dMp) + pass;
             int c0J = 0;
             for (int J = 0; J < nranks; c0J += ncols[J], J++) {
-                if (ncols[J] <= 0) continue;
+                if (ncols[J] <= 0 || (share && !rank_forms_block(J, rank, nranks))) continue;
                 const double *A = J == rank ? Yi : (const double *)peerY[J]; /* another rank's block: IPC / peer memory */
-                const int nl = launch_gemm_tn(ctx, A, ldv, B, ldv, ncols[J], ncI, K, 1.0, Cblk + (size_t)c0J * words, ncol, words);
+                /* the diagonal block is a Hermitian product of its own: upper-triangle tiles, mirrored (real part
+                   symmetric, imaginary part antisymmetric) */
+                const int sym = (share && J == rank) ? (pass == 0 ? +1 : -1) : 0;
+                const int nl = launch_gemm_tn(ctx, A, ldv, B, ldv, ncols[J], ncI, K, 1.0, Cblk + (size_t)c0J * words, ncol, words, sym);
                 if (nl < 0) return 1;
                 ctx->stats.kernel_launches += nl;
             }
@@ -178,6 +199,25 @@ extern "C" int chefsi_rank_project(chefsi_ctx_t *ctx, int is_complex, int nranks
     CHEFSI_CUDA(ctx, cudaMemcpy2DAsync(Hp_blk, ldp * esz, dHp, w, w, ncI, cudaMemcpyDeviceToHost, ctx->stream));
     CHEFSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+extern "C" int chefsi_rank_project(chefsi_ctx_t *ctx, int is_complex, int nranks, int rank, const int *ncols, void *const *peerY,
+                                   void *Hp_blk, void *Mp_blk, size_t ldp)
+{
+    return rank_project_impl(ctx, is_complex, nranks, rank, ncols, peerY, Hp_blk, Mp_blk, ldp, 0);
+}
+
+/* the same with every Hermitian block pair formed once: blocks of other ranks' shares come back as zeros */
+extern "C" int chefsi_rank_project_shared(chefsi_ctx_t *ctx, int is_complex, int nranks, int rank, const int *ncols,
+                                          void *const *peerY, void *Hp_blk, void *Mp_blk, size_t ldp)
+{
+    return rank_project_impl(ctx, is_complex, nranks, rank, ncols, peerY, Hp_blk, Mp_blk, ldp, 1);
+}
+
+/* 1 when rank `rank` of `nranks` forms block (rows of rank J, its own columns) in chefsi_rank_project_shared */
+extern "C" int chefsi_rank_forms_block(int J, int rank, int nranks)
+{
+    return (nranks > 0 && J >= 0 && J < nranks && rank >= 0 && rank < nranks && rank_forms_block(J, rank, nranks)) ? 1 : 0;
 }
 
 /* complex data: T_I = i Y_I, which the other ranks read next to Y_I (Y Q = Y Q_r + (i Y) Q_i on the real views) */

@@ -60,6 +60,12 @@ def test_rank_products_two_contexts_one_process(port, complex_, split):
             # numpy [n, m] = element (row m, column c0 + n) of the matrix
             assert rel_fro(Mp, Mp_want[:, c0:c0 + split[r]].T) < TOL
             assert rel_fro(Hp, Hp_want[:, c0:c0 + split[r]].T) < TOL
+        # every Hermitian block pair formed by one rank only, the rest mirrored on the host after the "all-gather"
+        from sparc_b200.band_parallel import assemble_hermitian
+        shared = [rank_project(ctxs[r], complex_, r, split, peerY, share=True) for r in range(2)]
+        assert not shared[1][0][:, :split[0]].any() and not shared[1][1][:, :split[0]].any()   # rank 1 leaves block (0, 1) to rank 0
+        assert rel_fro(assemble_hermitian([sb[1] for sb in shared], split), Mp_want.T) < TOL
+        assert rel_fro(assemble_hermitian([sb[0] for sb in shared], split), Hp_want.T) < TOL
         for c in ctxs:
             c._check(c._lib.chefsi_rank_rotate_prepare(c._h, int(complex_)))
         peerT = addr(2)

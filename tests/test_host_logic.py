@@ -57,3 +57,33 @@ def test_projector_tables_are_consistent():
     assert pr.n_img >= 2  # atom near the x face: its periodic image reaches into the cell
     assert pr.pos_off[-1] == pr.grid_pos.size and pr.chi_off[-1] == pr.chi.size
     assert (pr.grid_pos >= 0).all() and (pr.grid_pos < g.Nd).all()
+
+
+def test_shared_hermitian_projection_blocks_cover_every_pair_once_and_mirror_back():
+    """Band-parallel projection with every Hermitian block pair formed once (sparc_b200/band_parallel.py, the rule of
+    chefsi_rank_forms_block in ranks.cu): each unordered pair of ranks has exactly one owner, the per-rank share is
+    balanced, and assemble_hermitian rebuilds the full matrix from the zero-padded column blocks."""
+    import numpy as np
+    from sparc_b200.band_parallel import assemble_hermitian, rank_forms_block
+    for P in range(1, 10):
+        for I in range(P):
+            assert rank_forms_block(I, I, P)
+            for J in range(I + 1, P):
+                assert rank_forms_block(J, I, P) != rank_forms_block(I, J, P)       # exactly one of the two ranks
+        share = [sum(rank_forms_block(J, I, P) for J in range(P)) for I in range(P)]
+        assert max(share) - min(share) <= 1 and sum(share) == P * (P + 1) // 2
+    rng = np.random.default_rng(3)
+    for ncols, cplx in (([3, 2], False), ([2, 0, 3, 1], True), ([1, 1, 1, 1, 1], True), ([4, 3, 5], False)):
+        ns, P = sum(ncols), len(ncols)
+        A = rng.standard_normal((ns, ns)) + (1j * rng.standard_normal((ns, ns)) if cplx else 0)
+        H = A + A.conj().T                                                      # H[row, col]
+        G = np.ascontiguousarray(H.T)                                           # column-major: G[col, row]
+        off = np.concatenate([[0], np.cumsum(ncols)])
+        blocks = []
+        for I in range(P):
+            b = G[off[I]:off[I + 1]].copy()
+            for J in range(P):
+                if not rank_forms_block(J, I, P):
+                    b[:, off[J]:off[J + 1]] = 0
+            blocks.append(b)
+        assert np.array_equal(assemble_hermitian(blocks, ncols), G)
