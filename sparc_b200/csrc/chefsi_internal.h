@@ -217,6 +217,15 @@ int launch_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q
                    size_t ldc, int accumulate);
 /* ranks.cu */
 void rank_state_destroy(chefsi_ctx *ctx);
+/* Hp and Mp are Hermitian: of every off-diagonal block pair (J, I) / (I, J) of a column-block split over P ranks or devices
+   only one is formed.  Owner I forms block (J, I) -- rows of J, its own columns -- for the floor((P - 1) / 2) owners J
+   that follow it cyclically; for even P the lower owner of an antipodal pair forms that block. */
+inline bool rank_forms_block(int J, int I, int P)
+{
+    if (J == I) return true;
+    const int dist = ((J - I) % P + P) % P;
+    return 2 * dist < P || (2 * dist == P && I < J);
+}
 /* gradient.cu */
 int launch_gradient(chefsi_ctx *ctx, const void *x, void *out, int ncol, int dir, double c, double kdir, bool is_complex);
 int launch_rot90(chefsi_ctx *ctx, const void *in, void *out, size_t n, size_t ld, int ncol, double s);

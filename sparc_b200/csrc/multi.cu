@@ -450,7 +450,9 @@ int multi_subspace_project(chefsi_ctx *lead, const void *Y, size_t ldy, int ncol
         return cudaStreamSynchronize(k->stream) == cudaSuccess ? 0 : chefsi_fail(k, "subspace_project: H Y failed");
     });
     if (rc) return rc;
-    /* phase 2 (per device I): column block I of Mp and Hp; the A operand Y_J is read through peer memory */
+    /* phase 2 (per device I): column block I of Mp and Hp; the A operand Y_J is read through peer memory.  Both matrices
+       are Hermitian: of every off-diagonal block pair only one is formed (rank_forms_block), the diagonal blocks use
+       upper-triangle tiles, and the host mirrors the rest below */
     rc = multi_parallel(lead, [&](int I) {
         chefsi_ctx *k = ms->kids[I];
         int c0I, ncI;
@@ -476,9 +478,10 @@ int multi_subspace_project(chefsi_ctx *lead, const void *Y, size_t ldy, int ncol
                 for (int J = 0; J < n; J++) {
                     int c0J, ncJ;
                     kid_range(ncol, n, J, &c0J, &ncJ);
-                    if (ncJ <= 0) continue;
+                    if (ncJ <= 0 || !rank_forms_block(J, I, n)) continue;
                     const double *A = (const double *)ms->kids[J]->d_res_Y; /* peer pointer when J != I */
-                    const int nl = launch_gemm_tn(k, A, ms->kids[J]->ld * words, B, ldv, ncJ, ncI, K, 1.0, Cblk + (size_t)c0J * words, ncol, words);
+                    const int sym = J == I ? (pass == 0 ? +1 : -1) : 0; /* real part symmetric, imaginary part antisymmetric */
+                    const int nl = launch_gemm_tn(k, A, ms->kids[J]->ld * words, B, ldv, ncJ, ncI, K, 1.0, Cblk + (size_t)c0J * words, ncol, words, sym);
                     if (nl < 0) return 1;
                     k->stats.kernel_launches += nl;
                 }
@@ -493,6 +496,24 @@ int multi_subspace_project(chefsi_ctx *lead, const void *Y, size_t ldy, int ncol
         return 0;
     });
     if (rc) return rc;
+    /* block (rows of J, columns of I) that device I left out = conjugate transpose of block (rows of I, columns of J) */
+    for (int I = 0; I < n; I++)
+        for (int J = 0; J < n; J++) {
+            if (rank_forms_block(J, I, n)) continue;
+            int c0I, ncI, c0J, ncJ;
+            kid_range(ncol, n, I, &c0I, &ncI);
+            kid_range(ncol, n, J, &c0J, &ncJ);
+            for (int which = 0; which < 2; which++) {
+                double *M = (double *)(which ? Hp : Mp);
+                for (int c = c0I; c < c0I + ncI; c++)
+                    for (int r = c0J; r < c0J + ncJ; r++) {
+                        double *dst = M + ((size_t)c * ldp + r) * words;
+                        const double *src = M + ((size_t)r * ldp + c) * words;
+                        dst[0] = src[0];
+                        if (is_complex) dst[1] = -src[1];
+                    }
+            }
+        }
     ms->sub_ncol = ncol;
     ms->sub_complex = is_complex;
     return 0;

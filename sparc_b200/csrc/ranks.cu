@@ -129,14 +129,8 @@ extern "C" int chefsi_ipc_close(chefsi_ctx_t *ctx, void *dptr)
  * block (J, I) -- rows of rank J, its own columns -- when J is one of the floor((P - 1) / 2) ranks that follow it
  * cyclically, and for even P the lower rank of each antipodal pair forms that block: a balanced share of
  * (P + 1) / 2 instead of P blocks per rank (the diagonal one counts half: upper-triangle tiles, mirrored).  The host
- * mirrors the others after the all-gather (sparc_b200/band_parallel.py: assemble_hermitian). */
-static bool rank_forms_block(int J, int I, int P)
-{
-    if (J == I) return true;
-    const int dist = ((J - I) % P + P) % P;
-    return 2 * dist < P || (2 * dist == P && I < J);
-}
-
+ * mirrors the others after the all-gather (sparc_b200/band_parallel.py: assemble_hermitian).  The rule itself:
+ * rank_forms_block, chefsi_internal.h. */
 /* column block `rank` of Mp = Y^H Y and Hp = Y^H H Y: rows = all Ns columns of all ranks, columns = this rank's.
  * peerY[J]: device address of rank J's resident block in THIS process (chefsi_ipc_open, or chefsi_resident_ptr when
  * the ranks share a process); entry `rank` is ignored.  Hp_blk / Mp_blk: host, Ns x ncols[rank], column-major, ld = ldp.
