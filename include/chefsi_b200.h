@@ -237,13 +237,16 @@ int chefsi_ipc_open(chefsi_ctx_t *ctx, const void *handle64, void **dptr);
 int chefsi_ipc_close(chefsi_ctx_t *ctx, void *dptr);
 int chefsi_rank_project(chefsi_ctx_t *ctx, int is_complex, int nranks, int rank, const int *ncols, void *const *peerY,
                         void *Hp_blk, void *Mp_blk, size_t ldp);
-/* Hp and Mp are Hermitian: with chefsi_rank_project_shared every off-diagonal block pair is formed by one rank only
- * (rank I forms block (J, I) for the floor((P-1)/2) ranks J that follow it cyclically; for even P the lower rank of an
- * antipodal pair forms that block; the diagonal block uses upper-triangle tiles), the other blocks come back as zeros and
- * the caller mirrors them after the all-gather.  chefsi_rank_forms_block tells which. */
+/* Hp and Mp are Hermitian: with chefsi_rank_project_shared only one element of every mirrored pair is formed (rank I forms
+ * block (J, I) for the ranks J that follow it cyclically at a distance below P / 2; for even P the two ranks of an antipodal
+ * pair share that block: the lower one forms the first half of its columns, the upper one the rows that mirror the other
+ * half; the diagonal block uses upper-triangle tiles), the other elements come back as zeros and the caller mirrors them
+ * after the all-gather.  chefsi_rank_block_part tells which part of block (rows of rank J, columns of `rank`) `rank` forms:
+ * local rows [r0, r1) x columns [c0, c1); chefsi_rank_forms_block: whether that part is non-empty for equal column counts. */
 int chefsi_rank_project_shared(chefsi_ctx_t *ctx, int is_complex, int nranks, int rank, const int *ncols, void *const *peerY,
                                void *Hp_blk, void *Mp_blk, size_t ldp);
 int chefsi_rank_forms_block(int J, int rank, int nranks);
+void chefsi_rank_block_part(int J, int rank, int nranks, int ncJ, int ncI, int *r0, int *r1, int *c0, int *c1);
 int chefsi_rank_rotate_prepare(chefsi_ctx_t *ctx, int is_complex);
 int chefsi_rank_rotate(chefsi_ctx_t *ctx, int is_complex, int nranks, int rank, const int *ncols, void *const *peerY,
                        void *const *peerT, const void *Q_blk, size_t ldq, void *X_blk, size_t ldx);

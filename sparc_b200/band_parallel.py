@@ -54,35 +54,46 @@ def _ptr_array(addrs):
     return arr
 
 
-def rank_forms_block(J: int, rank: int, nranks: int) -> bool:
-    """Hp and Mp are Hermitian, so each off-diagonal block pair is formed once: rank I forms block (J, I) -- rows of rank J,
-    its own columns -- for the floor((P - 1) / 2) ranks J that follow it cyclically, and for even P the lower rank of an
-    antipodal pair forms that block (the rule of ``chefsi_rank_forms_block`` in ranks.cu, restated here for the host)."""
+def rank_block_part(J: int, rank: int, nranks: int, ncJ: int, ncI: int):
+    """Hp and Mp are Hermitian, so of every mirrored element pair only one is formed.  Rank I forms block (J, I) -- rows of
+    rank J, its own columns -- for the ranks J that follow it cyclically at a distance below P / 2; for even P the block at
+    distance P / 2 is shared by its two ranks: the lower one forms the first half of its columns, the upper one the rows
+    that mirror the other half.  Returns the part of block (J, rank) that `rank` forms as local (r0, r1, c0, c1): rows
+    [r0, r1) x columns [c0, c1), empty when r1 <= r0 or c1 <= c0 (the rule of ``rank_block_part`` in chefsi_internal.h,
+    restated here for the host)."""
     if J == rank:
-        return True
+        return 0, ncJ, 0, ncI
     dist = (J - rank) % nranks
-    return 2 * dist < nranks or (2 * dist == nranks and rank < J)
+    if 2 * dist < nranks:
+        return 0, ncJ, 0, ncI
+    if 2 * dist == nranks:
+        return (0, ncJ, 0, ncI // 2) if rank < J else (ncJ // 2, ncJ, 0, ncI)
+    return 0, 0, 0, 0
 
 
 def assemble_hermitian(blocks, ncols):
     """Full column-major matrix (as a C-ordered [Ns, Ns] array G with G[col, row]) from the per-rank column blocks of a
-    shared projection (``rank_project(..., share=True)``): block (J, I) that rank I did not form is the conjugate
-    transpose of block (I, J), which rank J formed."""
+    shared projection (``rank_project(..., share=True)``): every element that its column's rank did not form is the
+    conjugate of its mirror image, which the other rank formed."""
     P = len(ncols)
     G = np.ascontiguousarray(np.concatenate([np.asarray(b) for b in blocks if b.shape[0] > 0]))
     off = np.concatenate([[0], np.cumsum(ncols)]).astype(int)
     for I in range(P):
         for J in range(P):
-            if ncols[I] == 0 or ncols[J] == 0 or rank_forms_block(J, I, P):
+            if J == I or ncols[I] == 0 or ncols[J] == 0:
                 continue
-            # G[cols of I, rows of J] = conj(G[cols of J, rows of I])^T
-            G[off[I]:off[I + 1], off[J]:off[J + 1]] = np.conj(G[off[J]:off[J + 1], off[I]:off[I + 1]]).T
+            r0, r1, c0, c1 = rank_block_part(J, I, P, int(ncols[J]), int(ncols[I]))
+            formed = np.zeros((ncols[I], ncols[J]), dtype=bool)      # [column of I, row of J], the layout of G
+            formed[c0:c1, r0:r1] = True
+            mirror = np.conj(G[off[J]:off[J + 1], off[I]:off[I + 1]]).T   # [column of I, row of J] from rank J's block (I, J)
+            blk = G[off[I]:off[I + 1], off[J]:off[J + 1]]
+            blk[~formed] = mirror[~formed]
     return G
 
 
 def rank_project(ctx, is_complex, rank, ncols, peerY, share=False):
     """Column block `rank` of (Hp, Mp): numpy arrays [ncols[rank], Ns] (row n = column n of the block: column-major).
-    share: form only this rank's share of the Hermitian block pairs (``rank_forms_block``); the rest comes back as zeros
+    share: form only this rank's share of the Hermitian element pairs (``rank_block_part``); the rest comes back as zeros
     and is mirrored by ``assemble_hermitian`` after the all-gather."""
     ns, nc = int(sum(ncols)), int(ncols[rank])
     dt = np.complex128 if is_complex else np.float64

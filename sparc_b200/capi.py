@@ -21,7 +21,7 @@ EXPORTS = (
     "chefsi_gradient_mult", "chefsi_gradient_mult_kpt", "chefsi_gradient_mult_device",
     "chefsi_lanczos", "chefsi_lanczos_kpt", "chefsi_subspace_eig", "chefsi_subspace_eig_kpt", "chefsi_band_store", "chefsi_density_accumulate", "chefsi_density_accumulate_kpt", "chefsi_poisson_aar", "chefsi_subspace_reserve", "chefsi_subspace_reserve_kpt", "chefsi_subspace_project_kpt", "chefsi_subspace_rotate_kpt", "chefsi_subspace_project", "chefsi_subspace_rotate",
     "chefsi_rank_load", "chefsi_resident_ptr", "chefsi_ipc_export", "chefsi_ipc_open", "chefsi_ipc_close",
-    "chefsi_rank_project", "chefsi_rank_project_shared", "chefsi_rank_forms_block", "chefsi_rank_rotate_prepare", "chefsi_rank_rotate",
+    "chefsi_rank_project", "chefsi_rank_project_shared", "chefsi_rank_forms_block", "chefsi_rank_block_part", "chefsi_rank_rotate_prepare", "chefsi_rank_rotate",
     "chefsi_device_ld",
     "chefsi_chebyshev_filter_device", "chefsi_chebyshev_filter_kpt_device",
     "chefsi_hamiltonian_mult_device", "chefsi_hamiltonian_mult_kpt_device",
@@ -100,6 +100,8 @@ def load_library() -> C.CDLL:
     lib.chefsi_rank_project.argtypes = [vp, i, i, i, ip, C.POINTER(C.c_void_p), vp, vp, sz]
     lib.chefsi_rank_project_shared.argtypes = [vp, i, i, i, ip, C.POINTER(C.c_void_p), vp, vp, sz]
     lib.chefsi_rank_forms_block.argtypes = [i, i, i]
+    lib.chefsi_rank_block_part.argtypes = [i, i, i, i, i, ip, ip, ip, ip]
+    lib.chefsi_rank_block_part.restype = None
     lib.chefsi_rank_rotate_prepare.argtypes = [vp, i]
     lib.chefsi_rank_rotate.argtypes = [vp, i, i, i, ip, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), vp, sz, vp, sz]
     lib.chefsi_lanczos.argtypes = [vp, dp, d, d, i, C.POINTER(C.c_double), C.POINTER(C.c_double), ip]

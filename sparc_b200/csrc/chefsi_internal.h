@@ -218,13 +218,30 @@ int launch_gemm_nn(chefsi_ctx *ctx, const double *A, size_t lda, const double *Q
 /* ranks.cu */
 void rank_state_destroy(chefsi_ctx *ctx);
 /* Hp and Mp are Hermitian: of every off-diagonal block pair (J, I) / (I, J) of a column-block split over P ranks or devices
-   only one is formed.  Owner I forms block (J, I) -- rows of J, its own columns -- for the floor((P - 1) / 2) owners J
-   that follow it cyclically; for even P the lower owner of an antipodal pair forms that block. */
+   only one element of each mirrored pair is formed.  Owner I forms block (J, I) -- rows of J, its own columns -- for the
+   owners J that follow it cyclically at a distance below P / 2; for even P the block at distance P / 2 is shared by its
+   two owners: the lower one (I < J) forms the first half of its columns, the upper one the rows of the lower owner's
+   block that mirror the other half.  rank_block_part gives the part of block (J, I) that owner I forms as local
+   rows [r0, r1) x columns [c0, c1) (empty: r1 <= r0 or c1 <= c0); every owner forms (P + 1) / 2 blocks' worth. */
+inline void rank_block_part(int J, int I, int P, int ncJ, int ncI, int *r0, int *r1, int *c0, int *c1)
+{
+    *r0 = 0; *r1 = ncJ; *c0 = 0; *c1 = ncI;
+    if (J == I) return;
+    const int dist = ((J - I) % P + P) % P;
+    if (2 * dist < P) return;
+    if (2 * dist == P) {
+        if (I < J) *c1 = ncI / 2;   /* lower owner: columns [0, ncI / 2) of block (J, I) */
+        else *r0 = ncJ / 2;         /* upper owner: rows [ncJ / 2, ncJ) of block (J, I), J being the lower one */
+        return;
+    }
+    *r1 = 0;
+}
+/* block-level form of the rule: does owner I form anything of block (J, I)? */
 inline bool rank_forms_block(int J, int I, int P)
 {
     if (J == I) return true;
     const int dist = ((J - I) % P + P) % P;
-    return 2 * dist < P || (2 * dist == P && I < J);
+    return 2 * dist <= P;
 }
 /* gradient.cu */
 int launch_gradient(chefsi_ctx *ctx, const void *x, void *out, int ncol, int dir, double c, double kdir, bool is_complex);

@@ -478,10 +478,15 @@ int multi_subspace_project(chefsi_ctx *lead, const void *Y, size_t ldy, int ncol
                 for (int J = 0; J < n; J++) {
                     int c0J, ncJ;
                     kid_range(ncol, n, J, &c0J, &ncJ);
-                    if (ncJ <= 0 || !rank_forms_block(J, I, n)) continue;
+                    if (ncJ <= 0) continue;
+                    int r0, r1, q0, q1; /* the part of block (J, I) device I forms */
+                    rank_block_part(J, I, n, ncJ, ncI, &r0, &r1, &q0, &q1);
+                    if (r1 <= r0 || q1 <= q0) continue;
+                    const size_t lda = ms->kids[J]->ld * words;
                     const double *A = (const double *)ms->kids[J]->d_res_Y; /* peer pointer when J != I */
                     const int sym = J == I ? (pass == 0 ? +1 : -1) : 0; /* real part symmetric, imaginary part antisymmetric */
-                    const int nl = launch_gemm_tn(k, A, ms->kids[J]->ld * words, B, ldv, ncJ, ncI, K, 1.0, Cblk + (size_t)c0J * words, ncol, words, sym);
+                    const int nl = launch_gemm_tn(k, A + (size_t)r0 * lda, lda, B + (size_t)q0 * ldv, ldv, r1 - r0, q1 - q0, K, 1.0,
+                                                  Cblk + ((size_t)q0 * ncol + c0J + r0) * words, ncol, words, sym);
                     if (nl < 0) return 1;
                     k->stats.kernel_launches += nl;
                 }
@@ -496,19 +501,22 @@ int multi_subspace_project(chefsi_ctx *lead, const void *Y, size_t ldy, int ncol
         return 0;
     });
     if (rc) return rc;
-    /* block (rows of J, columns of I) that device I left out = conjugate transpose of block (rows of I, columns of J) */
+    /* every element (rows of J, columns of I) that device I left out = conjugate of its mirror image, which device J formed */
     for (int I = 0; I < n; I++)
         for (int J = 0; J < n; J++) {
-            if (rank_forms_block(J, I, n)) continue;
-            int c0I, ncI, c0J, ncJ;
+            if (J == I) continue;
+            int c0I, ncI, c0J, ncJ, r0, r1, q0, q1;
             kid_range(ncol, n, I, &c0I, &ncI);
             kid_range(ncol, n, J, &c0J, &ncJ);
+            if (ncI <= 0 || ncJ <= 0) continue;
+            rank_block_part(J, I, n, ncJ, ncI, &r0, &r1, &q0, &q1);
             for (int which = 0; which < 2; which++) {
                 double *M = (double *)(which ? Hp : Mp);
-                for (int c = c0I; c < c0I + ncI; c++)
-                    for (int r = c0J; r < c0J + ncJ; r++) {
-                        double *dst = M + ((size_t)c * ldp + r) * words;
-                        const double *src = M + ((size_t)r * ldp + c) * words;
+                for (int c = 0; c < ncI; c++)
+                    for (int r = 0; r < ncJ; r++) {
+                        if (r >= r0 && r < r1 && c >= q0 && c < q1) continue; /* formed by device I */
+                        double *dst = M + ((size_t)(c0I + c) * ldp + c0J + r) * words;
+                        const double *src = M + ((size_t)(c0J + r) * ldp + c0I + c) * words;
                         dst[0] = src[0];
                         if (is_complex) dst[1] = -src[1];
                     }

@@ -126,11 +126,11 @@ extern "C" int chefsi_ipc_close(chefsi_ctx_t *ctx, void *dptr)
 }
 
 /* Hp and Mp are Hermitian, so every off-diagonal block pair (J, I) / (I, J) has to be formed only once.  Rank I forms
- * block (J, I) -- rows of rank J, its own columns -- when J is one of the floor((P - 1) / 2) ranks that follow it
- * cyclically, and for even P the lower rank of each antipodal pair forms that block: a balanced share of
+ * block (J, I) -- rows of rank J, its own columns -- when J is one of the ranks that follow it cyclically at a distance
+ * below P / 2, and for even P the two ranks of an antipodal pair share that block half and half: a balanced share of
  * (P + 1) / 2 instead of P blocks per rank (the diagonal one counts half: upper-triangle tiles, mirrored).  The host
- * mirrors the others after the all-gather (sparc_b200/band_parallel.py: assemble_hermitian).  The rule itself:
- * rank_forms_block, chefsi_internal.h. */
+ * mirrors the rest after the all-gather (sparc_b200/band_parallel.py: assemble_hermitian).  The rule itself:
+ * rank_block_part, chefsi_internal.h. */
 /* column block `rank` of Mp = Y^H Y and Hp = Y^H H Y: rows = all Ns columns of all ranks, columns = this rank's.
  * peerY[J]: device address of rank J's resident block in THIS process (chefsi_ipc_open, or chefsi_resident_ptr when
  * the ranks share a process); entry `rank` is ignored.  Hp_blk / Mp_blk: host, Ns x ncols[rank], column-major, ld = ldp.
@@ -177,12 +177,16 @@ static int rank_project_impl(chefsi_ctx_t *ctx, int is_complex, int nranks, int 
             double *Cblk = (which ? dHp : dMp) + pass;
             int c0J = 0;
             for (int J = 0; J < nranks; c0J += ncols[J], J++) {
-                if (ncols[J] <= 0 || (share && !rank_forms_block(J, rank, nranks))) continue;
+                if (ncols[J] <= 0) continue;
+                int r0 = 0, r1 = ncols[J], q0 = 0, q1 = ncI; /* the part of block (J, rank) this rank forms */
+                if (share) rank_block_part(J, rank, nranks, ncols[J], ncI, &r0, &r1, &q0, &q1);
+                if (r1 <= r0 || q1 <= q0) continue;
                 const double *A = J == rank ? Yi : (const double *)peerY[J]; /* another rank's block: IPC / peer memory */
                 /* the diagonal block is a Hermitian product of its own: upper-triangle tiles, mirrored (real part
                    symmetric, imaginary part antisymmetric) */
                 const int sym = (share && J == rank) ? (pass == 0 ? +1 : -1) : 0;
-                const int nl = launch_gemm_tn(ctx, A, ldv, B, ldv, ncols[J], ncI, K, 1.0, Cblk + (size_t)c0J * words, ncol, words, sym);
+                const int nl = launch_gemm_tn(ctx, A + (size_t)r0 * ldv, ldv, B + (size_t)q0 * ldv, ldv, r1 - r0, q1 - q0, K, 1.0,
+                                              Cblk + ((size_t)q0 * ncol + c0J + r0) * words, ncol, words, sym);
                 if (nl < 0) return 1;
                 ctx->stats.kernel_launches += nl;
             }
@@ -212,6 +216,12 @@ extern "C" int chefsi_rank_project_shared(chefsi_ctx_t *ctx, int is_complex, int
 extern "C" int chefsi_rank_forms_block(int J, int rank, int nranks)
 {
     return (nranks > 0 && J >= 0 && J < nranks && rank >= 0 && rank < nranks && rank_forms_block(J, rank, nranks)) ? 1 : 0;
+}
+
+/* the part of block (rows of rank J, columns of `rank`) that `rank` forms: local rows [r0, r1) x columns [c0, c1) */
+extern "C" void chefsi_rank_block_part(int J, int rank, int nranks, int ncJ, int ncI, int *r0, int *r1, int *c0, int *c1)
+{
+    rank_block_part(J, rank, nranks, ncJ, ncI, r0, r1, c0, c1);
 }
 
 /* complex data: T_I = i Y_I, which the other ranks read next to Y_I (Y Q = Y Q_r + (i Y) Q_i on the real views) */

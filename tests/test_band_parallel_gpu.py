@@ -63,7 +63,9 @@ def test_rank_products_two_contexts_one_process(port, complex_, split):
         # every Hermitian block pair formed by one rank only, the rest mirrored on the host after the "all-gather"
         from sparc_b200.band_parallel import assemble_hermitian
         shared = [rank_project(ctxs[r], complex_, r, split, peerY, share=True) for r in range(2)]
-        assert not shared[1][0][:, :split[0]].any() and not shared[1][1][:, :split[0]].any()   # rank 1 leaves block (0, 1) to rank 0
+        h0 = split[0] // 2   # two ranks share their one off-diagonal block: rank 1 forms rows [h0, nc0) of block (0, 1) only
+        assert not shared[1][0][:, :h0].any() and not shared[1][1][:, :h0].any()
+        assert not shared[0][0][h0:, split[0]:].any() and not shared[0][1][h0:, split[0]:].any()
         assert rel_fro(assemble_hermitian([sb[1] for sb in shared], split), Mp_want.T) < TOL
         assert rel_fro(assemble_hermitian([sb[0] for sb in shared], split), Hp_want.T) < TOL
         for c in ctxs:

@@ -59,31 +59,55 @@ def test_projector_tables_are_consistent():
     assert (pr.grid_pos >= 0).all() and (pr.grid_pos < g.Nd).all()
 
 
-def test_shared_hermitian_projection_blocks_cover_every_pair_once_and_mirror_back():
-    """Band-parallel projection with every Hermitian block pair formed once (sparc_b200/band_parallel.py, the rule of
-    chefsi_rank_forms_block in ranks.cu): each unordered pair of ranks has exactly one owner, the per-rank share is
-    balanced, and assemble_hermitian rebuilds the full matrix from the zero-padded column blocks."""
+def test_shared_hermitian_projection_parts_cover_every_element_pair_once_and_mirror_back():
+    """Band-parallel projection with every Hermitian element pair formed once (sparc_b200/band_parallel.py, the rule of
+    rank_block_part in chefsi_internal.h): of each mirrored pair of off-diagonal elements exactly one is formed, the
+    per-rank share is balanced (antipodal blocks of an even rank count are split half and half), and assemble_hermitian
+    rebuilds the full matrix from the zero-padded column blocks."""
+    import ctypes as C
     import numpy as np
-    from sparc_b200.band_parallel import assemble_hermitian, rank_forms_block
-    for P in range(1, 10):
+    from sparc_b200 import capi
+    from sparc_b200.band_parallel import assemble_hermitian, rank_block_part
+    lib = capi.load_library()
+    for P, ncJ, ncI in ((2, 5, 4), (4, 3, 3), (5, 2, 7), (8, 6, 5)):           # the host restatement == the library's rule
         for I in range(P):
-            assert rank_forms_block(I, I, P)
-            for J in range(I + 1, P):
-                assert rank_forms_block(J, I, P) != rank_forms_block(I, J, P)       # exactly one of the two ranks
-        share = [sum(rank_forms_block(J, I, P) for J in range(P)) for I in range(P)]
-        assert max(share) - min(share) <= 1 and sum(share) == P * (P + 1) // 2
+            for J in range(P):
+                out = [C.c_int() for _ in range(4)]
+                lib.chefsi_rank_block_part(J, I, P, ncJ, ncI, *[C.byref(v) for v in out])
+                got, want = tuple(v.value for v in out), rank_block_part(J, I, P, ncJ, ncI)
+                assert got == want or (max(got[1] - got[0], 0) * max(got[3] - got[2], 0) == 0 and (want[1] - want[0]) * (want[3] - want[2]) == 0)
     rng = np.random.default_rng(3)
-    for ncols, cplx in (([3, 2], False), ([2, 0, 3, 1], True), ([1, 1, 1, 1, 1], True), ([4, 3, 5], False)):
+    cases = [([3, 2], False), ([2, 0, 3, 1], True), ([1, 1, 1, 1, 1], True), ([4, 3, 5], False), ([5, 4, 4, 5, 3, 4, 5, 4], False),
+             ([7, 6], True), ([1, 1], False)]
+    for P in range(1, 10):
+        cases.append(([4] * P, False))
+    for ncols, cplx in cases:
         ns, P = sum(ncols), len(ncols)
+        off = np.concatenate([[0], np.cumsum(ncols)]).astype(int)
+        formed = np.zeros((ns, ns), dtype=int)                                  # [row, col]
+        work = []
+        for I in range(P):
+            w = 0.0
+            for J in range(P):
+                r0, r1, c0, c1 = rank_block_part(J, I, P, ncols[J], ncols[I])
+                if r1 > r0 and c1 > c0:
+                    formed[off[J] + r0:off[J] + r1, off[I] + c0:off[I] + c1] += 1
+                    w += (r1 - r0) * (c1 - c0) * (0.5 if J == I else 1.0)
+            work.append(w)
+        offdiag = ~np.zeros((ns, ns), dtype=bool)
+        for I in range(P):
+            offdiag[off[I]:off[I + 1], off[I]:off[I + 1]] = False
+        assert np.all((formed + formed.T)[offdiag] == 1)                        # exactly one of each mirrored pair
+        if len(set(ncols)) == 1 and P > 1:
+            assert max(work) - min(work) <= ncols[0] + 1e-9     # balanced share (an odd column count splits into h and h + 1 columns)
         A = rng.standard_normal((ns, ns)) + (1j * rng.standard_normal((ns, ns)) if cplx else 0)
         H = A + A.conj().T                                                      # H[row, col]
         G = np.ascontiguousarray(H.T)                                           # column-major: G[col, row]
-        off = np.concatenate([[0], np.cumsum(ncols)])
         blocks = []
         for I in range(P):
-            b = G[off[I]:off[I + 1]].copy()
+            b = np.zeros_like(G[off[I]:off[I + 1]])
             for J in range(P):
-                if not rank_forms_block(J, I, P):
-                    b[:, off[J]:off[J + 1]] = 0
+                r0, r1, c0, c1 = rank_block_part(J, I, P, ncols[J], ncols[I])
+                b[c0:c1, off[J] + r0:off[J] + r1] = G[off[I] + c0:off[I] + c1, off[J] + r0:off[J] + r1]
             blocks.append(b)
         assert np.array_equal(assemble_hermitian(blocks, ncols), G)
