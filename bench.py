@@ -196,6 +196,12 @@ def cpu_filter_rate(g, veff, proj, bounds, m, cols_per_core, reps=1, want_y=Fals
     kind = "reference" if reference_available() else "port"
     if kind == "port":
         build_port()
+    else:
+        # map the compiled reference into THIS process too (the forked workers inherit it): whoever records which native
+        # libraries the arm loaded looks at the parent, and the workers alone would leave that list empty
+        import ctypes
+        from oracle.bindings import REF_SO
+        ctypes.CDLL(REF_SO)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cores = max(1, min(cores, int(os.environ.get("CHEFSI_BENCH_MAX_PROCS", "64"))))
     ctx = mp.get_context("fork")
