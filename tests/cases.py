@@ -89,7 +89,7 @@ def load_golden(name):
 
 
 GOLDEN = ["orth_gamma", "orth_dirichlet_gamma", "si8lat_gamma", "orth_kpt", "si8lat_kpt", "type14_mixedbc_gamma",
-          "stream_gamma", "stream_kpt", "overlap_gamma", "overlap_kpt"]
+          "stream_gamma", "stream_kpt", "overlap_gamma", "overlap_kpt", "stream_tiles_gamma"]
 
 # dumps of real ChebyshevFiltering[_kpt] calls inside the reference's SCF runs of its own test systems (real psp8 Chi
 # tables, real Gamma, SCF Veff and bounds; tests/golden/make_sparc_dumps.py).  No Hx / c_shift entries.

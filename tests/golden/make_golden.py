@@ -39,7 +39,12 @@ CASES = {
     # own periodic images overlap along z, 9 alpha partials on one atom; sized for the TMA streaming kernels
     "overlap_gamma": ("overlap:stream", None, False, 6),
     "overlap_kpt": ("overlap:stream", None, True, 6),
+    # disjoint spheres on a multi-tile grid whose last tiles are shifted inwards (48 x 40: tiles of 32 overlap), spheres cut by
+    # tile edges and by the periodic faces: the streaming kernel with its fused projector chain, pinned to reference-made vectors
+    "stream_tiles_gamma": ("disjoint", (0, 0, 0), False, 5),
 }
+
+DISJOINT = dict(N=(48, 40, 14), frac=[[0.64, 0.78, 0.3], [0.2, 0.2, 0.8], [0.97, 0.03, 0.5]], rc=[2.3, 2.6, 2.0], nproj=[18, 13, 7])
 
 
 def main():
@@ -52,6 +57,13 @@ def main():
         if isinstance(ct, str) and ct.startswith("overlap:"):
             g, veff, proj, x = overlap_case(ct.split(":")[1], complex_=cplx, ncol=2, seed=3)
             assert sphere_overlap_count(proj, g.Nd) > 0
+            a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
+        elif ct == "disjoint":
+            g = P.make_grid(DISJOINT["N"], tuple(0.45 * n for n in DISJOINT["N"]), BC=BC)
+            veff = P.synthetic_veff(g)
+            proj = P.make_projectors(g, np.array(DISJOINT["frac"]), rc=DISJOINT["rc"], nproj=DISJOINT["nproj"], seed=5)
+            assert sphere_overlap_count(proj, g.Nd) == 0
+            x = P.random_columns(g.Nd, 2, seed=19)
             a, b, a0 = 0.5, 1.01 * g.max_eig_mhalf_lap() + 0.5, -0.6
         else:
             N, L = spec[4] if len(spec) > 4 else SMALL
