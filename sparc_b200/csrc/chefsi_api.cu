@@ -92,6 +92,7 @@ extern "C" int chefsi_create(chefsi_ctx_t **out, int device)
     if (getenv("CHEFSI_B200_GEMM_BIG_TILES")) ctx->gemm_big_tiles = atoi(getenv("CHEFSI_B200_GEMM_BIG_TILES"));
     if (getenv("CHEFSI_B200_GEMM_SYMMETRIC")) ctx->gemm_symmetric = atoi(getenv("CHEFSI_B200_GEMM_SYMMETRIC"));
     if (getenv("CHEFSI_B200_SMALL_BRICK")) ctx->small_brick = atoi(getenv("CHEFSI_B200_SMALL_BRICK"));
+    if (getenv("CHEFSI_B200_NLOC_SORT")) ctx->nloc_sort = atoi(getenv("CHEFSI_B200_NLOC_SORT"));
     if (getenv("CHEFSI_B200_TMA_L2PROMO")) ctx->tma_l2promo = atoi(getenv("CHEFSI_B200_TMA_L2PROMO")) & 3;
     *out = ctx;
     return 0;
@@ -332,7 +333,20 @@ extern "C" int chefsi_set_projectors(chefsi_ctx_t *ctx, const chefsi_nloc_t *nl)
             seg_pt0.push_back(pt0);
             seg_ndc.push_back(std::min(kSeg, nl->img_ndc[J] - pt0));
         }
-    const int n_seg = (int)seg_img.size();
+    int n_seg = (int)seg_img.size();
+    if (ctx->nloc_sort) {
+        /* longest first: the projector kernels run one CTA per (segment, 32 columns) in list order, ~15 waves of CTAs on the
+           bench workload whose periodic images come in all sizes; with the big ones in front the last wave is made of the
+           small ones.  (The alpha partials of an atom are then summed in this order: fixed, so still deterministic.) */
+        std::vector<int> order(n_seg);
+        for (int i = 0; i < n_seg; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return seg_ndc[x] > seg_ndc[y]; });
+        std::vector<int> t_img(n_seg), t_atom(n_seg), t_ndc(n_seg), t_pt0(n_seg);
+        for (int i = 0; i < n_seg; i++) {
+            t_img[i] = seg_img[order[i]]; t_atom[i] = seg_atom[order[i]]; t_ndc[i] = seg_ndc[order[i]]; t_pt0[i] = seg_pt0[order[i]];
+        }
+        seg_img.swap(t_img); seg_atom.swap(t_atom); seg_ndc.swap(t_ndc); seg_pt0.swap(t_pt0);
+    }
     d.n_img = n_seg;
     /* CSR atom -> segments */
     std::vector<int> off(nl->n_atom + 1, 0), lst(n_seg);

@@ -147,6 +147,7 @@ struct chefsi_ctx {
     void *d_alpha_sum = nullptr;           /* per-atom sums of the partials (only when nl.max_parts is large) */
     int alpha_cur = 0;
     size_t alpha_bytes = 0;
+    int nloc_sort = 1;                     /* projector CTAs in order of decreasing sphere-segment size (CHEFSI_B200_NLOC_SORT) */
     /* stats */
     chefsi_stats_t stats{};
     int profiling = 0;
